@@ -1,0 +1,121 @@
+"""ctypes binding of libfrz.so (the C ABI declared in include/frz.h).
+
+There is deliberately no fallback: if the CUDA library has not been built (``python -c "import __graft_entry__ as g;
+g.build()"`` or ``make -C free_range_zoo_b200/csrc``) importing an environment raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBRARY_PATH = os.path.join(_HERE, 'csrc', 'libfrz.so')
+
+MAX_AGENTS = 32
+MAX_EQUIPMENT = 8
+MAX_CAPACITIES = 8
+MAX_CELLS = 256
+MAX_NODES = 32
+MAX_NET_STATES = 16
+MAX_PASSENGERS = 64
+PAD = -100
+
+FAULT_NAMES = {
+    0x1: 'action[:, 0] is not a valid index into the agent\'s task list',
+    0x2: 'cybersecurity attack / movement target outside [0, num_nodes)',
+    0x4: 'a non-present cybersecurity agent acted while show_bad_actions=False',
+    0x8: 'rideshare passenger table overflow',
+}
+
+
+class Control(C.Structure):
+    _fields_ = [('seed', C.c_uint64), ('step', C.c_uint64), ('ctas_done', C.c_uint32), ('alive_acc', C.c_uint32),
+                ('alive', C.c_uint32), ('error_word', C.c_uint32)]
+
+
+# bits of WildfireParams.flags (include/frz.h)
+WF_FLAGS = dict(suppressant_decrease=0x0001, suppressant_refill=0x0002, tank_switch=0x0004, critical_error=0x0008,
+                degrade=0x0010, repair=0x0020, fire_increase=0x0040, fire_decrease=0x0080,
+                special_burnout_probability=0x0100, fire_fuel=0x0200)
+WF_BURNOUT_SCALED = 0x0400
+WF_LOCALIZE_PUTOUTS = 0x0800
+WF_SHOW_BAD_ACTIONS = 0x1000
+
+
+class WildfireParams(C.Structure):
+    _fields_ = [
+        ('height', C.c_int32), ('width', C.c_int32), ('num_agents', C.c_int32), ('num_fire_states', C.c_int32),
+        ('num_equipment_states', C.c_int32), ('num_capacities', C.c_int32), ('max_steps', C.c_int32),
+        ('flags', C.c_uint32), ('env_offset', C.c_int64),
+        ('p_increase', C.c_float), ('p_burnout', C.c_float), ('p_decrease', C.c_float), ('decrease_bonus', C.c_float),
+        ('p_random_ignition', C.c_float), ('spread_lut', C.c_float * 16),
+        ('p_suppressant_decrease', C.c_float), ('p_refill', C.c_float), ('p_repair', C.c_float),
+        ('p_degrade', C.c_float), ('p_critical', C.c_float), ('p_tank_switch', C.c_float),
+        ('capacity_cum', C.c_float * MAX_CAPACITIES), ('capacity_value', C.c_float * MAX_CAPACITIES),
+        ('equipment_capacity_bonus', C.c_float * MAX_EQUIPMENT), ('equipment_power_bonus', C.c_float * MAX_EQUIPMENT),
+        ('bad_attack_penalty', C.c_float), ('burnout_penalty', C.c_float), ('termination_reward', C.c_float),
+        ('termination_kappa', C.c_float),
+        ('agent_y', C.c_int32 * MAX_AGENTS), ('agent_x', C.c_int32 * MAX_AGENTS), ('agent_power', C.c_float * MAX_AGENTS),
+    ]
+
+
+_WF_POINTERS = ('fires', 'intensity', 'fuel', 'suppressants', 'capacity', 'equipment', 'init_fires', 'init_intensity',
+                'init_fuel', 'init_suppressants', 'init_capacity', 'init_equipment', 'actions', 'rewards',
+                'cumulative_rewards', 'terminated', 'truncated', 'num_moves', 'num_burnouts', 'burnouts', 'putouts',
+                'env_task_count', 'agent_task_count', 'action_mask', 'self_obs', 'task_obs', 'cell_reward',
+                'cell_ignition', 'range_mask', 'control', 'field_uniforms', 'agent_uniforms')
+
+
+class WildfireBuffers(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in _WF_POINTERS] + [('mask_stride', C.c_int32), ('mask_words', C.c_int32)]
+
+
+_lib = None
+
+
+def library() -> C.CDLL:
+    """Load libfrz.so once; raise (never fall back) when it is missing or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBRARY_PATH):
+        raise RuntimeError(f'{LIBRARY_PATH} is missing: the B200 engine has no CPU fallback. '
+                           'Build it with `python -c "import __graft_entry__ as g; g.build()"`.')
+    lib = C.CDLL(LIBRARY_PATH)
+    lib.frz_version.restype = C.c_int
+    lib.frz_last_error.restype = C.c_char_p
+    lib.frz_control_init.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    for name in ('frz_wildfire_step', 'frz_wildfire_refresh'):
+        getattr(lib, name).argtypes = [C.POINTER(WildfireParams), C.POINTER(WildfireBuffers), C.c_int32, C.c_void_p]
+    lib.frz_wildfire_reset.argtypes = [C.POINTER(WildfireParams), C.POINTER(WildfireBuffers), C.c_int32, C.c_void_p,
+                                       C.c_void_p]
+    lib.frz_wildfire_sample_actions.argtypes = [C.POINTER(WildfireParams), C.POINTER(WildfireBuffers), C.c_int32,
+                                                C.c_uint64, C.c_void_p]
+    if lib.frz_version() != 1:
+        raise RuntimeError(f'libfrz.so ABI version {lib.frz_version()} != 1; rebuild the library')
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = '') -> None:
+    if status != 0:
+        message = library().frz_last_error().decode()
+        raise RuntimeError(f'libfrz {what} failed (status {status}): {message}')
+
+
+def stream_handle(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def pointer(tensor: torch.Tensor | None) -> int | None:
+    return None if tensor is None else tensor.data_ptr()
+
+
+def exported_symbols():
+    """Every extern "C" symbol include/frz.h declares (used by the CPU-side ABI test)."""
+    import re
+    header = os.path.join(os.path.dirname(_HERE), 'include', 'frz.h')
+    text = open(header).read()
+    return sorted(set(re.findall(r'\b(frz_[a-z_]+)\s*\(', text)))

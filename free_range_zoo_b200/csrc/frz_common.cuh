@@ -1,0 +1,102 @@
+// Shared device helpers for the fused step kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "frz.h"
+
+namespace frz {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs
+
+// ---------------------------------------------------------------------------------------------- host side
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+inline int persistent_grid(int work_ctas, int ctas_per_sm) {
+  const int cap = kSmCount * ctas_per_sm;
+  return work_ctas < cap ? (work_ctas < 1 ? 1 : work_ctas) : cap;
+}
+
+// ---------------------------------------------------------------------------------------------- Philox4x32-10
+
+struct Philox {
+  uint32_t key0, key1;
+  __device__ __forceinline__ Philox(uint64_t seed) : key0(uint32_t(seed)), key1(uint32_t(seed >> 32)) {}
+
+  // Counter-based: (env, step, stream) -> 4 x 32 random bits.  Trajectories depend only on the global environment
+  // index, the per-environment step counter and the event stream, never on the launch geometry or GPU count.
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t k0 = key0, k1 = key1;
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      c0 = hi1 ^ c1 ^ k0;
+      c1 = lo1;
+      c2 = hi0 ^ c3 ^ k1;
+      c3 = lo0;
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+
+// 24 random bits -> uniform in [0, 1) on the fp32 grid k * 2^-24 (same support as torch.rand's fp32 output)
+__device__ __forceinline__ float u01(uint32_t bits) { return float(bits >> 8) * 5.9604644775390625e-08f; }
+
+// position of the k-th (0-based) set bit of w; caller guarantees k < popc(w)
+__device__ __forceinline__ int select_bit(uint32_t w, int k) {
+  int pos = 0;
+#pragma unroll
+  for (int span = 16; span >= 1; span >>= 1) {
+    const int below = __popc(w & ((1u << span) - 1u));
+    if (k >= below) {
+      k -= below;
+      w >>= span;
+      pos += span;
+    }
+  }
+  return pos;
+}
+
+// ---------------------------------------------------------------------------------------------- launch epilogue
+
+// Called by every CTA once, after its last environment.  `alive_bits`: bit0 = this CTA saw an env that is still not
+// terminated, bit1 = one that is still not truncated.  The last CTA to arrive publishes the flags for the next
+// launch and advances the step counter -- every CTA read control->step / control->alive at its start, so there is
+// no reader left when they change.
+__device__ __forceinline__ void finish_launch(FrzControl* control, unsigned alive_bits, unsigned fault_bits,
+                                              bool advance) {
+  __shared__ unsigned s_alive, s_fault;
+  if (threadIdx.x == 0) {
+    s_alive = 0;
+    s_fault = 0;
+  }
+  __syncthreads();
+  if (alive_bits) atomicOr(&s_alive, alive_bits);
+  if (fault_bits) atomicOr(&s_fault, fault_bits);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_alive) atomicOr(&control->alive_acc, s_alive);
+    if (s_fault) atomicOr(&control->error_word, s_fault);
+    __threadfence();
+    const unsigned arrived = atomicAdd(&control->ctas_done, 1u) + 1u;
+    if (arrived == gridDim.x) {
+      __threadfence();
+      if (advance) {
+        control->alive = atomicExch(&control->alive_acc, 0u);
+        control->step += 1;
+      } else {
+        control->alive_acc = 0u;
+      }
+      control->ctas_done = 0u;
+    }
+  }
+}
+
+}  // namespace frz

@@ -1,0 +1,635 @@
+// Fused wildfire environment step for sm_100a.
+//
+// One launch = for every environment: action decode -> suppressant decrease -> equipment -> refill -> capacity ->
+// fire increase -> fire decrease -> fire spread -> rewards -> termination -> num_moves / truncation -> reward
+// accumulation -> observations -> task counts -> action masks.  It replaces, with identical results, the reference's
+//   envs/wildfire/env/wildfire.py:400-717 (step_environment, update_actions, update_observations),
+//   envs/wildfire/env/transitions/*.py (seven nn.Module transitions) and utils/env.py:215-237 (AEC bookkeeping).
+//
+// Mapping: a group of G lanes (8, 16 or 32) owns one environment.  Lane l of the group owns grid cells
+// l, l+G, l+2G, ... (CPL cells per lane) AND agent l.  Everything that couples cells or agents inside an environment
+// is a warp primitive: lit / burning / available sets are ballots (bit c = cell c, i.e. row-major nonzero() order, so
+// an env-local task index is a popcount), neighbour fire spread is a bit test on the burning ballot, the agents'
+// attacks reach the cells through width-G shuffles in agent order (fp32 sums associate exactly as the reference's
+// per-agent loop), per-environment reductions are shuffles / popcounts.  All global traffic is issued as contiguous
+// per-environment rows ([B, H*W] / [B, A] layouts) so a warp's loads and stores coalesce.
+#include <math_constants.h>
+
+#include "frz_common.cuh"
+
+namespace frz {
+namespace {
+
+constexpr int kThreads = 256;
+enum Mode { kStep = 0, kRefresh = 1 };
+
+template <int NW>
+__device__ __forceinline__ uint32_t word_at(const uint32_t (&words)[NW], int index) {
+  uint32_t w = words[0];
+#pragma unroll
+  for (int i = 1; i < NW; ++i) w = (index == i) ? words[i] : w;
+  return w;
+}
+
+template <int NW>
+__device__ __forceinline__ bool bit_at(const uint32_t (&words)[NW], int cell) {
+  return (word_at<NW>(words, cell >> 5) >> (cell & 31)) & 1u;
+}
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int offset = G / 2; offset >= 1; offset >>= 1) v += __shfl_xor_sync(kFullMask, v, offset, G);
+  return v;
+}
+
+template <int G>
+__device__ __forceinline__ int group_sum(int v) {
+#pragma unroll
+  for (int offset = G / 2; offset >= 1; offset >>= 1) v += __shfl_xor_sync(kFullMask, v, offset, G);
+  return v;
+}
+
+template <int G, int CPL>
+__global__ void __launch_bounds__(kThreads)
+wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_constant__ FrzWildfireBuffers io,
+                     const int B, const int mode) {
+  constexpr int kGroupsPerWarp = 32 / G;
+  constexpr int NW = (G * CPL + 31) / 32;
+  static_assert(G == 32 || CPL == 1, "sub-warp groups hold one cell per lane");
+  extern __shared__ __align__(16) unsigned char smem[];
+
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % G;
+  const int group_base = lane - sub;
+  const uint32_t group_mask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+  const uint32_t lanes_below = (1u << sub) - 1u;
+  const int HW = p.height * p.width;
+  const int A = p.num_agents;
+  const int E = p.num_equipment_states;
+  const uint32_t flags = p.flags;
+  const int groups_per_cta = (kThreads / 32) * kGroupsPerWarp;
+  const int group_in_cta = (threadIdx.x >> 5) * kGroupsPerWarp + lane / G;
+  const bool show_bad = flags & FRZ_WF_SHOW_BAD_ACTIONS;
+  const bool use_fuel = flags & FRZ_WF_FIRE_FUEL;
+
+  FrzControl* control = io.control;
+  const uint64_t step = control->step;
+  const uint32_t alive_prev = control->alive;
+  const Philox philox(control->seed);
+  // BatchedAECEnv.step returns before doing anything once every env is terminated, or every env is truncated
+  // (utils/env.py:212); the flags were published by the previous launch.
+  const bool skip = (mode == kStep) && ((alive_prev & 3u) != 3u);
+
+  // per-lane constants: the cells and the agent this lane owns are the same for every environment it processes
+  int cell[CPL], cy[CPL], cx[CPL], ignition[CPL];
+  float creward[CPL];
+  bool cvalid[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    cell[i] = i * G + sub;
+    cvalid[i] = cell[i] < HW;
+    cy[i] = cell[i] / p.width;
+    cx[i] = cell[i] - cy[i] * p.width;
+    creward[i] = cvalid[i] ? io.cell_reward[cell[i]] : 0.f;
+    ignition[i] = cvalid[i] ? io.cell_ignition[cell[i]] : 0;
+  }
+  const bool is_agent = sub < A;
+  const float base_power = is_agent ? p.agent_power[sub] : 0.f;
+  const float agent_yf = is_agent ? float(p.agent_y[sub]) : 0.f;
+  const float agent_xf = is_agent ? float(p.agent_x[sub]) : 0.f;
+
+  const int mask_stride = io.mask_stride;
+  const int region_words = (A * mask_stride) >> 2;
+  uint32_t* region = reinterpret_cast<uint32_t*>(smem) + size_t(group_in_cta) * region_words;
+  unsigned char* region_bytes = reinterpret_cast<unsigned char*>(region);
+
+  unsigned alive_bits = 0, faults = 0;
+
+  if (!skip) {
+    for (int env0 = blockIdx.x * groups_per_cta; env0 < B; env0 += gridDim.x * groups_per_cta) {
+      const int env = env0 + group_in_cta;
+      const bool valid = env < B;
+      const int e = valid ? env : B - 1;
+      const size_t cell_row = size_t(e) * HW;
+      const size_t agent_row = size_t(e) * A;
+
+      // ------------------------------------------------------------------ load
+      int fires[CPL], inten[CPL], fuel[CPL];
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        fires[i] = cvalid[i] ? io.fires[cell_row + cell[i]] : 0;
+        inten[i] = cvalid[i] ? io.intensity[cell_row + cell[i]] : 0;
+        fuel[i] = cvalid[i] ? io.fuel[cell_row + cell[i]] : 0;
+      }
+      float supp = 0.f, cap = 0.f;
+      int equip = 0;
+      if (is_agent) {
+        supp = io.suppressants[agent_row + sub];
+        cap = io.capacity[agent_row + sub];
+        equip = min(max(io.equipment[agent_row + sub], 0), E - 1);
+      }
+
+      uint32_t litw[NW];
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const uint32_t ballot = __ballot_sync(kFullMask, fires[i] > 0);
+        if (G == 32) litw[i] = ballot; else litw[0] = (ballot >> group_base) & group_mask;
+      }
+
+      float reward = 0.f, cumulative = 0.f;
+      int moves = 0, total_burnouts = 0, n_burned = 0, n_putout = 0;
+      bool terminated = false, truncated = false;
+
+      if (mode == kStep) {
+        // ---------------------------------------------------------------- action decode (wildfire.py:412-486)
+        int act_k = 0, act_id = -1;
+        if (is_agent) {
+          const int2 act = reinterpret_cast<const int2*>(io.actions)[agent_row + sub];
+          act_k = act.x;
+          act_id = act.y;
+          cumulative = io.cumulative_rewards[agent_row + sub];
+        }
+        moves = io.num_moves[e];
+        total_burnouts = io.num_burnouts[e];
+        const bool was_terminated = io.terminated[e] != 0;
+
+        // tasks this agent could fight at the start of the step == what update_actions published after the previous
+        // step (wildfire.py:587-666): lit & in Chebyshev range (equipment bonus folded in) & has suppressant
+        uint32_t availw[NW];
+        {
+          const uint32_t* rm = io.range_mask + (size_t(is_agent ? sub : 0) * E + equip) * io.mask_words;
+#pragma unroll
+          for (int w = 0; w < NW; ++w)
+            availw[w] = (is_agent && supp > 0.f && w < io.mask_words) ? (litw[w] & rm[w]) : 0u;
+        }
+        const bool refill = is_agent && act_id == -1;  // wildfire.py:431
+        int target = -1;
+        bool bad = false;
+        if (is_agent && !refill) {
+          int k = act_k, found = -1;
+          if (k >= 0) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+              const uint32_t choices = show_bad ? litw[w] : availw[w];
+              const int count = __popc(choices);
+              if (found < 0) {
+                if (k < count) found = w * 32 + select_bit(choices, k); else k -= count;
+              }
+            }
+          }
+          if (found < 0) faults |= FRZ_FAULT_BAD_TASK_INDEX;
+          else if (show_bad && !bit_at<NW>(availw, found)) bad = true;  // wildfire.py:464-477
+          else target = found;
+        }
+        const bool user = target >= 0;
+        const float power = base_power + p.equipment_power_bonus[equip];  // wildfire.py:455-457
+
+        // attack power per cell, accumulated in agent order (wildfire.py:470)
+        float attack[CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) attack[i] = 0.f;
+        for (int a = 0; a < A; ++a) {
+          const int t = __shfl_sync(kFullMask, target, a, G);
+          const float pw = __shfl_sync(kFullMask, power, a, G);
+#pragma unroll
+          for (int i = 0; i < CPL; ++i)
+            if (t == cell[i]) attack[i] = __fadd_rn(attack[i], pw);
+        }
+
+        // ---------------------------------------------------------------- randomness
+        const uint32_t env_lo = uint32_t(p.env_offset + e), env_hi = uint32_t(uint64_t(p.env_offset + e) >> 32);
+        float ua[5];
+        if (io.agent_uniforms != nullptr) {
+#pragma unroll
+          for (int ev = 0; ev < 5; ++ev)
+            ua[ev] = is_agent ? io.agent_uniforms[(size_t(ev) * B + e) * A + sub] : 1.f;
+        } else {
+          const uint4 r = philox(env_lo, uint32_t(step), 0x80000000u | uint32_t(sub), uint32_t(step >> 32) ^ env_hi);
+          ua[0] = u01(r.x);
+          ua[1] = u01(r.y);
+          ua[2] = u01(r.z);
+          ua[3] = u01(r.w);
+          ua[4] = u01(((r.x & 0xffu) << 24) | ((r.y & 0xffu) << 16) | ((r.z & 0xffu) << 8));
+        }
+
+        // ---------------------------------------------------------------- agent transitions
+        // suppressant_decrease.py:34-63
+        const bool decrease = user && (!(flags & FRZ_WF_STOCH_SUPPRESSANT_DECREASE) || ua[0] < p.p_suppressant_decrease);
+        supp = fmaxf(decrease ? __fadd_rn(supp, -1.f) : supp, 0.f);
+        // equipment.py:42-77 -- masks from the pre-update state, one uniform for all three tests
+        {
+          const bool pristine = equip == E - 1, damaged = equip == 0;
+          const bool wearable = pristine || !damaged;  // pristine | intermediate
+          const bool repairs = damaged && (!(flags & FRZ_WF_STOCH_REPAIR) || ua[1] < p.p_repair);
+          const bool critical = (flags & FRZ_WF_CRITICAL_ERROR) && pristine && ua[1] < p.p_critical;
+          const bool degrades = wearable && (!(flags & FRZ_WF_STOCH_DEGRADE) || ua[1] < p.p_degrade) && !critical;
+          if (repairs) equip = E - 1;
+          if (critical) equip = 0;
+          if (degrades) equip -= 1;
+        }
+        // suppressant_refill.py:43-74 -- bonus of the equipment state AFTER its transition
+        const bool increased = refill && (!(flags & FRZ_WF_STOCH_REFILL) || ua[2] < p.p_refill);
+        if (increased) supp = __fadd_rn(cap, p.equipment_capacity_bonus[max(equip, 0)]);
+        // capacity.py:39-66 -- bucketize(right=False): first i with r <= cum[i]
+        {
+          int pick = p.num_capacities - 1;
+          for (int i = p.num_capacities - 1; i >= 0; --i)
+            if (ua[3] <= p.capacity_cum[i]) pick = i;
+          const bool switches = increased && (!(flags & FRZ_WF_STOCH_TANK_SWITCH) || ua[4] < p.p_tank_switch);
+          const float extra = __fadd_rn(supp, -cap);
+          if (switches) {
+            cap = p.capacity_value[pick];
+            supp = __fadd_rn(cap, extra);
+          }
+        }
+
+        // ---------------------------------------------------------------- fire increase + decrease per cell
+        const int burned_state = p.num_fire_states - 1, almost_state = p.num_fire_states - 2;
+        bool burned[CPL], putout[CPL];
+        float uf2[CPL];
+        uint32_t burnw[NW];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          float u0, u1;
+          if (io.field_uniforms != nullptr) {
+            const size_t at = size_t(e) * HW + cell[i], plane = size_t(B) * HW;
+            u0 = cvalid[i] ? io.field_uniforms[at] : 1.f;
+            u1 = cvalid[i] ? io.field_uniforms[plane + at] : 1.f;
+            uf2[i] = cvalid[i] ? io.field_uniforms[2 * plane + at] : 1.f;
+          } else {
+            const uint4 r = philox(env_lo, uint32_t(step), uint32_t(cell[i]), uint32_t(step >> 32) ^ env_hi);
+            u0 = u01(r.x);
+            u1 = u01(r.y);
+            uf2[i] = u01(r.z);
+          }
+          int f = fires[i], it = inten[i], fu = fuel[i];
+          // fire_increase.py:43-95
+          float diff = __fadd_rn(f >= 0 ? float(f) : 0.f, -attack[i]);
+          bool burning = f > 0 && it > 0;
+          const bool unmet = diff > 0.f && burning;
+          const bool almost = unmet && it == almost_state;
+          float prob = 0.f;
+          if (unmet && !almost) prob = (flags & FRZ_WF_STOCH_FIRE_INCREASE) ? p.p_increase : 1.f;
+          if (almost) prob = (flags & FRZ_WF_SPECIAL_BURNOUT) ? p.p_burnout : p.p_increase;
+          prob = fminf(fmaxf(prob, 0.f), 1.f);
+          const bool grow = u0 < prob;
+          if (grow) it += 1;
+          burned[i] = grow && it >= burned_state;
+          if (burned[i]) {
+            f = -f;
+            fu = max(fu - 1, 0);
+          }
+          // fire_decrease.py:36-80 on the post-increase state; mul and add rounded separately like the reference
+          diff = __fadd_rn(f >= 0 ? float(f) : 0.f, -attack[i]);
+          burning = f > 0 && it > 0;
+          const bool met = diff <= 0.f && burning;
+          prob = 0.f;
+          if (met)
+            prob = (flags & FRZ_WF_STOCH_FIRE_DECREASE) ? __fadd_rn(p.p_decrease, __fmul_rn(-diff, p.decrease_bonus)) : 1.f;
+          prob = fminf(fmaxf(prob, 0.f), 1.f);
+          const bool shrink = u1 < prob;
+          if (shrink) it -= 1;
+          putout[i] = shrink && it <= 0;
+          if (putout[i]) {
+            f = -f;
+            fu -= 1;
+          }
+          fires[i] = f;
+          inten[i] = it;
+          fuel[i] = fu;
+          const uint32_t ballot = __ballot_sync(kFullMask, f > 0 && it > 0);
+          if (G == 32) burnw[i] = ballot; else burnw[0] = (ballot >> group_base) & group_mask;
+        }
+
+        // ---------------------------------------------------------------- fire spread (fire_spreads.py:33-59)
+        float my_put_reward = 0.f, my_burn_reward = 0.f;
+        int my_fuel = 0;
+        uint32_t putw[NW];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          int f = fires[i], it = inten[i];
+          if (cvalid[i]) {
+            int pattern = 0;
+            if (cy[i] > 0 && bit_at<NW>(burnw, cell[i] - p.width)) pattern |= 1;
+            if (cx[i] > 0 && bit_at<NW>(burnw, cell[i] - 1)) pattern |= 2;
+            if (cx[i] < p.width - 1 && bit_at<NW>(burnw, cell[i] + 1)) pattern |= 4;
+            if (cy[i] < p.height - 1 && bit_at<NW>(burnw, cell[i] + p.width)) pattern |= 8;
+            const bool unlit = f < 0 && it == 0 && (!use_fuel || fuel[i] > 0);
+            const float prob = unlit ? __fadd_rn(p.spread_lut[pattern], p.p_random_ignition) : 0.f;
+            if (uf2[i] < prob) {
+              f = -f;
+              it = ignition[i];
+            }
+          }
+          fires[i] = f;
+          inten[i] = it;
+          if (putout[i]) my_put_reward += creward[i];
+          if (burned[i]) my_burn_reward += creward[i];
+          my_fuel += fuel[i];
+          const uint32_t lit_ballot = __ballot_sync(kFullMask, f > 0);
+          const uint32_t put_ballot = __ballot_sync(kFullMask, putout[i]);
+          const uint32_t burn_ballot = __ballot_sync(kFullMask, burned[i]);
+          if (G == 32) {
+            litw[i] = lit_ballot;
+            putw[i] = put_ballot;
+          } else {
+            litw[0] = (lit_ballot >> group_base) & group_mask;
+            putw[0] = (put_ballot >> group_base) & group_mask;
+          }
+          n_putout += __popc((put_ballot >> group_base) & group_mask);
+          n_burned += __popc((burn_ballot >> group_base) & group_mask);
+        }
+
+        // ---------------------------------------------------------------- rewards + termination (wildfire.py:534-582)
+        const float put_total = group_sum<G>(my_put_reward);
+        const float burn_total = group_sum<G>(my_burn_reward);
+        const float penalty_total =
+            (flags & FRZ_WF_BURNOUT_SCALED) ? -burn_total : __fmul_rn(p.burnout_penalty, float(n_burned));
+        uint32_t any_lit = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) any_lit |= litw[w];
+        bool dead = any_lit == 0;
+        if (use_fuel) dead = dead && group_sum<G>(my_fuel) <= 0;
+        if (dead) {  // wildfire.py:570
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) fires[i] = 0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) litw[w] = 0;
+        }
+        const bool newly = !was_terminated && dead;
+        terminated = was_terminated || dead;
+        reward = bad ? p.bad_attack_penalty : 0.f;
+        float gain = put_total;
+        if (flags & FRZ_WF_LOCALIZE_PUTOUTS)
+          gain = (target >= 0 && bit_at<NW>(putw, target)) ? io.cell_reward[target] : 0.f;
+        reward = __fadd_rn(reward, __fadd_rn(gain, penalty_total));
+        if (newly) {
+          const float penalty = __fmul_rn(p.termination_kappa, logf(__fadd_rn(float(total_burnouts), 1.f)));
+          reward = __fadd_rn(reward, fmaxf(__fadd_rn(p.termination_reward, -penalty), 0.f));
+        }
+        total_burnouts += n_burned;
+        // utils/env.py:228-235
+        moves += 1;
+        truncated = moves >= p.max_steps;
+        cumulative = __fadd_rn(cumulative, reward);
+        if (valid) alive_bits |= (terminated ? 0u : 1u) | (truncated ? 0u : 2u);
+      }
+
+      // ------------------------------------------------------------------ update_actions / update_observations
+      int lit_before[CPL];  // env-local task index of this lane's cell if it is lit
+      int n_lit = 0;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const uint32_t word = (G == 32) ? litw[i] : litw[0];
+        lit_before[i] = n_lit + __popc(word & lanes_below);
+        n_lit += __popc(word);
+      }
+      uint32_t availw[NW];
+      int n_avail = 0;
+      {
+        const uint32_t* rm = io.range_mask + (size_t(is_agent ? sub : 0) * E + max(equip, 0)) * io.mask_words;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          availw[w] = (is_agent && supp > 0.f && w < io.mask_words) ? (litw[w] & rm[w]) : 0u;
+          n_avail += __popc(availw[w]);
+        }
+      }
+
+      // action mask [A, mask_stride] bytes, indexed by env-local task: staged in shared memory so that the global
+      // store is one contiguous, word-coalesced row per environment
+      for (int j = sub; j < region_words; j += G) region[j] = 0u;
+      __syncwarp();
+      for (int a = 0; a < A; ++a) {
+        uint32_t aw[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) aw[w] = __shfl_sync(kFullMask, availw[w], a, G);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          const uint32_t word = (G == 32) ? aw[i] : aw[0];
+          if ((word >> sub) & 1u) region_bytes[a * mask_stride + lit_before[i]] = 1;
+        }
+      }
+      __syncwarp();
+
+      if (valid) {
+        uint32_t* mask_row = reinterpret_cast<uint32_t*>(io.action_mask + size_t(env) * A * mask_stride);
+        for (int j = sub; j < region_words; j += G) mask_row[j] = region[j];
+
+        int4* task_row = reinterpret_cast<int4*>(io.task_obs) + cell_row;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          const uint32_t word = (G == 32) ? litw[i] : litw[0];
+          if ((word >> sub) & 1u) task_row[lit_before[i]] = make_int4(cy[i], cx[i], fires[i], inten[i]);
+          const int slot = i * G + sub;  // padding rows
+          if (slot >= n_lit && slot < HW) task_row[slot] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
+        }
+        if (is_agent) {
+          io.agent_task_count[agent_row + sub] = n_avail;
+          reinterpret_cast<float4*>(io.self_obs)[agent_row + sub] = make_float4(agent_yf, agent_xf, base_power, supp);
+        }
+        if (sub == 0) io.env_task_count[env] = n_lit;
+
+        if (mode == kStep) {
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) {
+            if (cvalid[i]) {
+              io.fires[cell_row + cell[i]] = fires[i];
+              io.intensity[cell_row + cell[i]] = inten[i];
+              io.fuel[cell_row + cell[i]] = fuel[i];
+            }
+          }
+          if (is_agent) {
+            io.suppressants[agent_row + sub] = supp;
+            io.capacity[agent_row + sub] = cap;
+            io.equipment[agent_row + sub] = equip;
+            io.rewards[agent_row + sub] = reward;
+            io.cumulative_rewards[agent_row + sub] = cumulative;
+          }
+          if (sub == 0) {
+            io.terminated[env] = terminated;
+            io.truncated[env] = truncated;
+            io.num_moves[env] = moves;
+            io.num_burnouts[env] = total_burnouts;
+            io.burnouts[env] = n_burned;
+            io.putouts[env] = n_putout;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  finish_launch(control, alive_bits, faults, mode == kStep && !skip);
+}
+
+// ------------------------------------------------------------------------------------------------ reset / sampling
+
+__global__ void wildfire_restore_kernel(const FrzWildfireParams p, const FrzWildfireBuffers io, const int B,
+                                        const uint8_t* __restrict__ env_mask) {
+  const int HW = p.height * p.width, A = p.num_agents;
+  const int per_env = HW > A ? HW : A;
+  const size_t total = size_t(B) * per_env;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int env = int(i / per_env), j = int(i % per_env);
+    if (env_mask != nullptr && !env_mask[env]) continue;
+    if (j < HW) {
+      const size_t at = size_t(env) * HW + j;
+      io.fires[at] = io.init_fires[at];
+      io.intensity[at] = io.init_intensity[at];
+      io.fuel[at] = io.init_fuel[at];
+    }
+    if (j < A) {
+      const size_t at = size_t(env) * A + j;
+      io.suppressants[at] = io.init_suppressants[at];
+      io.capacity[at] = io.init_capacity[at];
+      io.equipment[at] = io.init_equipment[at];
+      io.rewards[at] = 0.f;
+      io.cumulative_rewards[at] = 0.f;
+    }
+    if (j == 0) {
+      io.terminated[env] = 0;
+      io.truncated[env] = 0;
+      io.num_moves[env] = 0;
+      io.num_burnouts[env] = 0;
+      io.burnouts[env] = 0;
+      io.putouts[env] = 0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) io.control->alive = 3u;
+}
+
+__global__ void wildfire_sample_kernel(const FrzWildfireParams p, const FrzWildfireBuffers io, const int B,
+                                       const uint64_t sampler_seed) {
+  const int A = p.num_agents;
+  const Philox philox(sampler_seed);
+  const uint64_t step = io.control->step;
+  const bool show_bad = p.flags & FRZ_WF_SHOW_BAD_ACTIONS;
+  const int total = B * A;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int env = i / A, agent = i - env * A;
+    const int n = show_bad ? io.env_task_count[env] : io.agent_task_count[i];
+    const uint64_t genv = uint64_t(p.env_offset + env);
+    const uint4 r = philox(uint32_t(genv), uint32_t(step), 0xC0000000u | uint32_t(agent), uint32_t(step >> 32) ^ uint32_t(genv >> 32));
+    const int k = min(int(u01(r.x) * float(n + 1)), n);
+    reinterpret_cast<int2*>(const_cast<int32_t*>(io.actions))[i] = make_int2(k, k == n ? -1 : 0);
+  }
+}
+
+struct Geometry {
+  int group, cells_per_lane;
+};
+
+bool pick_geometry(const FrzWildfireParams& p, Geometry* g) {
+  const int HW = p.height * p.width, A = p.num_agents;
+  if (A < 1 || A > FRZ_MAX_AGENTS || HW < 1 || HW > FRZ_MAX_CELLS) return false;
+  if (HW <= 8 && A <= 8) *g = {8, 1};
+  else if (HW <= 16 && A <= 16) *g = {16, 1};
+  else if (HW <= 32) *g = {32, 1};
+  else if (HW <= 64) *g = {32, 2};
+  else if (HW <= 128) *g = {32, 4};
+  else *g = {32, 8};
+  return true;
+}
+
+template <int G, int CPL>
+int launch_step(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B, int mode, cudaStream_t stream) {
+  static int ctas_per_sm = 0, sm_count = 0;
+  static size_t cached_smem = ~size_t(0);
+  const int groups_per_cta = (kThreads / 32) * (32 / G);
+  const size_t smem = size_t(groups_per_cta) * p.num_agents * io.mask_stride;
+  auto kernel = wildfire_step_kernel<G, CPL>;
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+      return check_launch("wildfire smem attribute");
+  }
+  if (sm_count == 0) {
+    int device = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+  }
+  if (smem != cached_smem) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kThreads, smem);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    cached_smem = smem;
+  }
+  const int work = (B + groups_per_cta - 1) / groups_per_cta;
+  const int cap = sm_count * ctas_per_sm;
+  const int grid = work < cap ? work : cap;
+  kernel<<<grid, kThreads, smem, stream>>>(p, io, B, mode);
+  return check_launch("wildfire_step_kernel");
+}
+
+int dispatch(const FrzWildfireParams* p, const FrzWildfireBuffers* io, int B, int mode, void* stream) {
+  if (p == nullptr || io == nullptr || io->control == nullptr || io->fires == nullptr) {
+    set_error("frz_wildfire: NULL params / buffers");
+    return FRZ_ERR_NULL;
+  }
+  Geometry g;
+  if (B <= 0 || !pick_geometry(*p, &g) || p->num_equipment_states < 1 || p->num_equipment_states > FRZ_MAX_EQUIPMENT ||
+      p->num_capacities < 1 || p->num_capacities > FRZ_MAX_CAPACITIES || io->mask_stride % 4 != 0 ||
+      io->mask_stride < p->height * p->width) {
+    set_error("frz_wildfire: unsupported shape B=%d H=%d W=%d A=%d E=%d", B, p->height, p->width, p->num_agents,
+              p->num_equipment_states);
+    return FRZ_ERR_SHAPE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (g.group == 8) return launch_step<8, 1>(*p, *io, B, mode, s);
+  if (g.group == 16) return launch_step<16, 1>(*p, *io, B, mode, s);
+  switch (g.cells_per_lane) {
+    case 1: return launch_step<32, 1>(*p, *io, B, mode, s);
+    case 2: return launch_step<32, 2>(*p, *io, B, mode, s);
+    case 4: return launch_step<32, 4>(*p, *io, B, mode, s);
+    default: return launch_step<32, 8>(*p, *io, B, mode, s);
+  }
+}
+
+}  // namespace
+}  // namespace frz
+
+extern "C" {
+
+int frz_wildfire_step(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs, void* stream) {
+  if (io != nullptr && io->actions == nullptr) {
+    frz::set_error("frz_wildfire_step: actions is NULL");
+    return FRZ_ERR_NULL;
+  }
+  return frz::dispatch(params, io, parallel_envs, frz::kStep, stream);
+}
+
+int frz_wildfire_refresh(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
+                         void* stream) {
+  return frz::dispatch(params, io, parallel_envs, frz::kRefresh, stream);
+}
+
+int frz_wildfire_reset(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
+                       const uint8_t* env_mask, void* stream) {
+  if (params == nullptr || io == nullptr || io->init_fires == nullptr || io->control == nullptr) {
+    frz::set_error("frz_wildfire_reset: NULL params / buffers");
+    return FRZ_ERR_NULL;
+  }
+  if (parallel_envs <= 0) {
+    frz::set_error("frz_wildfire_reset: parallel_envs=%d", parallel_envs);
+    return FRZ_ERR_SHAPE;
+  }
+  const int HW = params->height * params->width;
+  const size_t total = size_t(parallel_envs) * (HW > params->num_agents ? HW : params->num_agents);
+  const int grid = int((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  frz::wildfire_restore_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*params, *io, parallel_envs, env_mask);
+  const int status = frz::check_launch("wildfire_restore_kernel");
+  if (status != FRZ_OK) return status;
+  return frz::dispatch(params, io, parallel_envs, frz::kRefresh, stream);
+}
+
+int frz_wildfire_sample_actions(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
+                                uint64_t sampler_seed, void* stream) {
+  if (params == nullptr || io == nullptr || io->actions == nullptr || io->control == nullptr) {
+    frz::set_error("frz_wildfire_sample_actions: NULL params / buffers");
+    return FRZ_ERR_NULL;
+  }
+  const int total = parallel_envs * params->num_agents;
+  const int grid = (total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8;
+  frz::wildfire_sample_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*params, *io, parallel_envs, sampler_seed);
+  return frz::check_launch("wildfire_sample_kernel");
+}
+
+}  // extern "C"

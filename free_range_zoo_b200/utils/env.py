@@ -1,0 +1,342 @@
+"""AEC runtime shell of the B200 engine.
+
+``BatchedAECEnv`` keeps the surface of the reference base class (free_range_zoo/utils/env.py:18-359): the same
+constructor keywords, ``reset / reset_batches / step / observe / state / action_space / observation_space``, the
+five domain hooks (``step_environment``, ``update_actions``, ``update_observations``, ``action_space``,
+``observation_space``) and the public attributes (``agents``, ``rewards``, ``terminations``, ``truncations``,
+``infos``, ``num_moves``, ``environment_task_count``, ``agent_task_count``, ``finished`` ...).
+
+What changed underneath: the whole cycle the reference runs on the last agent of an AEC round --
+``step_environment -> num_moves += 1 -> truncation -> accumulate rewards -> update_observations -> update_actions``
+(utils/env.py:220-237) -- is ONE fused CUDA launch through the C ABI of ``include/frz.h``.  All per-step outputs
+live in persistent device buffers that the kernel updates in place; the dictionaries handed to the caller are views
+of those buffers, so there is no host round trip, no ``.tolist()``, no allocation on the step path.  The reference's
+host-side "is every environment done?" test (utils/env.py:212, a device synchronisation per agent call) is evaluated
+on the device from flags the previous launch published.
+
+NOTE on aliasing: because buffers are updated in place, tensors returned by ``step`` are overwritten by the next
+``step``.  Pass ``detach_outputs=True`` to get fresh copies (the reference's behaviour) at the cost of one copy each.
+"""
+from __future__ import annotations
+
+import ctypes
+from abc import ABC, abstractmethod
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+
+from free_range_zoo_b200 import _lib
+from free_range_zoo_b200.utils.configuration import Configuration
+from free_range_zoo_b200.utils.containers import ObservationDict
+from free_range_zoo_b200.utils.selector import AgentSelector
+
+
+def _seed_to_u64(seed) -> int:
+    """Fold whatever ``reset(seed=...)`` received (None / int / list / tensor) into one 64-bit Philox key."""
+    if seed is None:
+        return int(torch.randint(0, 2**62, (1, )).item())
+    if isinstance(seed, torch.Tensor):
+        seed = seed.flatten().tolist()
+    if isinstance(seed, (list, tuple)):
+        folded = 0x9E3779B97F4A7C15
+        for value in seed:
+            folded = ((folded ^ (int(value) & 0xFFFFFFFFFFFFFFFF)) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+        return folded
+    return int(seed) & 0xFFFFFFFFFFFFFFFF
+
+
+class BatchedAECEnv(ABC):
+    """Batched agent-environment-cycle environment whose step runs as one CUDA kernel."""
+
+    metadata: Dict[str, Any] = {}
+
+    def __init__(
+        self,
+        *args,
+        configuration: Configuration = None,
+        max_steps: int = 1,
+        parallel_envs: int = 1,
+        device: torch.device = torch.device('cuda'),
+        render_mode: str | None = None,
+        log_directory: str = None,
+        single_seeding: bool = False,
+        buffer_size: int = 0,
+        override_initialization_check: bool = False,
+        env_offset: int = 0,
+        detach_outputs: bool = False,
+        **kwargs,
+    ):
+        """
+        Args (same meaning as the reference, utils/env.py:21-48):
+            configuration: the domain's configuration structure
+            max_steps: truncation horizon
+            parallel_envs: number of environments stepped together
+            device: must be a CUDA device -- there is no CPU path
+            render_mode / log_directory / override_initialization_check: accepted; logging and rendering are host-side
+                subsystems outside this engine (log_directory must be None)
+            single_seeding / buffer_size: accepted and ignored -- randomness is counter-based Philox generated inside
+                the step kernel, keyed by (seed, global env index, step), so there are no generator states to juggle
+            env_offset: global index of this shard's first environment (multi-GPU sharding keeps trajectories invariant)
+            detach_outputs: return copies instead of views of the in-place updated device buffers
+        """
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise RuntimeError(f'free_range_zoo_b200 runs on CUDA devices only (got device={device}); '
+                               'there is no CPU fallback -- use the reference implementation on CPU.')
+        if device.index is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        if log_directory is not None:
+            raise NotImplementedError('CSV / SQL logging is outside the B200 step engine; pass log_directory=None')
+        self.parallel_envs = int(parallel_envs)
+        self.max_steps = max_steps
+        self.device = device
+        self.render_mode = render_mode
+        self.log_directory = None
+        self.single_seeding = single_seeding
+        self.log_description = None
+        self.logger = None
+        self.env_offset = int(env_offset)
+        self.detach_outputs = detach_outputs
+
+        if configuration is not None:
+            self.config = configuration
+            # hoist the sub-configurations as attributes, like the reference (utils/env.py:58-63)
+            for key, value in vars(configuration).items():
+                if hasattr(value, 'validate') and not isinstance(value, torch.Tensor):
+                    setattr(self, key, value)
+
+        self._lib = _lib.library()
+        self._control = torch.zeros(4, dtype=torch.int64, device=self.device)  # FrzControl, 32 bytes
+        self._seed_value = None
+        self._graph = None
+
+    # ------------------------------------------------------------------------------------------ properties
+
+    @property
+    def num_agents(self) -> int:
+        return len(self.agents)
+
+    @property
+    def max_num_agents(self) -> int:
+        return len(self.possible_agents)
+
+    @property
+    def unwrapped(self) -> 'BatchedAECEnv':
+        return self
+
+    @property
+    def terminated(self) -> torch.Tensor:
+        """bool [B]; every agent of an environment terminates together (reference utils/env.py:341-349)."""
+        return self._terminated.view(torch.bool)
+
+    @property
+    def truncated(self) -> torch.Tensor:
+        return self._truncated.view(torch.bool)
+
+    @property
+    def finished(self) -> torch.Tensor:
+        return torch.logical_or(self.terminated, self.truncated)
+
+    @property
+    def agent_task_count(self) -> torch.Tensor:
+        """int32 [A, B] like the reference (utils/env.py:160); a transposed view of the kernel's [B, A] buffer."""
+        return self._agent_task_count.t()
+
+    @property
+    def rewards(self) -> Dict[str, torch.Tensor]:
+        """Per-agent rewards of the last environment step.  In the middle of an AEC round the reference has cleared
+        them to zero (utils/env.py:215,251-254); that is mirrored without touching device memory."""
+        if self._mid_cycle:
+            return {agent: self._zero_rewards for agent in self.agents}
+        return self._reward_views
+
+    # ------------------------------------------------------------------------------------------ allocation
+
+    def _allocate_runtime(self, num_agents: int) -> None:
+        """Persistent AEC buffers (what the reference re-creates in reset, utils/env.py:129-160)."""
+        B, A, dev = self.parallel_envs, num_agents, self.device
+        self._actions = torch.zeros((B, A, 2), dtype=torch.int32, device=dev)
+        self._rewards = torch.zeros((B, A), dtype=torch.float32, device=dev)
+        self._cumulative = torch.zeros((B, A), dtype=torch.float32, device=dev)
+        self._terminated = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self._truncated = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self.num_moves = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.environment_task_count = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._agent_task_count = torch.zeros((B, A), dtype=torch.int32, device=dev)
+        self._zero_rewards = torch.zeros(B, dtype=torch.float32, device=dev)
+
+    def _stream(self) -> ctypes.c_void_p:
+        return _lib.stream_handle(self.device)
+
+    def _horizon(self) -> int:
+        return 2**31 - 1 if self.max_steps is None else int(self.max_steps)
+
+    # ------------------------------------------------------------------------------------------ reset
+
+    @torch.no_grad()
+    def reset(self, seed=None, options: Optional[Dict[str, Any]] = None) -> None:
+        """Reset every environment (reference utils/env.py:95-160). Subclasses extend this with their state."""
+        options = options or {}
+        if options.get('max_steps') is not None:
+            self.max_steps = options['max_steps']
+        self._log_label = options.get('log_label')
+        self.log_description = options.get('log_description')
+
+        if options.get('skip_seeding'):
+            if self._seed_value is None:
+                raise ValueError("Seed must be set before skipping seeding is possible")
+        else:
+            self._seed_value = _seed_to_u64(seed)
+        self.seeds = torch.full((self.parallel_envs, ), self._seed_value & 0x7FFFFFFF, dtype=torch.int32,
+                                device=self.device)
+        _lib.check(self._lib.frz_control_init(self._control.data_ptr(), ctypes.c_uint64(self._seed_value), self._stream()),
+                   'frz_control_init')
+
+        self.agents = self.possible_agents
+        self.infos = {agent: {} for agent in self.agents}
+        self._reward_views = {a: self._rewards[:, i] for i, a in enumerate(self.agents)}
+        self._cumulative_rewards = {a: self._cumulative[:, i] for i, a in enumerate(self.agents)}
+        terminated, truncated = self.terminated, self.truncated
+        self.terminations = {a: terminated for a in self.agents}
+        self.truncations = {a: truncated for a in self.agents}
+        self.actions = {a: self._actions[:, i] for i, a in enumerate(self.agents)}
+        self._agent_slot = {a: i for i, a in enumerate(self.agents)}
+        self._mid_cycle = False
+
+        self.agent_selector = AgentSelector(self.agents)
+        self.agent_selection = self.agent_selector.reset()
+
+    @torch.no_grad()
+    def reset_batches(self, batch_indices, seed=None, options: Optional[Dict[str, Any]] = None) -> None:
+        """Reset only the environments ``batch_indices`` (reference utils/env.py:163-189; index list or tensor)."""
+        mask = torch.zeros(self.parallel_envs, dtype=torch.uint8, device=self.device)
+        mask[torch.as_tensor(batch_indices, device=self.device, dtype=torch.int64)] = 1
+        self._reset_masked(mask)
+
+    @abstractmethod
+    def _reset_masked(self, mask: Optional[torch.Tensor]) -> None:
+        """Launch the domain's reset kernel for the environments selected by ``mask`` (uint8 [B]; None = all)."""
+
+    # ------------------------------------------------------------------------------------------ step
+
+    @abstractmethod
+    def step_environment(self) -> Tuple[Dict[str, torch.Tensor], Dict[str, torch.Tensor], Dict[str, Dict]]:
+        """Launch the domain's fused step kernel; returns (rewards, terminations, infos) views."""
+
+    @abstractmethod
+    def update_actions(self) -> None:
+        """Refresh task counts / action masks from the current state (already done inside the fused step)."""
+
+    @abstractmethod
+    def update_observations(self) -> None:
+        """Refresh observations from the current state (already done inside the fused step)."""
+
+    @abstractmethod
+    def action_space(self, agent: str):
+        """Per-environment action spaces of ``agent`` (a lazily materialised ``Space.Vector``)."""
+
+    @abstractmethod
+    def observation_space(self, agent: str):
+        """Per-environment observation spaces of ``agent``."""
+
+    @torch.no_grad()
+    def step(self, actions: torch.Tensor) -> None:
+        """AEC step of the currently selected agent (reference utils/env.py:203-242).
+
+        The agent's ``[B, 2]`` actions are staged into the device action table; when the last agent of the round has
+        acted, one fused launch advances every environment.
+        """
+        self._actions[:, self._agent_slot[self.agent_selection]].copy_(actions, non_blocking=True)
+        self._mid_cycle = True
+        if self.agent_selector.is_last():
+            self._advance()
+        self.agent_selection = self.agent_selector.next()
+
+    @torch.no_grad()
+    def step_all(self, actions: Optional[torch.Tensor] = None) -> None:
+        """One environment step for all agents at once: ``actions`` int32 [B, A, 2] (None = already staged in
+        ``env._actions``, e.g. by ``sample_actions``).  Equivalent to A consecutive ``step`` calls."""
+        if actions is not None and actions.data_ptr() != self._actions.data_ptr():
+            self._actions.copy_(actions, non_blocking=True)
+        self._advance()
+
+    def _advance(self) -> None:
+        _, _, infos = self.step_environment()
+        self.infos = infos
+        self._mid_cycle = False
+        self._rebind_outputs()
+
+    def _rebind_outputs(self) -> None:
+        """Re-create the lazily evaluated observation views after the device buffers changed."""
+        self.update_observation_views()
+        if self.detach_outputs:
+            self._reward_views = {a: self._rewards[:, i].clone() for i, a in enumerate(self.agents)}
+            terminated, truncated = self.terminated.clone(), self.truncated.clone()
+            self.terminations = {a: terminated for a in self.agents}
+            self.truncations = {a: truncated for a in self.agents}
+
+    @abstractmethod
+    def update_observation_views(self) -> None:
+        """Build ``self.observations`` (dict agent -> ObservationDict) as views of the device buffers."""
+
+    @torch.no_grad()
+    def observe(self, agent: str) -> ObservationDict:
+        return self.observations[agent]
+
+    @torch.no_grad()
+    def state(self):
+        return self._state
+
+    def last(self, observe: bool = True):
+        """pettingzoo AEC convenience: (observation, reward, termination, truncation, info) of the selected agent."""
+        agent = self.agent_selection
+        observation = self.observe(agent) if observe else None
+        return (observation, self._cumulative_rewards[agent], self.terminations[agent], self.truncations[agent],
+                self.infos[agent])
+
+    # ------------------------------------------------------------------------------------------ diagnostics
+
+    def control_block(self) -> Dict[str, int]:
+        """Host copy of the device control block (synchronises; diagnostics / tests only)."""
+        raw = self._control.cpu().numpy().tobytes()
+        block = _lib.Control.from_buffer_copy(raw)
+        return {name: getattr(block, name) for name, _ in _lib.Control._fields_}
+
+    def check_errors(self) -> None:
+        """Raise ``ValueError`` for data-dependent faults the kernels recorded (the reference raises these eagerly,
+        at the price of a host sync per step: cybersecurity.py:341-363).  Synchronises; call it off the hot path."""
+        word = self.control_block()['error_word']
+        if word:
+            self._control.view(torch.int32)[7] = 0
+            reasons = [text for bit, text in _lib.FAULT_NAMES.items() if word & bit]
+            raise ValueError('invalid actions were submitted: ' + '; '.join(reasons))
+
+    # ------------------------------------------------------------------------------------------ CUDA graph
+
+    def capture_graph(self, sample: bool = False, sampler_seed: int = 2026) -> None:
+        """Capture ``[sample_actions ->] step`` in a CUDA graph; ``replay()`` then costs one graph launch per step.
+        Kernel arguments are pointer-stable and the step counter lives on the device, so the graph needs no updates."""
+        torch.cuda.synchronize(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):  # warm-up outside capture (lazy module load, occupancy query)
+            if sample:
+                self.sample_actions(sampler_seed)
+            self.step_environment()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            if sample:
+                self.sample_actions(sampler_seed)
+            self.step_environment()
+        self._graph = graph
+
+    def replay(self) -> None:
+        self._graph.replay()
+        self._mid_cycle = False
+
+    def sample_actions(self, sampler_seed: int = 2026) -> torch.Tensor:
+        """Uniform random legal actions for every agent, generated on the device into the staged action table
+        (the caller side of the path: replaces ``action_space(agent).sample_nested()`` per agent per step)."""
+        raise NotImplementedError

@@ -1,0 +1,184 @@
+/*
+ * frz.h -- C ABI of libfrz.so, the B200 (sm_100a) batched environment-step engine for free-range-zoo.
+ *
+ * The reference has no FFI: its "plugin" boundary is the set of BatchedAECEnv hooks
+ *   step_environment()   free_range_zoo/utils/env.py:197-201
+ *   update_actions()     free_range_zoo/utils/env.py:273-276
+ *   update_observations()free_range_zoo/utils/env.py:278-281
+ * plus the AEC bookkeeping of BatchedAECEnv.step (utils/env.py:203-242).  Each frz_<domain>_step below replaces the
+ * bodies of those hooks for one domain with ONE fused kernel launch; frz_<domain>_reset replaces
+ * BatchedAECEnv.reset / reset_batches (utils/env.py:95-189) on the device side.
+ *
+ * Conventions
+ *  - Plain C, no torch types.  Every pointer inside a Frz*Buffers struct is a DEVICE pointer owned by the caller
+ *    (a torch tensor's data_ptr()); the library allocates nothing, frees nothing and keeps no device state.
+ *  - Every call only enqueues work on the caller's cudaStream_t (passed as void*): no synchronisation, no
+ *    allocation, no host read-back -> capturable in a CUDA graph.  The step counter / seed / done flags live in the
+ *    device-side FrzControl block and are advanced by the kernels themselves, so graph replays need no new arguments.
+ *  - Return value: FRZ_OK or a FrzStatus error; the message is available from frz_last_error() (thread-local).
+ *    Data-dependent faults (the reference's ValueErrors, e.g. cybersecurity.py:341-363) set bits in
+ *    FrzControl.error_word on the device and are read lazily by the host, never on the step path.
+ *  - Layouts are environment-major ("[B, ...]", B = parallel_envs) with the reference's dtypes
+ *    (int32 / float32 / uint8 for bool), so state tensors are directly the reference's State fields.
+ */
+#ifndef FRZ_H_
+#define FRZ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRZ_ABI_VERSION 1
+
+#define FRZ_MAX_AGENTS 32      /* agents per environment (one warp lane each) */
+#define FRZ_MAX_EQUIPMENT 8    /* wildfire equipment states */
+#define FRZ_MAX_CAPACITIES 8   /* wildfire tank sizes */
+#define FRZ_MAX_CELLS 256      /* wildfire H*W */
+#define FRZ_MAX_NODES 32       /* cybersecurity subnetworks */
+#define FRZ_MAX_NET_STATES 16  /* cybersecurity states per subnetwork */
+#define FRZ_MAX_PASSENGERS 64  /* rideshare passengers simultaneously tracked per environment */
+#define FRZ_PAD (-100)         /* padding value of padded observations (the reference pads with -100) */
+
+typedef enum {
+  FRZ_OK = 0,
+  FRZ_ERR_NULL = 1,        /* a required pointer is NULL */
+  FRZ_ERR_SHAPE = 2,       /* B <= 0 or a size outside the compiled limits */
+  FRZ_ERR_CUDA = 3,        /* cudaGetLastError() after the launch */
+  FRZ_ERR_UNSUPPORTED = 4
+} FrzStatus;
+
+/* bits of FrzControl.error_word (data-dependent faults found on the device) */
+#define FRZ_FAULT_BAD_TASK_INDEX 0x1u  /* action[:,0] is not a valid index into the agent's task list */
+#define FRZ_FAULT_BAD_NODE 0x2u        /* cybersecurity: attack / move target outside [0, N) (cybersecurity.py:341,357) */
+#define FRZ_FAULT_ABSENT_ACTED 0x4u    /* cybersecurity: non-present agent acted with show_bad_actions=False (:345,362) */
+#define FRZ_FAULT_TABLE_FULL 0x8u      /* rideshare: more passengers present than FrzRideshareParams.capacity */
+
+/* Device-resident control block (32 bytes). */
+typedef struct {
+  uint64_t seed;        /* Philox key */
+  uint64_t step;        /* number of executed environment steps since the last full reset (Philox counter) */
+  uint32_t ctas_done;   /* scratch: CTAs of the running launch that have finished */
+  uint32_t alive_acc;   /* scratch: bit0 = some env not terminated, bit1 = some env not truncated (this launch) */
+  uint32_t alive;       /* the same two bits as of the previous launch; 0 in a bit => BatchedAECEnv.step early-out
+                           (utils/env.py:212) => the whole launch is a no-op */
+  uint32_t error_word;  /* FRZ_FAULT_* bits, sticky until cleared by the host */
+} FrzControl;
+
+/* ----------------------------------------------------------------------------------------------- wildfire */
+
+/* bits of FrzWildfireParams.flags: StochasticConfiguration (structures/configuration.py:271-322), reward switches
+ * (:15-56) and the show_bad_actions constructor flag (wildfire.py:176-178) */
+#define FRZ_WF_STOCH_SUPPRESSANT_DECREASE 0x0001u
+#define FRZ_WF_STOCH_REFILL 0x0002u
+#define FRZ_WF_STOCH_TANK_SWITCH 0x0004u
+#define FRZ_WF_CRITICAL_ERROR 0x0008u
+#define FRZ_WF_STOCH_DEGRADE 0x0010u
+#define FRZ_WF_STOCH_REPAIR 0x0020u
+#define FRZ_WF_STOCH_FIRE_INCREASE 0x0040u
+#define FRZ_WF_STOCH_FIRE_DECREASE 0x0080u
+#define FRZ_WF_SPECIAL_BURNOUT 0x0100u
+#define FRZ_WF_FIRE_FUEL 0x0200u
+#define FRZ_WF_BURNOUT_SCALED 0x0400u
+#define FRZ_WF_LOCALIZE_PUTOUTS 0x0800u
+#define FRZ_WF_SHOW_BAD_ACTIONS 0x1000u
+
+/* WildfireConfiguration flattened once at construction (passed by value to the kernel). */
+typedef struct {
+  int32_t height, width, num_agents;
+  int32_t num_fire_states;       /* S: burned out = S-1, almost burned out = S-2 (fire_increase.py:25-26) */
+  int32_t num_equipment_states;  /* E */
+  int32_t num_capacities;
+  int32_t max_steps;             /* truncation horizon (utils/env.py:230-233); INT32_MAX = none */
+  uint32_t flags;
+  int64_t env_offset;            /* global index of local env 0 (multi-GPU shard) -> RNG stream invariant to sharding */
+  float p_increase, p_burnout, p_decrease, decrease_bonus;
+  float p_random_ignition;       /* fire_random_spread_weight (configuration.py:365-371) */
+  float spread_lut[16];          /* fp32 conv sum per lit-neighbour pattern, bit0 N, bit1 W, bit2 E, bit3 S */
+  float p_suppressant_decrease, p_refill, p_repair, p_degrade, p_critical, p_tank_switch;
+  float capacity_cum[FRZ_MAX_CAPACITIES];    /* cumsum(capacity_probabilities) (capacity.py:28) */
+  float capacity_value[FRZ_MAX_CAPACITIES];  /* possible_capacities */
+  float equipment_capacity_bonus[FRZ_MAX_EQUIPMENT]; /* equipment_states[:,0] */
+  float equipment_power_bonus[FRZ_MAX_EQUIPMENT];    /* equipment_states[:,1]; the range column is folded into range_mask */
+  float bad_attack_penalty, burnout_penalty, termination_reward, termination_kappa;
+  int32_t agent_y[FRZ_MAX_AGENTS], agent_x[FRZ_MAX_AGENTS];
+  float agent_power[FRZ_MAX_AGENTS];         /* fire_reduction_power */
+} FrzWildfireParams;
+
+typedef struct {
+  /* WildfireState (structures/state.py:11-33), updated in place */
+  int32_t* fires;       /* [B, H*W] */
+  int32_t* intensity;   /* [B, H*W] */
+  int32_t* fuel;        /* [B, H*W] */
+  float* suppressants;  /* [B, A] */
+  float* capacity;      /* [B, A] */
+  int32_t* equipment;   /* [B, A] */
+  /* copies restored by frz_wildfire_reset (State.save_initial, utils/state.py:36-38) */
+  const int32_t* init_fires;
+  const int32_t* init_intensity;
+  const int32_t* init_fuel;
+  const float* init_suppressants;
+  const float* init_capacity;
+  const int32_t* init_equipment;
+  /* AEC runtime (utils/env.py:129-160) */
+  const int32_t* actions;      /* [B, A, 2]  (agent-local task index, action id; id -1 = refill/noop) */
+  float* rewards;              /* [B, A] */
+  float* cumulative_rewards;   /* [B, A] */
+  uint8_t* terminated;         /* [B] */
+  uint8_t* truncated;          /* [B] */
+  int32_t* num_moves;          /* [B] */
+  int32_t* num_burnouts;       /* [B]  (wildfire.py:360,580) */
+  int32_t* burnouts;           /* [B]  infos['burnouts'] (wildfire.py:581) */
+  int32_t* putouts;            /* [B]  infos['putouts'] (wildfire.py:582) */
+  /* what update_actions / update_observations produce (wildfire.py:587-717) */
+  int32_t* env_task_count;     /* [B] */
+  int32_t* agent_task_count;   /* [B, A] */
+  uint8_t* action_mask;        /* [B, A, mask_stride]: 1 iff env-local task t can be fought by the agent */
+  float* self_obs;             /* [B, A, 4] (y, x, power, suppressant) */
+  int32_t* task_obs;           /* [B, H*W, 4] (y, x, fires, intensity) in row-major lit order, padded with FRZ_PAD */
+  /* static tables */
+  const float* cell_reward;    /* [H*W] reward_config.fire_rewards */
+  const int32_t* cell_ignition;/* [H*W] fire_config.ignition_temp */
+  const uint32_t* range_mask;  /* [A, E, mask_words] bit c set iff cell c is within the agent's Chebyshev range when
+                                  its equipment is in state e (wildfire.py:606-616, utils/in_range_check.py:5-23) */
+  /* randomness */
+  FrzControl* control;
+  const float* field_uniforms; /* nullable: injected uniforms [3, B, H, W] (wildfire.py:409) instead of Philox */
+  const float* agent_uniforms; /* nullable: injected uniforms [5, B, A]    (wildfire.py:410) */
+  int32_t mask_stride;         /* row stride of action_mask in bytes: H*W rounded up to a multiple of 4 */
+  int32_t mask_words;          /* ceil(H*W / 32) */
+} FrzWildfireBuffers;
+
+/* One full environment step for all B envs: action decode, the seven transitions in the reference order, rewards,
+ * termination, num_moves/truncation, reward accumulation, observations, task counts and action masks.
+ * Replaces wildfire.py:400-717 + utils/env.py:215-237. */
+int frz_wildfire_step(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs, void* stream);
+
+/* Recompute observations / counts / masks from the current state without stepping (what reset() does through
+ * update_observations + update_actions, wildfire.py:368-371). */
+int frz_wildfire_refresh(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
+                         void* stream);
+
+/* Restore the saved initial state and zero the AEC fields of the envs selected by env_mask (uint8 [B], device;
+ * NULL = all), then refresh.  Replaces utils/env.py:163-189 + wildfire.py:376-397. */
+int frz_wildfire_reset(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
+                       const uint8_t* env_mask, void* stream);
+
+/* Uniform random legal actions written into io->actions (caller side of the path: replaces
+ * env.action_space(agent).sample_nested(), wildfire.py:720-734 + spaces/actions.py:10-41). */
+int frz_wildfire_sample_actions(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
+                                uint64_t sampler_seed, void* stream);
+
+/* ----------------------------------------------------------------------------------------------- common */
+
+int frz_version(void);
+const char* frz_last_error(void);
+/* (re)initialise a control block on the device: seed, step = 0, alive = 3, error_word = 0 */
+int frz_control_init(FrzControl* control, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRZ_H_ */

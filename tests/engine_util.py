@@ -1,0 +1,47 @@
+"""Dump the engine's device state in the golden-fixture layout (tests/golden/gen_golden.py::*_outputs)."""
+import numpy as np
+import torch
+
+PAD = -100
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+def padded_indices(mask: np.ndarray) -> np.ndarray:
+    """bool [B, T] -> int32 [B, T]: positions of the set entries of each row, left-packed, padded with -100."""
+    out = np.full(mask.shape, PAD, np.int32)
+    for b in range(mask.shape[0]):
+        idx = np.nonzero(mask[b])[0]
+        out[b, :len(idx)] = idx
+    return out
+
+
+def wildfire_outputs(env) -> dict:
+    raw = env.unwrapped
+    A = len(raw.agents)
+    HW = raw.max_y * raw.max_x
+    s = raw.state()
+    mask = cpu(raw.action_mask) != 0  # [B, A, HW] over env-local tasks
+    counts = cpu(raw.environment_task_count)
+    lit_tasks = np.arange(HW)[None, :] < counts[:, None]
+    out = dict(
+        fires=cpu(s.fires), intensity=cpu(s.intensity), fuel=cpu(s.fuel), suppressants=cpu(s.suppressants),
+        capacity=cpu(s.capacity), equipment=cpu(s.equipment),
+        rewards=np.stack([cpu(raw.rewards[a]) for a in raw.agents], axis=1),
+        terminated=np.stack([cpu(raw.terminations[a]) for a in raw.agents], axis=1),
+        truncated=np.stack([cpu(raw.truncations[a]) for a in raw.agents], axis=1),
+        num_moves=cpu(raw.num_moves), num_burnouts=cpu(raw.num_burnouts),
+        burnouts=cpu(raw.infos['burnouts']), putouts=cpu(raw.infos['putouts']),
+        env_task_count=counts, agent_task_count=cpu(raw.agent_task_count).T,
+        self_obs=np.stack([cpu(raw.observations[a]['self']) for a in raw.agents], axis=1),
+        others_obs=np.stack([cpu(raw.observations[a]['others']) for a in raw.agents], axis=0),
+        task_obs=cpu(raw.observations[raw.agents[0]]['tasks_padded']),
+    )
+    if raw.show_bad_actions:
+        out['action_map'] = np.stack([padded_indices(lit_tasks) for _ in range(A)], axis=0)
+        out['bad_map'] = np.stack([padded_indices(lit_tasks & ~mask[:, a]) for a in range(A)], axis=0)
+    else:
+        out['action_map'] = np.stack([padded_indices(mask[:, a]) for a in range(A)], axis=0)
+    return out
