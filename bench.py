@@ -1,0 +1,325 @@
+"""Benchmark of the fused environment-step path (BASELINE.json metric: env-steps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wildfire_c4] [--impl engine|reference]
+
+A "step" is one environment step of ALL ``parallel_envs`` environments with random legal actions.  At N=1 the workload
+is BASELINE.json configs[3] -- wildfire 10x10 / 10 agents, agent+task+frame openness, parallel_envs=65,536 -- the
+configuration the headline target (>= 50x the host-CPU path, >= 60 % of HBM roofline) is quoted on.  For N>1 (launched
+by ``python -m torch.distributed.run``) every rank steps its own 65,536-env shard (weak scaling, no step-path
+collective; the global env index keys the RNG so trajectories do not depend on N) and NCCL is used only for the
+barrier / max-over-ranks timing / statistics all-reduce.
+
+One JSON line is printed by rank 0:
+  value     whole-job env-steps/s, inputs resident in HBM, [sample_actions -> step] captured in one CUDA graph
+  roofline  the step kernel alone: algorithmic bytes per launch / CUDA-event duration vs measured HBM peak
+  e2e       same metric through the public Parallel API with HOST buffers: pinned actions H2D + step + rewards/dones D2H
+  cpu_baseline  the CPU oracle port of the same workload on the box's host cores (bounded sample)
+``--impl reference`` times the CPU oracle port (the reference's algorithm restated in numpy: the Python reference
+cannot travel to the GPU box) on all host cores and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (domain, preset, parallel_envs per GPU, max_steps, algorithmic bytes per env-step, agents)
+    'wildfire_c4': ('wildfire', 'wildfire_large', 65536, 1 << 30, 5600, 10),
+    'wildfire_c1': ('wildfire', 'wildfire_3x3', 1024, 1 << 30, 581, 3),
+}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop, self._thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-i',
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([field.strip() for field in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, flag in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[3:7]):
+                if flag.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'samples': len(sm),
+                'power_w_max': max(float(s[2]) for s in self.samples), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+
+
+def _oracle_worker(args):
+    domain, preset_name, envs, steps, seed = args
+    import numpy as np
+    from free_range_zoo_b200 import presets
+    from oracle.wildfire import WildfireOracle
+    config = getattr(presets, preset_name)()
+    oracle = WildfireOracle(config, envs, 1 << 30)
+    oracle.reset()
+    rng = np.random.default_rng(seed)
+    H, W, A = oracle.H, oracle.W, oracle.A
+
+    def one_step():
+        counts = oracle.agent_task_count
+        k = np.minimum((rng.random(counts.shape) * (counts + 1)).astype(np.int64), counts)
+        actions = np.stack([k, np.where(k == counts, -1, 0)], axis=2).astype(np.int32)
+        u_field = rng.random((3, envs, H, W), dtype=np.float32)
+        u_agent = rng.random((5, envs, A), dtype=np.float32)
+        start = time.perf_counter()  # action sampling and uniform generation are excluded, like SURVEY 8(d)
+        oracle.step(actions, u_field, u_agent)
+        return time.perf_counter() - start
+
+    one_step()
+    return sum(one_step() for _ in range(steps))
+
+
+def cpu_oracle_throughput(workload: str, processes: int, envs_per_process: int, steps: int):
+    """env-steps/s of the numpy oracle, `processes` workers each stepping its own batch (max over workers)."""
+    import multiprocessing as mp
+    domain, preset_name = WORKLOADS[workload][:2]
+    jobs = [(domain, preset_name, envs_per_process, steps, 100 + i) for i in range(processes)]
+    if processes == 1:
+        seconds = [_oracle_worker(jobs[0])]
+    else:
+        with mp.get_context('fork').Pool(processes) as pool:
+            seconds = pool.map(_oracle_worker, jobs)
+    return processes * envs_per_process * steps / max(seconds)
+
+
+def run_reference(args):
+    """--impl reference: the CPU oracle port on all host cores (rank 0 only)."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    domain, preset_name, B, _, _, agents = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    envs_per_process, steps = 1024, max(1, min(args.steps, 5))
+    cpu_oracle_throughput(args.workload, cores, envs_per_process, max(1, min(args.warmup, 1)))
+    start = time.perf_counter()
+    value = cpu_oracle_throughput(args.workload, cores, envs_per_process, steps)
+    wall = time.perf_counter() - start
+    sample = (f'{cores} processes x {envs_per_process} envs x {steps} steps of {args.workload} '
+              f'(numpy oracle port, oracle/wildfire.py; step() only)')
+    line = {
+        'impl': 'reference', 'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * cores * envs_per_process / value,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32+f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'parallel_envs_sampled': cores * envs_per_process, 'agents': agents},
+        'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0, 'wall_s': wall,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+
+    from free_range_zoo_b200 import presets
+    from free_range_zoo_b200.envs import wildfire_v0
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+
+    domain, preset_name, B, max_steps, bytes_per_env, agents = WORKLOADS[args.workload]
+    if args.parallel_envs:
+        B = args.parallel_envs
+    config = getattr(presets, preset_name)()
+    env = wildfire_v0.parallel_env(parallel_envs=B, max_steps=max_steps, configuration=config, device=device,
+                                   env_offset=rank * B)
+    raw = env.unwrapped
+    K, W = args.steps, max(3, args.warmup)
+    SEED, SAMPLER = 2026, 2026
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- (1) device-resident throughput: [sample_actions -> step] as one CUDA graph per step
+    env.reset(seed=SEED)
+    raw.capture_graph(sample=True, sampler_seed=SAMPLER)
+    env.reset(seed=SEED)
+    for _ in range(W):
+        raw.replay()
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        start.record()
+        for _ in range(K):
+            raw.replay()
+        stop.record()
+        barrier()
+    graph_ms = max_over_ranks(start.elapsed_time(stop))
+    value = world * B * K / (graph_ms * 1e-3)
+
+    # ---- (2) the step kernel alone, CUDA events around each launch on the launching stream
+    pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for _ in range(W):
+        raw.sample_actions(SAMPLER)
+        raw.step_environment()
+    barrier()
+    for before, after in pairs:
+        raw.sample_actions(SAMPLER)
+        before.record()
+        raw.step_environment()
+        after.record()
+    barrier()
+    kernel_ms = sum(b.elapsed_time(a) for b, a in pairs) / K
+    peak, peak_kind = measured_peak_gbs()
+    achieved = bytes_per_env * B / (kernel_ms * 1e-3) / 1e9
+    raw.check_errors()
+
+    # ---- (3) end to end through the public Parallel API with host buffers
+    # legal actions for every step are produced by a recorded dry run of the same seeded rollout
+    host_actions = torch.empty((W + K, B, agents, 2), dtype=torch.int32).pin_memory()
+    env.reset(seed=SEED)
+    for t in range(W + K):
+        raw.sample_actions(SAMPLER)
+        host_actions[t].copy_(raw._actions, non_blocking=True)
+        raw.step_all()
+    torch.cuda.synchronize(device)
+    host_rewards = torch.empty((B, agents), dtype=torch.float32).pin_memory()
+    host_done = torch.empty((2, B), dtype=torch.uint8).pin_memory()
+    staged = raw._actions  # the engine's own device action table: H2D lands where the kernel reads
+    env.reset(seed=SEED)
+
+    def e2e_step(t):
+        staged.copy_(host_actions[t], non_blocking=True)  # H2D from pinned memory
+        env.step(staged)  # public API: Parallel step
+        host_rewards.copy_(raw._rewards, non_blocking=True)  # D2H of the step's results
+        host_done[0].copy_(raw._terminated, non_blocking=True)
+        host_done[1].copy_(raw._truncated, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()  # the caller reads rewards / dones before acting again
+
+    for t in range(W):
+        e2e_step(t)
+    barrier()
+    start.record()
+    for t in range(W, W + K):
+        e2e_step(t)
+    stop.record()
+    barrier()
+    e2e_ms = max_over_ranks(start.elapsed_time(stop))
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
+    h2d = staged.numel() * 4
+    d2h = host_rewards.numel() * 4 + host_done.numel()
+
+    # ---- episode statistics: the only collective, off the step path
+    stats = torch.stack([raw._cumulative.sum().double(), raw.terminated.sum().double(), raw.num_moves.sum().double()])
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+
+    line = None
+    if rank == 0:
+        cores = 1
+        cpu_envs, cpu_steps = 1024, 10
+        cpu_value = cpu_oracle_throughput(args.workload, cores, cpu_envs, cpu_steps) if world == 1 else None
+        line = {
+            'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': graph_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'int32+f32', 'data': 'synthetic',
+            'config': {
+                'workload': args.workload, 'domain': domain, 'preset': preset_name, 'parallel_envs_per_gpu': B,
+                'parallel_envs_total': world * B, 'agents': agents, 'agent_steps_per_s': value * agents,
+                'actions': 'uniform random legal actions sampled on device (Philox), inside the timed region',
+                'l2': f'state+outputs per step = {bytes_per_env * B / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)'
+                if bytes_per_env * B > 126e6 else 'working set fits in L2 (launch-latency-bound config)',
+                'parallelism': f'dp{world} (env-batch sharding, no step-path collective)',
+            },
+            'roofline': {
+                'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'peak_kind': peak_kind, 'kernel': 'wildfire_step_kernel',
+                'kernel_ms': kernel_ms, 'algorithmic_bytes_per_env_step': bytes_per_env,
+            },
+            'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': e2e_ms / K},
+            'gpu_launches': 2 * K,
+            'clocks': clocks.summary(),
+            'stats': {'cumulative_reward_sum': float(stats[0]), 'terminated_envs': float(stats[1]),
+                      'env_steps_executed': float(stats[2])},
+        }
+        if cpu_value is not None:
+            line['cpu_baseline'] = {
+                'value': cpu_value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+                'sample': f'{cpu_envs} envs x {cpu_steps} steps of {args.workload}, numpy oracle port (oracle/wildfire.py), '
+                          f'1 process; step() only, action sampling excluded'}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=50)
+    parser.add_argument('--warmup', type=int, default=5)
+    parser.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    parser.add_argument('--workload', default='wildfire_c4', choices=sorted(WORKLOADS))
+    parser.add_argument('--parallel-envs', type=int, default=0, help='override parallel_envs per GPU')
+    args = parser.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == '__main__':
+    main()

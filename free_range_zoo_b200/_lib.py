@@ -32,7 +32,8 @@ FAULT_NAMES = {
 
 class Control(C.Structure):
     _fields_ = [('seed', C.c_uint64), ('step', C.c_uint64), ('ctas_done', C.c_uint32), ('alive_acc', C.c_uint32),
-                ('alive', C.c_uint32), ('error_word', C.c_uint32)]
+                ('alive', C.c_uint32), ('error_word', C.c_uint32), ('agents_with_tasks_acc', C.c_uint32),
+                ('agents_with_tasks', C.c_uint32), ('reserved', C.c_uint32 * 6)]
 
 
 # bits of WildfireParams.flags (include/frz.h)

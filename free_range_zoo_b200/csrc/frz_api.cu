@@ -30,6 +30,8 @@ __global__ void control_init_kernel(FrzControl* control, uint64_t seed) {
   control->alive_acc = 0;
   control->alive = 3u;
   control->error_word = 0;
+  control->agents_with_tasks_acc = 0;
+  control->agents_with_tasks = 0;
 }
 }  // namespace
 

@@ -66,34 +66,41 @@ __device__ __forceinline__ int select_bit(uint32_t w, int k) {
 
 // ---------------------------------------------------------------------------------------------- launch epilogue
 
-// Called by every CTA once, after its last environment.  `alive_bits`: bit0 = this CTA saw an env that is still not
-// terminated, bit1 = one that is still not truncated.  The last CTA to arrive publishes the flags for the next
-// launch and advances the step counter -- every CTA read control->step / control->alive at its start, so there is
-// no reader left when they change.
+// Called by every CTA once, after its last environment.
+//   alive_bits: bit0 = this CTA saw an env that is still not terminated, bit1 = one that is still not truncated
+//   agent_bits: bit a = agent a has at least one task in some env of this CTA (after this launch)
+// The last CTA to arrive publishes the accumulated flags for the next launch and advances the step counter -- every
+// CTA read control->step / alive / agents_with_tasks at its start, so no reader is left when they change.
+enum Publish { kPublishNothing = 0, kPublishRefresh = 1, kPublishStep = 2 };
+
 __device__ __forceinline__ void finish_launch(FrzControl* control, unsigned alive_bits, unsigned fault_bits,
-                                              bool advance) {
-  __shared__ unsigned s_alive, s_fault;
+                                              unsigned agent_bits, int publish) {
+  __shared__ unsigned s_alive, s_fault, s_agents;
   if (threadIdx.x == 0) {
     s_alive = 0;
     s_fault = 0;
+    s_agents = 0;
   }
   __syncthreads();
   if (alive_bits) atomicOr(&s_alive, alive_bits);
   if (fault_bits) atomicOr(&s_fault, fault_bits);
+  if (agent_bits) atomicOr(&s_agents, agent_bits);
   __syncthreads();
   if (threadIdx.x == 0) {
     if (s_alive) atomicOr(&control->alive_acc, s_alive);
     if (s_fault) atomicOr(&control->error_word, s_fault);
+    if (s_agents) atomicOr(&control->agents_with_tasks_acc, s_agents);
     __threadfence();
     const unsigned arrived = atomicAdd(&control->ctas_done, 1u) + 1u;
     if (arrived == gridDim.x) {
       __threadfence();
-      if (advance) {
-        control->alive = atomicExch(&control->alive_acc, 0u);
+      const unsigned alive = atomicExch(&control->alive_acc, 0u);
+      const unsigned agents = atomicExch(&control->agents_with_tasks_acc, 0u);
+      if (publish == kPublishStep) {
+        control->alive = alive;
         control->step += 1;
-      } else {
-        control->alive_acc = 0u;
       }
+      if (publish != kPublishNothing) control->agents_with_tasks = agents;
       control->ctas_done = 0u;
     }
   }

@@ -76,6 +76,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   FrzControl* control = io.control;
   const uint64_t step = control->step;
   const uint32_t alive_prev = control->alive;
+  const uint32_t agents_with_tasks = control->agents_with_tasks;
   const Philox philox(control->seed);
   // BatchedAECEnv.step returns before doing anything once every env is terminated, or every env is truncated
   // (utils/env.py:212); the flags were published by the previous launch.
@@ -104,7 +105,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   uint32_t* region = reinterpret_cast<uint32_t*>(smem) + size_t(group_in_cta) * region_words;
   unsigned char* region_bytes = reinterpret_cast<unsigned char*>(region);
 
-  unsigned alive_bits = 0, faults = 0;
+  unsigned alive_bits = 0, faults = 0, agent_bits = 0;
 
   if (!skip) {
     for (int env0 = blockIdx.x * groups_per_cta; env0 < B; env0 += gridDim.x * groups_per_cta) {
@@ -166,7 +167,9 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         const bool refill = is_agent && act_id == -1;  // wildfire.py:431
         int target = -1;
         bool bad = false;
-        if (is_agent && !refill) {
+        // an agent without a single task in ANY environment is skipped by the reference's decode loop
+        // (wildfire.py:434): no attack, no bad-action penalty -- only its refill flag is recorded
+        if (is_agent && !refill && ((agents_with_tasks >> sub) & 1u)) {
           int k = act_k, found = -1;
           if (k >= 0) {
 #pragma unroll
@@ -426,6 +429,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         }
         if (is_agent) {
           io.agent_task_count[agent_row + sub] = n_avail;
+          if (n_avail > 0) agent_bits |= 1u << sub;
           reinterpret_cast<float4*>(io.self_obs)[agent_row + sub] = make_float4(agent_yf, agent_xf, base_power, supp);
         }
         if (sub == 0) io.env_task_count[env] = n_lit;
@@ -459,7 +463,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       __syncwarp();
     }
   }
-  finish_launch(control, alive_bits, faults, mode == kStep && !skip);
+  finish_launch(control, alive_bits, faults, agent_bits,
+                skip ? kPublishNothing : (mode == kStep ? kPublishStep : kPublishRefresh));
 }
 
 // ------------------------------------------------------------------------------------------------ reset / sampling

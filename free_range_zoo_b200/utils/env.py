@@ -106,7 +106,7 @@ class BatchedAECEnv(ABC):
                     setattr(self, key, value)
 
         self._lib = _lib.library()
-        self._control = torch.zeros(4, dtype=torch.int64, device=self.device)  # FrzControl, 32 bytes
+        self._control = torch.zeros(8, dtype=torch.int64, device=self.device)  # FrzControl, 64 bytes
         self._seed_value = None
         self._graph = None
 
@@ -300,7 +300,7 @@ class BatchedAECEnv(ABC):
         """Host copy of the device control block (synchronises; diagnostics / tests only)."""
         raw = self._control.cpu().numpy().tobytes()
         block = _lib.Control.from_buffer_copy(raw)
-        return {name: getattr(block, name) for name, _ in _lib.Control._fields_}
+        return {name: getattr(block, name) for name, _ in _lib.Control._fields_ if name != 'reserved'}
 
     def check_errors(self) -> None:
         """Raise ``ValueError`` for data-dependent faults the kernels recorded (the reference raises these eagerly,

@@ -56,7 +56,7 @@ typedef enum {
 #define FRZ_FAULT_ABSENT_ACTED 0x4u    /* cybersecurity: non-present agent acted with show_bad_actions=False (:345,362) */
 #define FRZ_FAULT_TABLE_FULL 0x8u      /* rideshare: more passengers present than FrzRideshareParams.capacity */
 
-/* Device-resident control block (32 bytes). */
+/* Device-resident control block (64 bytes). */
 typedef struct {
   uint64_t seed;        /* Philox key */
   uint64_t step;        /* number of executed environment steps since the last full reset (Philox counter) */
@@ -65,6 +65,10 @@ typedef struct {
   uint32_t alive;       /* the same two bits as of the previous launch; 0 in a bit => BatchedAECEnv.step early-out
                            (utils/env.py:212) => the whole launch is a no-op */
   uint32_t error_word;  /* FRZ_FAULT_* bits, sticky until cleared by the host */
+  uint32_t agents_with_tasks_acc; /* scratch: bit a = agent a has >= 1 task in some env (this launch) */
+  uint32_t agents_with_tasks;     /* the same as of the previous launch: the reference skips an agent's whole action
+                                     decode when it has no task in ANY environment (wildfire.py:434) */
+  uint32_t reserved[6];
 } FrzControl;
 
 /* ----------------------------------------------------------------------------------------------- wildfire */
