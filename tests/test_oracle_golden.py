@@ -20,3 +20,30 @@ def test_wildfire_oracle_matches_reference(name):
         stepped = oracle.step(gold['actions'][t], gold['u_field'][t], gold['u_agent'][t])
         assert stepped
         G.compare(oracle.outputs(), gold, t + 1, context=name)
+
+
+@pytest.mark.parametrize('name', G.fixtures('cyber'))
+def test_cybersecurity_oracle_matches_reference(name):
+    from oracle.cybersecurity import CybersecurityOracle
+    meta, gold = G.load(name)
+    config = getattr(presets, meta['preset'])()
+    oracle = CybersecurityOracle(config, meta['B'], meta['max_steps'], **meta['env_kwargs'])
+    oracle.reset()
+    G.compare(oracle.outputs(meta['agents']), gold, 0, context=name)
+    for t in range(meta['steps']):
+        assert oracle.step(gold['actions'][t], gold['u_network'][t], gold['u_agent'][t])
+        G.compare(oracle.outputs(meta['agents']), gold, t + 1, context=name)
+    assert not oracle.faults
+
+
+@pytest.mark.parametrize('name', G.fixtures('rideshare'))
+def test_rideshare_oracle_matches_reference(name):
+    from oracle.rideshare import RideshareOracle
+    meta, gold = G.load(name)
+    config = getattr(presets, meta['preset'])(**meta['preset_kwargs'])
+    oracle = RideshareOracle(config, meta['B'], meta['max_steps'])
+    oracle.reset()
+    G.compare(oracle.outputs(), gold, 0, context=name)
+    for t in range(meta['steps']):
+        assert oracle.step(gold['actions'][t])
+        G.compare(oracle.outputs(), gold, t + 1, context=name)
