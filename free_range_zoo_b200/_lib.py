@@ -73,6 +73,31 @@ class WildfireBuffers(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in _WF_POINTERS] + [('mask_stride', C.c_int32), ('mask_words', C.c_int32)]
 
 
+CY_STOCHASTIC_STATE = 0x1
+CY_SHOW_BAD_ACTIONS = 0x2
+CY_MAX_LUT_BITS = 12
+
+
+class CyberParams(C.Structure):
+    _fields_ = [
+        ('num_nodes', C.c_int32), ('num_attackers', C.c_int32), ('num_defenders', C.c_int32), ('num_states', C.c_int32),
+        ('max_steps', C.c_int32), ('flags', C.c_uint32), ('env_offset', C.c_int64), ('lut_bits', C.c_int32),
+        ('temperature', C.c_float), ('patch_reward', C.c_float), ('bad_action_penalty', C.c_float),
+        ('power', C.c_float * MAX_AGENTS), ('persist', C.c_float * MAX_AGENTS), ('returns', C.c_float * MAX_AGENTS),
+        ('state_rewards', C.c_float * MAX_NET_STATES), ('criticality', C.c_float * MAX_NODES),
+    ]
+
+
+_CY_POINTERS = ('network_state', 'location', 'presence', 'init_network_state', 'init_location', 'init_presence',
+                'actions', 'rewards', 'cumulative_rewards', 'terminated', 'truncated', 'num_moves', 'env_task_count',
+                'agent_task_count', 'attacker_self', 'defender_self', 'task_obs', 'monitored', 'score_lut', 'control',
+                'network_uniforms', 'agent_uniforms')
+
+
+class CyberBuffers(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in _CY_POINTERS]
+
+
 _lib = None
 
 
@@ -94,6 +119,11 @@ def library() -> C.CDLL:
                                        C.c_void_p]
     lib.frz_wildfire_sample_actions.argtypes = [C.POINTER(WildfireParams), C.POINTER(WildfireBuffers), C.c_int32,
                                                 C.c_uint64, C.c_void_p]
+    for name in ('frz_cyber_step', 'frz_cyber_refresh'):
+        getattr(lib, name).argtypes = [C.POINTER(CyberParams), C.POINTER(CyberBuffers), C.c_int32, C.c_void_p]
+    lib.frz_cyber_reset.argtypes = [C.POINTER(CyberParams), C.POINTER(CyberBuffers), C.c_int32, C.c_void_p, C.c_void_p]
+    lib.frz_cyber_sample_actions.argtypes = [C.POINTER(CyberParams), C.POINTER(CyberBuffers), C.c_int32, C.c_uint64,
+                                             C.c_void_p]
     if lib.frz_version() != 1:
         raise RuntimeError(f'libfrz.so ABI version {lib.frz_version()} != 1; rebuild the library')
     _lib = lib

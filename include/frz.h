@@ -175,6 +175,73 @@ int frz_wildfire_reset(const FrzWildfireParams* params, const FrzWildfireBuffers
 int frz_wildfire_sample_actions(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
                                 uint64_t sampler_seed, void* stream);
 
+/* ----------------------------------------------------------------------------------------------- cybersecurity */
+
+#define FRZ_CY_STOCHASTIC_STATE 0x1u   /* StochasticConfiguration.network_state (configuration.py:240-253) */
+#define FRZ_CY_SHOW_BAD_ACTIONS 0x2u   /* constructor flag (cybersecurity.py:164-168) */
+#define FRZ_CY_MAX_LUT_BITS 12
+
+/* CybersecurityConfiguration flattened once at construction.  Agents are indexed attackers first, then defenders,
+ * exactly like the reference's presence tensor (structures/state.py:13-27). */
+typedef struct {
+  int32_t num_nodes, num_attackers, num_defenders, num_states;
+  int32_t max_steps;
+  uint32_t flags;
+  int64_t env_offset;
+  int32_t lut_bits;      /* num_attackers + num_defenders when score_lut is provided, else 0 (tanhf in-kernel) */
+  float temperature;
+  float patch_reward, bad_action_penalty;
+  float power[FRZ_MAX_AGENTS];          /* threat of attacker a / mitigation of defender d, agent-indexed */
+  float persist[FRZ_MAX_AGENTS];        /* presence.py:35-60 */
+  float returns[FRZ_MAX_AGENTS];
+  float state_rewards[FRZ_MAX_NET_STATES];
+  float criticality[FRZ_MAX_NODES];     /* adj_matrix.sum(1) as float (configuration.py:215-217, cybersecurity.py:399) */
+} FrzCyberParams;
+
+typedef struct {
+  /* CybersecurityState (structures/state.py:13-27), updated in place */
+  int32_t* network_state;  /* [B, N] */
+  int32_t* location;       /* [B, D]  -1 = home node */
+  uint8_t* presence;       /* [B, Att+D] */
+  const int32_t* init_network_state;
+  const int32_t* init_location;
+  const uint8_t* init_presence;
+  /* AEC runtime */
+  const int32_t* actions;     /* [B, Att+D, 2] (node, action id: 0 attack/move, -1 noop, -2 patch, -3 monitor) */
+  float* rewards;             /* [B, Att+D] */
+  float* cumulative_rewards;  /* [B, Att+D] */
+  uint8_t* terminated;        /* [B] (never set: cybersecurity.py:299) */
+  uint8_t* truncated;         /* [B] */
+  int32_t* num_moves;         /* [B] */
+  /* update_actions / update_observations (cybersecurity.py:414-526) */
+  int32_t* env_task_count;    /* [B] = N */
+  int32_t* agent_task_count;  /* [B, Att+D] = N * presence */
+  float* attacker_self;       /* [B, Att, 2] (threat, presence) */
+  float* defender_self;       /* [B, D, 3] (mitigation, presence, location) */
+  int32_t* task_obs;          /* [B, N, 2] (state, criticality) -- the reference's task_store */
+  uint8_t* monitored;         /* [B, D] 1 iff the defender's last action was monitor (-3): with partial observability
+                                 a defender only sees task_obs after monitoring (cybersecurity.py:497,510-511) */
+  /* static */
+  const float* score_lut;     /* nullable: [2^(Att+D)] tanh((patches-attacks)/T) for every (attacker set | defender set
+                                 << Att) acting on one node, evaluated on the host with the reference's own tanh */
+  /* randomness */
+  FrzControl* control;
+  const float* network_uniforms; /* nullable: injected [1, B, N]      (cybersecurity.py:304-309) */
+  const float* agent_uniforms;   /* nullable: injected [1, B, Att+D]  (cybersecurity.py:310-315) */
+} FrzCyberBuffers;
+
+/* One fused step: action decode, movement, presence, subnetwork transitions, rewards, num_moves / truncation,
+ * observations and task counts.  Replaces cybersecurity.py:296-526 + utils/env.py:215-237. */
+int frz_cyber_step(const FrzCyberParams* params, const FrzCyberBuffers* io, int32_t parallel_envs, void* stream);
+int frz_cyber_refresh(const FrzCyberParams* params, const FrzCyberBuffers* io, int32_t parallel_envs, void* stream);
+/* Restore initial rows (env_mask uint8 [B] on device, NULL = all), zero AEC fields, mark "not monitored", refresh.
+ * Replaces utils/env.py:163-189 + cybersecurity.py:274-293. */
+int frz_cyber_reset(const FrzCyberParams* params, const FrzCyberBuffers* io, int32_t parallel_envs,
+                    const uint8_t* env_mask, void* stream);
+/* Uniform random legal actions (replaces action_space(agent).sample_nested(), spaces/actions.py:11-99). */
+int frz_cyber_sample_actions(const FrzCyberParams* params, const FrzCyberBuffers* io, int32_t parallel_envs,
+                             uint64_t sampler_seed, void* stream);
+
 /* ----------------------------------------------------------------------------------------------- common */
 
 int frz_version(void);

@@ -45,3 +45,27 @@ def wildfire_outputs(env) -> dict:
     else:
         out['action_map'] = np.stack([padded_indices(mask[:, a]) for a in range(A)], axis=0)
     return out
+
+
+def cyber_outputs(env) -> dict:
+    raw = env.unwrapped
+    agents = raw.agents
+    s = raw.state()
+    N = raw._n_nodes
+    out = dict(
+        network_state=cpu(s.network_state), location=cpu(s.location), presence=cpu(s.presence),
+        rewards=np.stack([cpu(raw.rewards[a]) for a in agents], axis=1),
+        terminated=np.stack([cpu(raw.terminations[a]) for a in agents], axis=1),
+        truncated=np.stack([cpu(raw.truncations[a]) for a in agents], axis=1),
+        num_moves=cpu(raw.num_moves), env_task_count=cpu(raw.environment_task_count),
+        agent_task_count=cpu(raw.agent_task_count).T,
+        attacker_self=np.stack([cpu(raw.observations[a]['self']) for a in agents if a.startswith('attacker')], axis=1),
+        defender_self=np.stack([cpu(raw.observations[a]['self']) for a in agents if a.startswith('defender')], axis=1),
+        task_obs=np.stack([cpu(raw.observations[a]['tasks']) for a in agents], axis=0),
+        task_store=cpu(raw.task_store),
+    )
+    counts = cpu(raw.agent_task_count).T
+    for i, a in enumerate(agents):
+        out[f'others__{a}'] = cpu(raw.observations[a]['others'])
+        out[f'action_map__{a}'] = padded_indices(np.arange(N)[None, :] < counts[:, i:i + 1])
+    return out
