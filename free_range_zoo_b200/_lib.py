@@ -98,6 +98,33 @@ class CyberBuffers(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in _CY_POINTERS]
 
 
+RS_FAST_TRAVEL = 0x1
+RS_DIAGONAL_TRAVEL = 0x2
+RS_VARIABLE_MOVE_COST = 0x4
+RS_WAITING_COSTS = 0x8
+RS_PASSENGER_COLUMNS = 11
+RS_TASK_COLUMNS = 8
+
+
+class RideshareParams(C.Structure):
+    _fields_ = [
+        ('num_agents', C.c_int32), ('capacity', C.c_int32), ('schedule_rows', C.c_int32), ('pool_limit', C.c_int32),
+        ('max_steps', C.c_int32), ('flags', C.c_uint32), ('env_offset', C.c_int64), ('wait_limit', C.c_int32 * 3),
+        ('long_wait_time', C.c_int32), ('move_cost', C.c_float), ('drop_cost', C.c_float), ('noop_cost', C.c_float),
+        ('accept_cost', C.c_float), ('pool_limit_cost', C.c_float), ('general_wait_cost', C.c_float),
+        ('long_wait_cost', C.c_float),
+    ]
+
+
+_RS_POINTERS = ('agents', 'passengers', 'init_agents', 'init_passengers', 'init_count', 'schedule', 'actions',
+                'rewards', 'cumulative_rewards', 'terminated', 'truncated', 'num_moves', 'env_task_count',
+                'agent_task_count', 'task_mask', 'self_obs', 'task_obs', 'control')
+
+
+class RideshareBuffers(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in _RS_POINTERS]
+
+
 _lib = None
 
 
@@ -124,6 +151,12 @@ def library() -> C.CDLL:
     lib.frz_cyber_reset.argtypes = [C.POINTER(CyberParams), C.POINTER(CyberBuffers), C.c_int32, C.c_void_p, C.c_void_p]
     lib.frz_cyber_sample_actions.argtypes = [C.POINTER(CyberParams), C.POINTER(CyberBuffers), C.c_int32, C.c_uint64,
                                              C.c_void_p]
+    for name in ('frz_rideshare_step', 'frz_rideshare_refresh'):
+        getattr(lib, name).argtypes = [C.POINTER(RideshareParams), C.POINTER(RideshareBuffers), C.c_int32, C.c_void_p]
+    lib.frz_rideshare_reset.argtypes = [C.POINTER(RideshareParams), C.POINTER(RideshareBuffers), C.c_int32, C.c_void_p,
+                                        C.c_void_p]
+    lib.frz_rideshare_sample_actions.argtypes = [C.POINTER(RideshareParams), C.POINTER(RideshareBuffers), C.c_int32,
+                                                 C.c_uint64, C.c_void_p]
     if lib.frz_version() != 1:
         raise RuntimeError(f'libfrz.so ABI version {lib.frz_version()} != 1; rebuild the library')
     _lib = lib

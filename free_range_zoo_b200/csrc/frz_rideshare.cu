@@ -1,0 +1,526 @@
+// Fused rideshare environment step for sm_100a.
+//
+// One launch = for every environment: action decode -> movement -> passenger state (accept conflicts, picks) ->
+// passenger exit -> passenger entry -> rewards -> num_moves / truncation -> reward accumulation -> observations ->
+// task lists.  Replaces, with identical results, the reference's envs/rideshare/env/rideshare.py:249-467,
+// env/transitions/{movement,passenger_state,passenger_exit,passenger_entry}.py and utils/env.py:215-237.
+//
+// The reference keeps all passengers of all environments in one flat table [N_total, 11] sorted by environment and
+// re-sorts / compacts it with `unique`, boolean-mask indexing and a stable `argsort` every step.  Here environment b
+// owns rows passengers[b, 0:count[b]] (same relative order).  One warp owns one environment: the rows are staged in
+// shared memory with coalesced loads, lane p owns table row p (and p+32 when K > 32), lane a owns agent a.  Task
+// lists, conflict detection, compaction and the per-class "last row" reward quirk are ballots, match_any and
+// popcounts; agent -> passenger effects travel through shuffles.
+#include <math_constants.h>
+
+#include "frz_common.cuh"
+
+namespace frz {
+namespace {
+
+constexpr int kRsThreads = 128;
+constexpr int kCols = FRZ_RS_PASSENGER_COLUMNS;
+enum RsMode { kRsStep = 0, kRsRefresh = 1, kRsEntryRefresh = 2 };
+enum Col { cBatch = 0, cY, cX, cDestY, cDestX, cFare, cState, cAssoc, cEntered, cAccepted, cPicked };
+
+// stay, N, E, S, W, NW, NE, SE, SW (transitions/movement.py:27-45)
+__constant__ int kDirY[9] = {0, -1, 0, 1, 0, -1, -1, 1, 1};
+__constant__ int kDirX[9] = {0, 0, 1, 0, -1, -1, 1, 1, -1};
+
+template <int PPL>
+__device__ __forceinline__ uint64_t ballot_rows(const bool (&pred)[PPL]) {
+  uint64_t mask = __ballot_sync(kFullMask, pred[0]);
+  if (PPL == 2) mask |= uint64_t(__ballot_sync(kFullMask, pred[PPL - 1])) << 32;
+  return mask;
+}
+
+__device__ __forceinline__ int select_bit64(uint64_t mask, int k) {
+  const uint32_t lo = uint32_t(mask);
+  const int in_lo = __popc(lo);
+  return k < in_lo ? select_bit(lo, k) : 32 + select_bit(uint32_t(mask >> 32), k - in_lo);
+}
+
+__device__ __forceinline__ float l2(int dy, int dx) { return __fsqrt_rn(float(dy * dy + dx * dx)); }
+
+template <int PPL>
+__global__ void __launch_bounds__(kRsThreads)
+rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid_constant__ FrzRideshareBuffers io,
+                      const int B, const int mode, const uint8_t* __restrict__ entry_mask) {
+  extern __shared__ int smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int K = p.capacity, A = p.num_agents, S = p.schedule_rows;
+  int* table = smem + warp * (K * kCols);
+  const uint32_t lanes_below = (1u << lane) - 1u;
+
+  FrzControl* control = io.control;
+  const uint32_t alive_prev = control->alive;
+  const uint32_t agents_with_tasks = control->agents_with_tasks;
+  const bool skip = (mode == kRsStep) && ((alive_prev & 3u) != 3u);  // utils/env.py:212
+  const bool is_agent = lane < A;
+  const bool fast = p.flags & FRZ_RS_FAST_TRAVEL, diagonal = p.flags & FRZ_RS_DIAGONAL_TRAVEL;
+  const int directions = diagonal ? 9 : 5;
+  unsigned alive_bits = 0, faults = 0, agent_bits = 0;
+
+  if (!skip) {
+    for (int env = blockIdx.x * warps + warp; env < B; env += gridDim.x * warps) {
+      const int n_before = min(io.env_task_count[env], K);
+      int* global_rows = io.passengers + size_t(env) * K * kCols;
+      for (int i = lane; i < n_before * kCols; i += 32) table[i] = global_rows[i];
+      __syncwarp();
+
+      const size_t agent_row = size_t(env) * A;
+      int agent_y = 0, agent_x = 0;
+      if (is_agent) {
+        const int2 at = reinterpret_cast<const int2*>(io.agents)[agent_row + lane];
+        agent_y = at.x;
+        agent_x = at.y;
+      }
+      const int t_now = io.num_moves[env];
+      int n_kept = n_before, fare_won = 0;
+      float move_cost = 0.f;
+      bool noop = false, accept = false;
+
+      if (mode == kRsStep) {
+        // rows owned by this lane
+        int row[PPL][kCols];
+        bool valid[PPL];
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          const int r = lane + 32 * i;
+          valid[i] = r < n_before;
+#pragma unroll
+          for (int c = 0; c < kCols; ++c) row[i][c] = valid[i] ? table[r * kCols + c] : -1;
+        }
+
+        // ---------------------------------------------------------------- task lists (rideshare.py:374-386)
+        bool pred[PPL];
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) pred[i] = valid[i] && row[i][cState] == 0;
+        const uint64_t unaccepted = ballot_rows<PPL>(pred);
+        uint64_t mine = 0;
+        for (int a = 0; a < A; ++a) {
+#pragma unroll
+          for (int i = 0; i < PPL; ++i) pred[i] = valid[i] && row[i][cAssoc] == a;
+          const uint64_t own = ballot_rows<PPL>(pred);
+          if (lane == a) mine = unaccepted | own;
+        }
+
+        // ---------------------------------------------------------------- decode (rideshare.py:255-300)
+        int2 act = make_int2(0, -100);
+        if (is_agent) act = reinterpret_cast<const int2*>(io.actions)[agent_row + lane];
+        noop = act.y == -1;
+        accept = act.y == 0;
+        const bool pick = act.y == 1, drop = act.y == 2;
+        int target = -1;
+        // the reference only resolves targets of agents that have a task in SOME environment (rideshare.py:276)
+        if (is_agent && !noop && ((agents_with_tasks >> lane) & 1u)) {
+          if (act.x >= 0 && act.x < __popcll(mine)) target = select_bit64(mine, act.x);
+          else if (accept || pick || drop) faults |= FRZ_FAULT_BAD_TASK_INDEX;
+        }
+        const bool has_vector = target >= 0 && (accept || pick || drop);
+        int goal_y = 0, goal_x = 0, fare_target = 0;
+        if (has_vector) {
+          const int* t = table + target * kCols;
+          goal_y = drop ? t[cDestY] : t[cY];
+          goal_x = drop ? t[cDestX] : t[cX];
+          fare_target = t[cFare];
+        }
+
+        // ---------------------------------------------------------------- movement (transitions/movement.py:57-116)
+        int move_y = 0, move_x = 0;
+        float distance = CUDART_INF_F;  // agent -> goal before moving (passenger_state.py:48-49)
+        if (has_vector) {
+          distance = l2(agent_y - goal_y, agent_x - goal_x);
+          if (fast) {
+            move_y = goal_y - agent_y;
+            move_x = goal_x - agent_x;
+          } else {
+            float best = CUDART_INF_F;
+            for (int d = 0; d < directions; ++d) {  // first argmin: strict <
+              const float candidate = l2(agent_y + kDirY[d] - goal_y, agent_x + kDirX[d] - goal_x);
+              if (candidate < best) {
+                best = candidate;
+                move_y = kDirY[d];
+                move_x = kDirX[d];
+              }
+            }
+          }
+          move_cost = diagonal ? l2(move_y, move_x) : float(abs(move_y) + abs(move_x));
+        }
+        agent_y += move_y;
+        agent_x += move_x;
+        // riding passengers travel with their driver; association -1 wraps to the last agent like the tensor index
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          int driver = row[i][cAssoc] < 0 ? row[i][cAssoc] + A : row[i][cAssoc];
+          driver = min(max(driver, 0), 31);
+          const int dy = __shfl_sync(kFullMask, move_y, driver), dx = __shfl_sync(kFullMask, move_x, driver);
+          if (valid[i] && row[i][cState] == 2) {
+            row[i][cY] += dy;
+            row[i][cX] += dx;
+          }
+        }
+
+        // ---------------------------------------------------------------- accept conflicts (passenger_state.py:50-74)
+        int claim = (accept && target >= 0) ? target : -1;
+        {
+          const unsigned key = claim >= 0 ? unsigned(claim) : (0x80000000u | unsigned(lane));
+          const bool duplicated = __popc(__match_any_sync(kFullMask, key)) > 1;
+          if (__ballot_sync(kFullMask, duplicated)) {
+            // among ALL duplicated claims of the environment only the closest claimant (first on ties) survives
+            float contest = duplicated ? distance : CUDART_INF_F, closest = contest;
+#pragma unroll
+            for (int offset = 16; offset >= 1; offset >>= 1)
+              closest = fminf(closest, __shfl_xor_sync(kFullMask, closest, offset));
+            const int keeper = __ffs(__ballot_sync(kFullMask, duplicated && contest == closest)) - 1;
+            if (duplicated && lane != keeper) claim = -1;
+          }
+        }
+        const int picked = (pick && target >= 0 && distance < 1e-6f) ? target : -1;  // passenger_state.py:89-92
+        const int dropped = (drop && target >= 0 && distance == 0.f) ? target : -1;   // passenger_exit.py:40-45
+        fare_won = dropped >= 0 ? fare_target : 0;
+
+        // ---------------------------------------------------------------- apply to the rows (accept, then pick, exit)
+        bool keep[PPL];
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) keep[i] = valid[i];
+        for (int a = 0; a < A; ++a) {
+          const int c = __shfl_sync(kFullMask, claim, a);
+#pragma unroll
+          for (int i = 0; i < PPL; ++i) {
+            if (valid[i] && c == lane + 32 * i) {
+              row[i][cState] = 1;
+              row[i][cAccepted] = t_now;
+              row[i][cAssoc] = a;
+            }
+          }
+        }
+        for (int a = 0; a < A; ++a) {
+          const int c = __shfl_sync(kFullMask, picked, a), d = __shfl_sync(kFullMask, dropped, a);
+#pragma unroll
+          for (int i = 0; i < PPL; ++i) {
+            if (valid[i] && c == lane + 32 * i) {
+              row[i][cState] = 2;
+              row[i][cPicked] = t_now;
+            }
+            if (d == lane + 32 * i) keep[i] = false;
+          }
+        }
+
+        // ---------------------------------------------------------------- exit: order-preserving compaction
+        const uint64_t kept = ballot_rows<PPL>(keep);
+        n_kept = __popcll(kept);
+        __syncwarp();  // every read of the old table (targets) is done
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          if (keep[i]) {
+            const uint64_t below = (i == 0) ? uint64_t(lanes_below) : ((uint64_t(lanes_below) << 32) | 0xffffffffull);
+            int* out = table + __popcll(kept & below) * kCols;
+#pragma unroll
+            for (int c = 0; c < kCols; ++c) out[c] = row[i][c];
+          }
+        }
+      }
+
+      // ------------------------------------------------------------------ entry (passenger_entry.py:25-72)
+      int n_rows = n_kept;
+      const bool admits = mode == kRsStep || (mode == kRsEntryRefresh && (entry_mask == nullptr || entry_mask[env]));
+      if (admits) {
+        const int t_entry = (mode == kRsStep) ? t_now + 1 : t_now;  // rideshare.py:307 vs :212
+        const int64_t global_env = p.env_offset + env;
+        int lo = 0, hi = S;  // first schedule row with time >= t_entry (rows are sorted by time)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (io.schedule[mid * 7] < t_entry) lo = mid + 1; else hi = mid;
+        }
+        for (int base = lo; base < S; base += 32) {
+          const int r = base + lane;
+          const bool now = r < S && io.schedule[r * 7] == t_entry;
+          const int batch = now ? io.schedule[r * 7 + 1] : 0;
+          const bool enters = now && (batch == -1 || batch == global_env);
+          const unsigned entering = __ballot_sync(kFullMask, enters);
+          const int slot = n_rows + __popc(entering & lanes_below);
+          if (enters) {
+            if (slot < K) {
+              int* out = table + slot * kCols;
+              const int* s = io.schedule + r * 7;
+              out[cBatch] = env;
+              out[cY] = s[2];
+              out[cX] = s[3];
+              out[cDestY] = s[4];
+              out[cDestX] = s[5];
+              out[cFare] = s[6];
+              out[cState] = 0;
+              out[cAssoc] = -1;
+              out[cEntered] = t_entry;
+              out[cAccepted] = -1;
+              out[cPicked] = -1;
+            } else {
+              faults |= FRZ_FAULT_TABLE_FULL;
+            }
+          }
+          n_rows = min(n_rows + __popc(entering), K);
+          if (__ballot_sync(kFullMask, now) != kFullMask) break;
+        }
+      }
+      __syncwarp();
+
+      // ------------------------------------------------------------------ the new table, one row per lane again
+      int state[PPL], assoc[PPL], stamp[PPL];
+      bool present[PPL];
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        const int r = lane + 32 * i;
+        present[i] = r < n_rows;
+        const int* t = table + r * kCols;
+        state[i] = present[i] ? t[cState] : -1;
+        assoc[i] = present[i] ? t[cAssoc] : -1;
+        stamp[i] = present[i] ? t[state[i] == 0 ? cEntered : (state[i] == 1 ? cAccepted : cPicked)] : 0;
+        // task observation row (rideshare.py:398-416) + padding of rows that just became free
+        if (r < K && (present[i] || r < n_before || mode != kRsStep)) {
+          int4 head = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD), tail = head;
+          if (present[i]) {
+            head = make_int4(t[cY], t[cX], t[cDestY], t[cDestX]);
+            tail = make_int4(state[i] == 1 ? assoc[i] : FRZ_PAD, state[i] == 2 ? assoc[i] : FRZ_PAD, t[cFare], t[cEntered]);
+          }
+          int4* out = reinterpret_cast<int4*>(io.task_obs) + (size_t(env) * K + r) * 2;
+          out[0] = head;
+          out[1] = tail;
+        }
+      }
+
+      // per-agent counts; lane a keeps agent a's
+      int associated = 0, n_accepted = 0, n_riding = 0, n_tasks = 0;
+      bool pred[PPL];
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) pred[i] = present[i] && state[i] == 0;
+      const uint64_t unaccepted = ballot_rows<PPL>(pred);
+      for (int a = 0; a < A; ++a) {
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) pred[i] = present[i] && assoc[i] == a;
+        const uint64_t own = ballot_rows<PPL>(pred);
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) pred[i] = present[i] && assoc[i] == a && state[i] == 1;
+        const uint64_t own_accepted = ballot_rows<PPL>(pred);
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) pred[i] = present[i] && assoc[i] == a && state[i] == 2;
+        const uint64_t own_riding = ballot_rows<PPL>(pred);
+        const uint64_t members = unaccepted | own;
+        if (lane == a) {
+          associated = __popcll(own);
+          n_accepted = __popcll(own_accepted);
+          n_riding = __popcll(own_riding);
+          n_tasks = __popcll(members);
+        }
+        uint8_t* mask_row = io.task_mask + (agent_row + a) * K;
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+          const int r = lane + 32 * i;
+          if (r < K) mask_row[r] = (members >> r) & 1u;
+        }
+      }
+
+      if (mode == kRsStep) {
+        // ---------------------------------------------------------------- rewards (rideshare.py:309-363)
+        float shared = 0.f;
+        if (p.flags & FRZ_RS_WAITING_COSTS) {
+          // `global[idx] += v` with duplicate indices keeps ONE write per statement: the last row of the class
+          int elapsed_unaccepted = 0;
+          bool any_unaccepted = false;
+          for (int cls = 0; cls < 3; ++cls) {
+#pragma unroll
+            for (int i = 0; i < PPL; ++i) pred[i] = present[i] && state[i] == cls;
+            const uint64_t members = ballot_rows<PPL>(pred);
+            if (members) {
+              const int last = 63 - __clzll(members);
+              int when = __shfl_sync(kFullMask, stamp[0], last & 31);
+              if (PPL == 2) {
+                const int upper = __shfl_sync(kFullMask, stamp[PPL - 1], last & 31);
+                when = last >= 32 ? upper : when;
+              }
+              const int elapsed = t_now - when;
+              shared = __fadd_rn(shared, __fmul_rn(elapsed >= p.wait_limit[cls] ? 1.f : 0.f, p.general_wait_cost));
+              if (cls == 0) {
+                any_unaccepted = true;
+                elapsed_unaccepted = elapsed;
+              }
+            }
+          }
+          if (any_unaccepted)
+            shared = __fadd_rn(shared, __fmul_rn(elapsed_unaccepted >= p.long_wait_time ? 1.f : 0.f, p.long_wait_cost));
+          const int free_slots = A * p.pool_limit - n_rows;
+          const float unserved = __fmul_rn(__popcll(unaccepted) >= free_slots ? 1.f : 0.f, -0.5f);
+          shared = __fadd_rn(shared, __fmul_rn(unserved, float(free_slots)));
+        }
+        const int moves = t_now + 1;
+        const bool truncated = moves >= p.max_steps;
+        if (is_agent) {
+          float reward = associated > p.pool_limit ? p.pool_limit_cost : 0.f;
+          reward = __fadd_rn(reward, __fmul_rn(noop ? 1.f : 0.f, p.noop_cost));
+          reward = __fadd_rn(reward, __fmul_rn(accept ? 1.f : 0.f, p.accept_cost));
+          reward = __fadd_rn(reward, fare_won > 0 ? __fadd_rn(float(fare_won), -p.drop_cost) : 0.f);
+          float move_reward = __fmul_rn(move_cost, p.move_cost);
+          if (p.flags & FRZ_RS_VARIABLE_MOVE_COST) move_reward = __fdiv_rn(move_reward, float(associated + 1));
+          reward = __fadd_rn(reward, move_reward);
+          reward = __fadd_rn(reward, shared);
+          io.rewards[agent_row + lane] = reward;
+          io.cumulative_rewards[agent_row + lane] = __fadd_rn(io.cumulative_rewards[agent_row + lane], reward);
+          reinterpret_cast<int2*>(io.agents)[agent_row + lane] = make_int2(agent_y, agent_x);
+        }
+        if (lane == 0) {
+          io.num_moves[env] = moves;
+          io.truncated[env] = truncated;
+        }
+        alive_bits |= 1u | (truncated ? 0u : 2u);  // rideshare never terminates (rideshare.py:252)
+      }
+
+      // ------------------------------------------------------------------ publish
+      if (is_agent) {
+        io.agent_task_count[agent_row + lane] = n_tasks;
+        if (n_tasks > 0) agent_bits |= 1u << lane;
+        reinterpret_cast<int4*>(io.self_obs)[agent_row + lane] = make_int4(agent_y, agent_x, n_accepted, n_riding);
+      }
+      if (lane == 0) io.env_task_count[env] = n_rows;
+      if (admits)
+        for (int i = lane; i < n_rows * kCols; i += 32) global_rows[i] = table[i];
+      __syncwarp();
+    }
+  }
+  finish_launch(control, alive_bits, faults, agent_bits,
+                skip ? kPublishNothing : (mode == kRsStep ? kPublishStep : kPublishRefresh));
+}
+
+__global__ void rideshare_restore_kernel(const FrzRideshareParams p, const FrzRideshareBuffers io, const int B,
+                                         const uint8_t* __restrict__ env_mask) {
+  const int A = p.num_agents, K = p.capacity;
+  const int per_env = K * kCols;
+  const size_t total = size_t(B) * per_env;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int env = int(i / per_env), j = int(i % per_env);
+    if (env_mask != nullptr && !env_mask[env]) continue;
+    io.passengers[i] = io.init_passengers[i];
+    if (j < 2 * A) io.agents[size_t(env) * 2 * A + j] = io.init_agents[size_t(env) * 2 * A + j];
+    if (j < A) {
+      io.rewards[size_t(env) * A + j] = 0.f;
+      io.cumulative_rewards[size_t(env) * A + j] = 0.f;
+    }
+    if (j == 0) {
+      io.env_task_count[env] = io.init_count[env];
+      io.terminated[env] = 0;
+      io.truncated[env] = 0;
+      io.num_moves[env] = 0;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) io.control->alive = 3u;
+}
+
+// Uniform over [task 0 .. task n-1, noop]; the action id of a task is the passenger's state (0 accept / 1 pick /
+// 2 drop), which is the only id the reference's action space offers for it (spaces/actions.py:10-50).
+__global__ void rideshare_sample_kernel(const FrzRideshareParams p, const FrzRideshareBuffers io, const int B,
+                                        const uint64_t sampler_seed) {
+  const int A = p.num_agents, K = p.capacity;
+  const Philox philox(sampler_seed);
+  const uint64_t step = io.control->step;
+  const int total = B * A;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int env = i / A, agent = i - env * A;
+    const int n = io.agent_task_count[i];
+    const uint64_t genv = uint64_t(p.env_offset + env);
+    const uint4 r = philox(uint32_t(genv), uint32_t(step), 0xC0000000u | uint32_t(agent), uint32_t(step >> 32) ^ uint32_t(genv >> 32));
+    const int k = min(int(u01(r.x) * float(n + 1)), n);
+    int ident = -1;
+    if (k < n) {
+      const uint8_t* mask = io.task_mask + size_t(i) * K;
+      int seen = 0;
+      for (int row = 0; row < K; ++row) {
+        if (mask[row]) {
+          if (seen == k) {
+            const int* obs = io.task_obs + (size_t(env) * K + row) * FRZ_RS_TASK_COLUMNS;
+            ident = obs[5] != FRZ_PAD ? 2 : (obs[4] != FRZ_PAD ? 1 : 0);
+            break;
+          }
+          ++seen;
+        }
+      }
+    }
+    reinterpret_cast<int2*>(const_cast<int32_t*>(io.actions))[i] = make_int2(k, ident);
+  }
+}
+
+int rideshare_validate(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, const char* what) {
+  if (p == nullptr || io == nullptr || io->control == nullptr || io->passengers == nullptr || io->agents == nullptr ||
+      (p->schedule_rows > 0 && io->schedule == nullptr)) {
+    set_error("%s: NULL params / buffers", what);
+    return FRZ_ERR_NULL;
+  }
+  if (B <= 0 || p->num_agents < 1 || p->num_agents > FRZ_MAX_AGENTS || p->capacity < 1 ||
+      p->capacity > FRZ_MAX_PASSENGERS || p->schedule_rows < 0) {
+    set_error("%s: unsupported shape B=%d agents=%d capacity=%d schedule=%d", what, B, p->num_agents, p->capacity,
+              p->schedule_rows);
+    return FRZ_ERR_SHAPE;
+  }
+  return FRZ_OK;
+}
+
+int rideshare_launch(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, int mode, void* stream,
+                     const uint8_t* entry_mask = nullptr) {
+  const int warps = kRsThreads / 32;
+  const size_t smem = size_t(warps) * p->capacity * kCols * sizeof(int);
+  const int grid = persistent_grid((B + warps - 1) / warps, 12);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->capacity <= 32) rideshare_step_kernel<1><<<grid, kRsThreads, smem, s>>>(*p, *io, B, mode, entry_mask);
+  else rideshare_step_kernel<2><<<grid, kRsThreads, smem, s>>>(*p, *io, B, mode, entry_mask);
+  return check_launch("rideshare_step_kernel");
+}
+
+}  // namespace
+}  // namespace frz
+
+extern "C" {
+
+int frz_rideshare_step(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
+                       void* stream) {
+  const int status = frz::rideshare_validate(params, io, parallel_envs, "frz_rideshare_step");
+  if (status != FRZ_OK) return status;
+  if (io->actions == nullptr) {
+    frz::set_error("frz_rideshare_step: actions is NULL");
+    return FRZ_ERR_NULL;
+  }
+  return frz::rideshare_launch(params, io, parallel_envs, frz::kRsStep, stream);
+}
+
+int frz_rideshare_refresh(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
+                          void* stream) {
+  const int status = frz::rideshare_validate(params, io, parallel_envs, "frz_rideshare_refresh");
+  if (status != FRZ_OK) return status;
+  return frz::rideshare_launch(params, io, parallel_envs, frz::kRsRefresh, stream);
+}
+
+int frz_rideshare_reset(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
+                        const uint8_t* env_mask, void* stream) {
+  int status = frz::rideshare_validate(params, io, parallel_envs, "frz_rideshare_reset");
+  if (status != FRZ_OK) return status;
+  if (io->init_agents == nullptr || io->init_passengers == nullptr || io->init_count == nullptr) {
+    frz::set_error("frz_rideshare_reset: initial state is NULL");
+    return FRZ_ERR_NULL;
+  }
+  const size_t total = size_t(parallel_envs) * params->capacity * FRZ_RS_PASSENGER_COLUMNS;
+  const int grid = frz::persistent_grid(int((total + 255) / 256), 8);
+  frz::rideshare_restore_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*params, *io, parallel_envs, env_mask);
+  status = frz::check_launch("rideshare_restore_kernel");
+  if (status != FRZ_OK) return status;
+  // only the environments being reset admit their t = 0 passengers; the others are merely re-published
+  return frz::rideshare_launch(params, io, parallel_envs, frz::kRsEntryRefresh, stream, env_mask);
+}
+
+int frz_rideshare_sample_actions(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
+                                 uint64_t sampler_seed, void* stream) {
+  const int status = frz::rideshare_validate(params, io, parallel_envs, "frz_rideshare_sample_actions");
+  if (status != FRZ_OK) return status;
+  const int total = parallel_envs * params->num_agents;
+  const int grid = frz::persistent_grid((total + 255) / 256, 8);
+  frz::rideshare_sample_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*params, *io, parallel_envs, sampler_seed);
+  return frz::check_launch("rideshare_sample_kernel");
+}
+
+}  // extern "C"

@@ -81,3 +81,12 @@ def jagged_indices_from_mask(mask: torch.Tensor) -> torch.Tensor:
     offsets = torch.zeros(mask.shape[0] + 1, dtype=torch.int64, device=mask.device)
     offsets[1:] = torch.cumsum(counts, dim=0)
     return torch.nested.nested_tensor_from_jagged(values, offsets=offsets)
+
+
+def jagged_rows_from_mask(values: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Dense ``[B, K, C]`` + boolean ``[B, K]`` -> jagged ``[B, j, C]`` keeping the selected rows of each batch entry
+    in order (the per-agent task observations of rideshare, rideshare.py:436-455)."""
+    counts = mask.sum(dim=1)
+    offsets = torch.zeros(mask.shape[0] + 1, dtype=torch.int64, device=mask.device)
+    offsets[1:] = torch.cumsum(counts, dim=0)
+    return torch.nested.nested_tensor_from_jagged(values[mask], offsets=offsets)

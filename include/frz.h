@@ -242,6 +242,70 @@ int frz_cyber_reset(const FrzCyberParams* params, const FrzCyberBuffers* io, int
 int frz_cyber_sample_actions(const FrzCyberParams* params, const FrzCyberBuffers* io, int32_t parallel_envs,
                              uint64_t sampler_seed, void* stream);
 
+/* ----------------------------------------------------------------------------------------------- rideshare */
+
+#define FRZ_RS_FAST_TRAVEL 0x1u          /* AgentConfiguration.use_fast_travel (configuration.py:83-110) */
+#define FRZ_RS_DIAGONAL_TRAVEL 0x2u      /* AgentConfiguration.use_diagonal_travel */
+#define FRZ_RS_VARIABLE_MOVE_COST 0x4u   /* RewardConfiguration.use_variable_move_cost */
+#define FRZ_RS_WAITING_COSTS 0x8u        /* RewardConfiguration.use_waiting_costs */
+#define FRZ_RS_PASSENGER_COLUMNS 11      /* (batch, y, x, dest_y, dest_x, fare, state, assoc, entered, accepted, picked) */
+#define FRZ_RS_TASK_COLUMNS 8            /* (y, x, dest_y, dest_x, accepted_by, riding_by, fare, entered) */
+
+/* RideshareConfiguration flattened once at construction. */
+typedef struct {
+  int32_t num_agents;
+  int32_t capacity;        /* K: rows of the per-environment passenger table (<= FRZ_MAX_PASSENGERS) */
+  int32_t schedule_rows;   /* S */
+  int32_t pool_limit;
+  int32_t max_steps;
+  uint32_t flags;
+  int64_t env_offset;      /* global index of local env 0: schedule rows name global environment indices */
+  int32_t wait_limit[3];   /* RewardConfiguration.wait_limit: unaccepted / accepted / riding */
+  int32_t long_wait_time;
+  float move_cost, drop_cost, noop_cost, accept_cost, pool_limit_cost, general_wait_cost, long_wait_cost;
+} FrzRideshareParams;
+
+typedef struct {
+  /* RideshareState (structures/state.py:11-22).  The reference keeps one flat table [N_total, 11] sorted by
+   * environment; here environment b owns rows passengers[b, 0 : env_task_count[b]] in the same order (rows beyond
+   * the count are undefined). */
+  int32_t* agents;           /* [B, A, 2] (y, x) */
+  int32_t* passengers;       /* [B, K, 11] */
+  const int32_t* init_agents;        /* [B, A, 2] */
+  const int32_t* init_passengers;    /* [B, K, 11] table before the t = 0 entry (normally empty) */
+  const int32_t* init_count;         /* [B] */
+  const int32_t* schedule;   /* [S, 7] (t, batch | -1, y, x, dest_y, dest_x, fare), stably sorted by t */
+  /* AEC runtime */
+  const int32_t* actions;    /* [B, A, 2] (agent-local task index, action id: 0 accept, 1 pick, 2 drop, -1 noop) */
+  float* rewards;            /* [B, A] */
+  float* cumulative_rewards; /* [B, A] */
+  uint8_t* terminated;       /* [B] (never set: rideshare.py:252) */
+  uint8_t* truncated;        /* [B] */
+  int32_t* num_moves;        /* [B] */
+  /* update_actions / update_observations (rideshare.py:368-467) */
+  int32_t* env_task_count;   /* [B] passengers present == valid rows of the table */
+  int32_t* agent_task_count; /* [B, A] */
+  uint8_t* task_mask;        /* [B, A, K] 1 iff table row p is in the agent's task list (unaccepted or its own) */
+  int32_t* self_obs;         /* [B, A, 4] (y, x, #accepted, #riding) */
+  int32_t* task_obs;         /* [B, K, 8] one row per passenger in table order, padded with FRZ_PAD */
+  FrzControl* control;
+} FrzRideshareBuffers;
+
+/* One fused step: action decode, movement, passenger state / exit / entry transitions, rewards, num_moves /
+ * truncation, observations, task lists.  Replaces rideshare.py:249-467 + env/transitions/*.py + utils/env.py:215-237. */
+int frz_rideshare_step(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
+                       void* stream);
+int frz_rideshare_refresh(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
+                          void* stream);
+/* Restore agents + the pre-entry table of the envs selected by env_mask (NULL = all), zero their AEC fields, let the
+ * t = 0 passengers enter (rideshare.py:212) and refresh.  The reference raises NotImplementedError for the partial
+ * form (rideshare.py:231-246); it is implemented here to the evident intent. */
+int frz_rideshare_reset(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
+                        const uint8_t* env_mask, void* stream);
+/* Uniform random legal actions: task k with id = passenger state, or noop (spaces/actions.py:10-50). */
+int frz_rideshare_sample_actions(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
+                                 uint64_t sampler_seed, void* stream);
+
 /* ----------------------------------------------------------------------------------------------- common */
 
 int frz_version(void);

@@ -69,3 +69,45 @@ def cyber_outputs(env) -> dict:
         out[f'others__{a}'] = cpu(raw.observations[a]['others'])
         out[f'action_map__{a}'] = padded_indices(np.arange(N)[None, :] < counts[:, i:i + 1])
     return out
+
+
+def _widen(array: np.ndarray, axis: int, width: int) -> np.ndarray:
+    """Pad ``array`` with -100 along ``axis`` up to ``width`` (golden tables are as wide as the whole schedule)."""
+    if array.shape[axis] >= width:
+        return array
+    shape = list(array.shape)
+    shape[axis] = width - array.shape[axis]
+    return np.concatenate([array, np.full(shape, PAD, array.dtype)], axis=axis)
+
+
+def rideshare_outputs(env, width: int) -> dict:
+    raw = env.unwrapped
+    agents = raw.agents
+    s = raw.state()
+    K = raw._capacity
+    counts = cpu(raw.environment_task_count)
+    valid = np.arange(K)[None, :] < counts[:, None]
+    table = cpu(s.passenger_table).copy()
+    table[:, :, 0] = np.arange(table.shape[0])[:, None]
+    table[~valid] = PAD
+    mask = cpu(raw.task_mask)  # [B, A, K]
+    task_store = cpu(raw._task_obs)
+    task_obs, action_map = [], []
+    for i in range(len(agents)):
+        per_agent = np.full_like(task_store, PAD)
+        for b in range(task_store.shape[0]):
+            rows = np.nonzero(mask[b, i])[0]
+            per_agent[b, :len(rows)] = task_store[b, rows]
+        task_obs.append(per_agent)
+        action_map.append(padded_indices(mask[:, i]))
+    return dict(
+        agents=cpu(s.agents), passengers=_widen(table, 1, width), passenger_count=counts,
+        rewards=np.stack([cpu(raw.rewards[a]) for a in agents], axis=1),
+        terminated=np.stack([cpu(raw.terminations[a]) for a in agents], axis=1),
+        truncated=np.stack([cpu(raw.truncations[a]) for a in agents], axis=1),
+        num_moves=cpu(raw.num_moves), env_task_count=counts, agent_task_count=cpu(raw.agent_task_count).T,
+        self_obs=np.stack([cpu(raw.observations[a]['self']) for a in agents], axis=1),
+        others_obs=np.stack([cpu(raw.observations[a]['others']) for a in agents], axis=0),
+        task_store=_widen(task_store, 1, width), task_obs=_widen(np.stack(task_obs, axis=0), 2, width),
+        action_map=_widen(np.stack(action_map, axis=0), 2, width),
+    )

@@ -1,0 +1,143 @@
+"""GPU parity tests of the fused rideshare step (through the C ABI, via the public Parallel API)."""
+import numpy as np
+import pytest
+import torch
+
+from free_range_zoo_b200 import presets
+from tests import golden_util as G
+from tests.engine_util import cpu, rideshare_outputs
+
+pytestmark = pytest.mark.gpu
+
+
+def make_env(config, B, max_steps, **kwargs):
+    from free_range_zoo_b200.envs import rideshare_v0
+    return rideshare_v0.parallel_env(parallel_envs=B, max_steps=max_steps, configuration=config,
+                                     device=torch.device('cuda'), **kwargs)
+
+
+@pytest.mark.parametrize('name', G.fixtures('rideshare'))
+def test_matches_reference_trajectory(name):
+    meta, gold = G.load(name)
+    config = getattr(presets, meta['preset'])(**meta['preset_kwargs'])
+    env = make_env(config, meta['B'], meta['max_steps'])
+    env.reset(seed=0)
+    width = gold['passengers'].shape[2]
+    G.compare(rideshare_outputs(env, width), gold, 0, context=name)
+    for t in range(meta['steps']):
+        actions = torch.from_numpy(gold['actions'][t]).cuda()
+        env.step({a: actions[:, i] for i, a in enumerate(env.agents)})
+        G.compare(rideshare_outputs(env, width), gold, t + 1, context=name)
+    env.unwrapped.check_errors()
+
+
+def policy_actions(oracle, rng, wild):
+    """Random task or noop per agent; the action id is the passenger's state, or (with probability ``wild``) any of
+    accept / pick / drop -- ids the reference's step code accepts without complaint."""
+    B, A = oracle.B, oracle.A
+    acts = np.zeros((B, A, 2), np.int32)
+    for b in range(B):
+        for a in range(A):
+            mine = oracle._task_list(b, a)
+            k = min(int(rng.random() * (len(mine) + 1)), len(mine))
+            if k == len(mine):
+                acts[b, a] = (k, -1)
+            else:
+                ident = oracle.tables[b][mine[k]][6]
+                if rng.random() < wild:
+                    ident = int(rng.integers(0, 3))
+                acts[b, a] = (k, ident)
+    return acts
+
+
+@pytest.mark.parametrize('preset,preset_kwargs,B,steps,wild', [
+    ('rideshare_c2', {}, 512, 90, 0.0),
+    ('rideshare_c2', {}, 300, 60, 0.3),
+    ('rideshare_quirks', dict(parallel_envs=200), 200, 40, 0.2),
+    ('rideshare_quirks', dict(parallel_envs=128, diagonal=False, fast=True), 128, 40, 0.1),
+    ('rideshare_profile', {}, 100, 20, 0.0),
+])
+def test_matches_oracle_on_random_rollouts(preset, preset_kwargs, B, steps, wild):
+    from oracle.rideshare import RideshareOracle
+    config = getattr(presets, preset)(**preset_kwargs)
+    oracle = RideshareOracle(config, B, steps)
+    oracle.reset()
+    env = make_env(config, B, steps)
+    env.reset(seed=1)
+    rng = np.random.default_rng(17)
+    width = oracle.K
+    for t in range(steps):
+        actions = policy_actions(oracle, rng, wild)
+        assert oracle.step(actions)
+        env.step(torch.from_numpy(actions).cuda())
+        want = {key: value[None] for key, value in oracle.outputs().items()}
+        G.compare(rideshare_outputs(env, width), want, 0, context=f'{preset} t={t}')
+    env.unwrapped.check_errors()
+
+
+def test_full_size_sampler_rollout_properties():
+    """C2 at its full size (16,384 envs): invariants of any legal rollout, driven by the on-device sampler."""
+    B = 16384
+    env = make_env(presets.rideshare_c2(), B, 100)
+    env.reset(seed=3)
+    raw = env.unwrapped
+    total = torch.zeros((B, 4), device='cuda')
+    delivered = torch.zeros(B, device='cuda')
+    for t in range(100):
+        before = raw.environment_task_count.clone()
+        raw.sample_actions(41)
+        raw.step_all()
+        total += raw._rewards
+        s = raw.state()
+        K = raw._capacity
+        valid = torch.arange(K, device='cuda')[None, :] < s.passenger_count[:, None]
+        table = s.passenger_table
+        # every present passenger and every driver stays on the 10x10 grid
+        assert ((table[..., 1:5][valid] >= 0) & (table[..., 1:5][valid] <= 9)).all()
+        assert ((s.agents >= 0) & (s.agents <= 9)).all()
+        states = table[..., 6]
+        assert ((states[valid] >= 0) & (states[valid] <= 2)).all()
+        # accepted / riding passengers are associated with a driver, unaccepted ones are not
+        assert (table[..., 7][valid & (states > 0)] >= 0).all() and (table[..., 7][valid & (states == 0)] == -1).all()
+        # rows are in entry order (stable compaction) and padding rows of the observation are -100
+        entered = torch.where(valid, table[..., 8], 10**6)
+        assert (entered[:, 1:] >= entered[:, :-1]).all()
+        assert (raw._task_obs[~valid] == -100).all()
+        # the agent task lists are exactly: unaccepted or own
+        mask = raw.task_mask
+        expect = valid[:, None, :] & ((states[:, None, :] == 0) | (table[..., 7][:, None, :] == torch.arange(4, device='cuda')[None, :, None]))
+        assert torch.equal(mask, expect)
+        assert torch.equal(mask.sum(2).int(), raw._agent_task_count)
+        # self observation counts
+        for a in range(4):
+            own = valid & (table[..., 7] == a)
+            assert torch.equal(raw._self_obs[:, a, 2], (own & (states == 1)).sum(1).int())
+            assert torch.equal(raw._self_obs[:, a, 3], (own & (states == 2)).sum(1).int())
+    assert torch.allclose(total, raw._cumulative, rtol=1e-5, atol=1e-3)
+    assert (raw.num_moves == 100).all() and raw.truncated.all() and not raw.terminated.any()
+    raw.check_errors()
+
+
+def test_flat_table_view_and_partial_reset():
+    env = make_env(presets.rideshare_c2(), 64, 100)
+    env.reset(seed=4)
+    raw = env.unwrapped
+    first = raw.state().passengers.clone()
+    assert first.shape[1] == 11 and (first[:, 8] == 0).all()
+    for _ in range(15):
+        raw.sample_actions(9)
+        raw.step_all()
+    flat = raw.state().passengers
+    assert flat.shape[0] == int(raw.environment_task_count.sum())
+    assert (flat[1:, 0] >= flat[:-1, 0]).all()  # sorted by environment like the reference's flat table
+    moved = raw.state().clone()
+    picked = torch.tensor([1, 7, 63], device='cuda')
+    env.reset_batches(picked)
+    torch.cuda.synchronize()
+    assert (raw.num_moves[picked] == 0).all() and (raw.num_moves[0] == 15)
+    assert torch.equal(raw.state().agents[picked], raw._init_agents[picked])
+    assert torch.equal(raw.state().agents[0], moved.agents[0])
+    again = raw.state().passengers
+    assert torch.equal(again[again[:, 0] == 7][:, 1:], first[first[:, 0] == 7][:, 1:])
+    assert torch.equal(raw.state().passenger_table[0, :int(moved.passenger_count[0])],
+                       moved.passenger_table[0, :int(moved.passenger_count[0])])
