@@ -69,24 +69,22 @@ def jagged_from_padded(padded: torch.Tensor, counts: torch.Tensor, dtype: torch.
     values = padded[keep]
     if dtype is not None:
         values = values.to(dtype)
-    offsets = torch.zeros(counts.shape[0] + 1, dtype=torch.int64, device=padded.device)
+    return _jagged(values, counts)
+
+
+def _jagged(values: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    offsets = torch.zeros(counts.shape[0] + 1, dtype=torch.int64, device=values.device)
     offsets[1:] = torch.cumsum(counts, dim=0)
-    return torch.nested.nested_tensor_from_jagged(values, offsets=offsets)
+    longest = int(counts.max().item()) if counts.numel() else 0
+    return torch.nested.nested_tensor_from_jagged(values, offsets=offsets, min_seqlen=0, max_seqlen=max(longest, 1))
 
 
 def jagged_indices_from_mask(mask: torch.Tensor) -> torch.Tensor:
     """Boolean ``[B, T]`` -> jagged int64 ``[B, j]`` holding the positions of the set entries of each row."""
-    counts = mask.sum(dim=1)
-    values = mask.nonzero(as_tuple=False)[:, 1]
-    offsets = torch.zeros(mask.shape[0] + 1, dtype=torch.int64, device=mask.device)
-    offsets[1:] = torch.cumsum(counts, dim=0)
-    return torch.nested.nested_tensor_from_jagged(values, offsets=offsets)
+    return _jagged(mask.nonzero(as_tuple=False)[:, 1], mask.sum(dim=1))
 
 
 def jagged_rows_from_mask(values: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """Dense ``[B, K, C]`` + boolean ``[B, K]`` -> jagged ``[B, j, C]`` keeping the selected rows of each batch entry
     in order (the per-agent task observations of rideshare, rideshare.py:436-455)."""
-    counts = mask.sum(dim=1)
-    offsets = torch.zeros(mask.shape[0] + 1, dtype=torch.int64, device=mask.device)
-    offsets[1:] = torch.cumsum(counts, dim=0)
-    return torch.nested.nested_tensor_from_jagged(values[mask], offsets=offsets)
+    return _jagged(values[mask], mask.sum(dim=1))

@@ -28,6 +28,37 @@ def danger_score(patches: np.ndarray, attacks: np.ndarray, temperature) -> np.nd
     return torch.tanh(diff / torch.tensor(float(temperature), dtype=torch.float32)).numpy()
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The three transitions as pure functions (tests/test_oracle_kat.py feeds them the reference's unit-test inputs).
+
+
+def movement(location, targets, mask):
+    """transitions/movement.py:17-32."""
+    return np.where(mask, targets, location).astype(np.int32)
+
+
+def presence_transition(presence, location, u, persist, returns, num_attackers):
+    """transitions/presence.py:35-60; returns (presence, location)."""
+    returning = ~presence & (u < returns)
+    leaving = presence & (u >= persist)
+    new_presence = (presence | returning) & ~leaving
+    new_location = np.where(returning[:, num_attackers:], -1, location).astype(np.int32)
+    return new_presence, new_location
+
+
+def subnetwork(network_state, patches, attacks, u, temperature, stochastic, num_states):
+    """transitions/subnetwork.py:40-72."""
+    score = danger_score(patches, attacks, temperature)
+    if stochastic:
+        magnitude = np.abs(score)
+        better = (score > 0) & (magnitude <= u)
+        worse = (score < 0) & (magnitude <= u)
+    else:
+        better, worse = score > 0, score < 0
+    state = network_state - better.astype(np.int32) + worse.astype(np.int32)
+    return np.clip(state, 0, num_states - 1).astype(np.int32)
+
+
 class CybersecurityOracle:
     """Reference semantics of ``cybersecurity_v0`` for one batch; agents are ordered attackers then defenders."""
 
@@ -150,23 +181,11 @@ class CybersecurityOracle:
                 rewards[patch, agent] += self.patch_reward  # :376
                 # :379-381 -- patch already requires location != -1, so the bad-action penalty never fires
 
-        self.location = np.where(move_mask, move_target, self.location)  # transitions/movement.py:30
-        # transitions/presence.py:35-60
-        r = u_agent[0]
-        returning = ~self.presence & (r < self.returns)
-        leaving = self.presence & (r >= self.persist)
-        self.presence = (self.presence | returning) & ~leaving
-        self.location = np.where(returning[:, self.n_att:], -1, self.location).astype(np.int32)
-        # transitions/subnetwork.py:40-72
-        score = danger_score(patches, attacks, self.temperature)
-        if self.stochastic:
-            magnitude = np.abs(score)
-            better = (score > 0) & (magnitude <= u_network[0])
-            worse = (score < 0) & (magnitude <= u_network[0])
-        else:
-            better, worse = score > 0, score < 0
-        state = self.network_state - better.astype(np.int32) + worse.astype(np.int32)
-        self.network_state = np.clip(state, 0, self.num_states - 1).astype(np.int32)
+        self.location = movement(self.location, move_target, move_mask)
+        self.presence, self.location = presence_transition(self.presence, self.location, u_agent[0], self.persist,
+                                                           self.returns, self.n_att)
+        self.network_state = subnetwork(self.network_state, patches, attacks, u_network[0], self.temperature,
+                                        self.stochastic, self.num_states)
         # rewards, cybersecurity.py:395-409: matmul([B,N] f32, criticality f32 [N]) accumulated in node order
         node_rewards = self.state_rewards[self.network_state]
         network = np.zeros(B, np.float32)

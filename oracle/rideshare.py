@@ -113,6 +113,59 @@ class RideshareOracle:
                 table[b, :len(rows)] = rows
         return table
 
+    # ------------------------------------------------------------------ transitions (one environment at a time)
+
+    def movement(self, b: int, vector):
+        """transitions/movement.py:94-116: move every agent one step towards its goal; riding passengers follow their
+        driver.  Returns the distance cost of each agent."""
+        cost = np.zeros(self.A, np.float32)
+        moves = []
+        for a in range(self.A):
+            move, cost[a] = self._move(vector[a][:2], vector[a][2:])
+            moves.append(move)
+            self.agents[b, a, 0] += move[0]
+            self.agents[b, a, 1] += move[1]
+        for p in self.tables[b]:
+            if p[STATE] == 2:
+                move = moves[p[ASSOC]]  # ASSOC == -1 wraps to the last agent, exactly like the tensor index does
+                p[Y] += move[0]
+                p[X] += move[1]
+        return cost
+
+    def passenger_state(self, b: int, accept, pick, target, vector, t_now: int):
+        """transitions/passenger_state.py:24-100; distances come from the PRE-move vectors.  Returns them."""
+        A, table = self.A, self.tables[b]
+        dist = [np.inf if v[0] == PAD else _norm(v[0] - v[2], v[1] - v[3]) for v in vector]
+        claims = [target[a] if accept[a] else PAD for a in range(A)]
+        duplicated = [claims[a] != PAD and claims.count(claims[a]) > 1 for a in range(A)]
+        if any(duplicated):  # among ALL duplicated claims of the env only the closest claimant (first on ties) survives
+            contest = [dist[a] if duplicated[a] else np.inf for a in range(A)]
+            keep = int(np.argmin(np.array(contest, dtype=np.float32)))
+            for a in range(A):
+                if duplicated[a] and a != keep:
+                    claims[a] = PAD
+        for a in range(A):
+            if claims[a] != PAD:
+                p = table[claims[a]]
+                p[STATE], p[ACCEPTED], p[ASSOC] = 1, t_now, a
+        for a in range(A):
+            if pick[a] and target[a] != PAD and dist[a] < 1e-6:
+                p = table[target[a]]
+                p[STATE], p[PICKED] = 2, t_now
+        return dist
+
+    def passenger_exit(self, b: int, drop, target, dist):
+        """transitions/passenger_exit.py:23-56: a drop succeeds iff the driver stood on the destination."""
+        table = self.tables[b]
+        fares = np.zeros(self.A, np.int32)
+        finished = set()
+        for a in range(self.A):
+            if drop[a] and target[a] != PAD and dist[a] == 0:
+                fares[a] = table[target[a]][FARE]
+                finished.add(target[a])
+        self.tables[b] = [p for i, p in enumerate(table) if i not in finished]
+        return fares
+
     # ------------------------------------------------------------------ step
 
     def _move(self, start, goal):
@@ -161,44 +214,10 @@ class RideshareOracle:
                     vector[a] = (self.agents[b, a, 0], self.agents[b, a, 1], p[Y], p[X])
                 elif drop[a]:
                     vector[a] = (self.agents[b, a, 0], self.agents[b, a, 1], p[DEST_Y], p[DEST_X])
-            # ---- movement (transitions/movement.py:94-116); riding passengers move with their driver
-            moves, cost = [], np.zeros(A, np.float32)
-            for a in range(A):
-                move, cost[a] = self._move(vector[a][:2], vector[a][2:])
-                moves.append(move)
-                self.agents[b, a, 0] += move[0]
-                self.agents[b, a, 1] += move[1]
-            for p in table:
-                if p[STATE] == 2:
-                    move = moves[p[ASSOC]]  # ASSOC == -1 wraps to the last agent, exactly like the tensor index does
-                    p[Y] += move[0]
-                    p[X] += move[1]
-            # ---- passenger state (transitions/passenger_state.py:24-100), distances from the PRE-move vectors
-            dist = [np.inf if v[0] == PAD else _norm(v[0] - v[2], v[1] - v[3]) for v in vector]
-            claims = [target[a] if accept[a] else PAD for a in range(A)]
-            duplicated = [claims[a] != PAD and claims.count(claims[a]) > 1 for a in range(A)]
-            if any(duplicated):
-                contest = [dist[a] if duplicated[a] else np.inf for a in range(A)]
-                keep = int(np.argmin(np.array(contest, dtype=np.float32)))
-                for a in range(A):
-                    if duplicated[a] and a != keep:
-                        claims[a] = PAD
-            for a in range(A):
-                if claims[a] != PAD:
-                    p = table[claims[a]]
-                    p[STATE], p[ACCEPTED], p[ASSOC] = 1, t_now, a
-            for a in range(A):
-                if pick[a] and target[a] != PAD and dist[a] < 1e-6:
-                    p = table[target[a]]
-                    p[STATE], p[PICKED] = 2, t_now
-            # ---- exit (transitions/passenger_exit.py:23-56)
-            fares = np.zeros(A, np.int32)
-            finished = set()
-            for a in range(A):
-                if drop[a] and target[a] != PAD and dist[a] == 0:
-                    fares[a] = table[target[a]][FARE]
-                    finished.add(target[a])
-            self.tables[b] = table = [p for i, p in enumerate(table) if i not in finished]
+            cost = self.movement(b, vector)
+            dist = self.passenger_state(b, accept, pick, target, vector, t_now)
+            fares = self.passenger_exit(b, drop, target, dist)
+            table = self.tables[b]
             # ---- entry at num_moves + 1 (rideshare.py:307)
             for row in self.schedule:
                 if row[0] == t_now + 1 and (row[1] == b or row[1] == -1):

@@ -46,6 +46,114 @@ def spread_lut(weights: np.ndarray) -> np.ndarray:
     return lut
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The seven transitions as pure functions over numpy arrays (state arrays are updated in place where the reference
+# mutates its state).  ``WildfireOracle.step`` chains them; tests/test_oracle_kat.py feeds them the inputs of the
+# reference's own transition unit tests.
+
+
+def suppressant_decrease(suppressants, users, u, stochastic, p):
+    """transitions/suppressant_decrease.py:34-63."""
+    decrease = users & (u < F32(p)) if stochastic else users
+    return np.maximum(np.where(decrease, suppressants - F32(1), suppressants), F32(0)).astype(np.float32)
+
+
+def equipment_transition(equipment, u, num_states, stochastic_repair, p_repair, stochastic_degrade, p_degrade,
+                         critical_error, p_critical):
+    """transitions/equipment.py:42-77 -- all masks from the pre-update equipment, one uniform for the three tests."""
+    pristine = equipment == num_states - 1
+    damaged = equipment == 0
+    intermediate = ~pristine & ~damaged
+    repairs = damaged & (u < F32(p_repair)) if stochastic_repair else damaged
+    updated = equipment.copy()
+    updated[repairs] = num_states - 1
+    criticals = np.zeros_like(pristine)
+    if critical_error:
+        criticals = pristine & (u < F32(p_critical))
+        updated[criticals] = 0
+    degrades = (pristine | intermediate) & (u < F32(p_degrade)) if stochastic_degrade else (pristine | intermediate)
+    degrades = degrades & ~criticals
+    updated[degrades] -= 1
+    return updated
+
+
+def suppressant_refill(suppressants, capacity, equipment, refills, u, stochastic, p, capacity_bonuses):
+    """transitions/suppressant_refill.py:43-74 (``equipment`` is the state AFTER the equipment transition)."""
+    increase = refills & (u < F32(p)) if stochastic else refills.copy()
+    bonus = np.asarray(capacity_bonuses, np.float32)[equipment]
+    return np.where(increase, (capacity + bonus).astype(np.float32), suppressants).astype(np.float32), increase
+
+
+def capacity_transition(suppressants, capacity, targets, u_size, u_switch, stochastic, p_switch, capacities, cumulative):
+    """transitions/capacity.py:39-66 (bucketize right=False: first i with r <= cum[i])."""
+    capacities = np.asarray(capacities, np.float32)
+    size_index = np.searchsorted(np.asarray(cumulative, np.float32), u_size, side='left')
+    new_max = capacities[np.minimum(size_index, len(capacities) - 1)]
+    switch = targets & (u_switch < F32(p_switch)) if stochastic else targets
+    extra = (suppressants - capacity).astype(np.float32)
+    new_capacity = np.where(switch, new_max, capacity).astype(np.float32)
+    new_suppressants = np.where(switch, (new_max + extra).astype(np.float32), suppressants).astype(np.float32)
+    return new_suppressants, new_capacity
+
+
+def fire_increase(fires, intensity, fuel, attack, u, num_states, stochastic_increase, p_increase, stochastic_burnouts,
+                  p_burnout):
+    """transitions/fire_increase.py:43-95; mutates fires / intensity / fuel, returns the just-burned-out mask."""
+    required = np.where(fires >= 0, fires, 0).astype(np.float32)
+    diff = required - attack
+    burning = (fires > 0) & (intensity > 0)
+    unmet = (diff > 0) & burning
+    almost = unmet & (intensity == num_states - 2)
+    prob = np.zeros(fires.shape, np.float32)
+    prob[unmet & ~almost] = F32(p_increase) if stochastic_increase else F32(1.0)
+    prob[almost] = F32(p_burnout) if stochastic_burnouts else F32(p_increase)
+    prob = np.clip(prob, 0, 1)
+    grow = u < prob
+    intensity[grow] += 1
+    burned = grow & (intensity >= num_states - 1)
+    fires[burned] *= -1
+    fuel[burned] = np.maximum(fuel[burned] - 1, 0)
+    return burned
+
+
+def fire_decrease(fires, intensity, fuel, attack, u, stochastic_decrease, p_decrease, bonus):
+    """transitions/fire_decrease.py:36-80 (no FMA: multiply then add, each rounded to fp32); returns put-out mask."""
+    required = np.where(fires >= 0, fires, 0).astype(np.float32)
+    diff = required - attack
+    burning = (fires > 0) & (intensity > 0)
+    met = (diff <= 0) & burning
+    prob = np.zeros(fires.shape, np.float32)
+    if stochastic_decrease:
+        prob[met] = (F32(p_decrease) + (F32(-1) * diff[met]).astype(np.float32) * F32(bonus)).astype(np.float32)
+    else:
+        prob[met] = 1.0
+    prob = np.clip(prob, 0, 1)
+    shrink = u < prob
+    intensity[shrink] -= 1
+    put_out = shrink & (intensity <= 0)
+    fires[put_out] *= -1
+    fuel[put_out] -= 1
+    return put_out
+
+
+def fire_spread(fires, intensity, fuel, u, lut, p_random, ignition_temp, use_fuel):
+    """transitions/fire_spreads.py:33-59 on [B, H, W] arrays; mutates fires / intensity."""
+    B, H, W = fires.shape
+    burning = (fires > 0) & (intensity > 0)
+    padded = np.pad(burning, ((0, 0), (1, 1), (1, 1)))
+    pattern = (padded[:, 0:H, 1:W + 1].astype(np.int32) | (padded[:, 1:H + 1, 0:W].astype(np.int32) << 1) |
+               (padded[:, 1:H + 1, 2:W + 2].astype(np.int32) << 2) | (padded[:, 2:H + 2, 1:W + 1].astype(np.int32) << 3))
+    prob = np.asarray(lut, np.float32)[pattern]
+    unlit = (fires < 0) & (intensity == 0)
+    if use_fuel:
+        unlit &= fuel > 0
+    prob = np.where(unlit, (prob + F32(p_random)).astype(np.float32), F32(0))
+    ignite = u < prob
+    fires[ignite] *= -1
+    intensity[ignite] = np.broadcast_to(np.asarray(ignition_temp), fires.shape)[ignite]
+    return ignite
+
+
 class WildfireOracle:
     """Reference semantics of ``wildfire_v0`` for one batch of environments, state held as numpy arrays.
 
@@ -232,92 +340,28 @@ class WildfireOracle:
                 users[b, a] = True
                 hit[b, a, cell] = True
 
-        # ---- transitions/suppressant_decrease.py:34-63
-        decrease = users & (u_agent[0] < self.p_supp_decrease) if sc.suppressant_decrease else users
-        self.suppressants = np.maximum(np.where(decrease, self.suppressants - F32(1), self.suppressants), F32(0))
+        # ---- agent transitions, in the reference order (wildfire.py:488-514)
+        self.suppressants = suppressant_decrease(self.suppressants, users, u_agent[0], sc.suppressant_decrease,
+                                                 self.p_supp_decrease)
+        self.equipment = equipment_transition(self.equipment, u_agent[1], self.E, sc.repair, self.p_repair, sc.degrade,
+                                              self.p_degrade, sc.critical_error, self.p_critical)
+        self.suppressants, increase = suppressant_refill(self.suppressants, self.capacity, self.equipment, refills,
+                                                         u_agent[2], sc.suppressant_refill, self.p_refill,
+                                                         self.equipment_states[:, 0])
+        self.suppressants, self.capacity = capacity_transition(self.suppressants, self.capacity, increase, u_agent[3],
+                                                               u_agent[4], sc.tank_switch, self.p_tank_switch,
+                                                               self.capacities, self.capacity_cum)
 
-        # ---- transitions/equipment.py:42-77 (all masks from the pre-update equipment, one uniform for the three tests)
-        r = u_agent[1]
-        eq = self.equipment
-        pristine = eq == self.E - 1
-        damaged = eq == 0
-        intermediate = ~pristine & ~damaged
-        repairs = damaged & (r < self.p_repair) if sc.repair else damaged
-        new_eq = eq.copy()
-        new_eq[repairs] = self.E - 1
-        criticals = np.zeros_like(pristine)
-        if sc.critical_error:
-            criticals = pristine & (r < self.p_critical)
-            new_eq[criticals] = 0
-        degrades = (pristine | intermediate) & (r < self.p_degrade) if sc.degrade else (pristine | intermediate)
-        degrades = degrades & ~criticals
-        new_eq[degrades] -= 1
-        self.equipment = new_eq
-
-        # ---- transitions/suppressant_refill.py:43-74 (bonus from the equipment AFTER its transition)
-        increase = refills & (u_agent[2] < self.p_refill) if sc.suppressant_refill else refills.copy()
-        bonus = self.equipment_states[self.equipment, 0]
-        self.suppressants = np.where(increase, (self.capacity + bonus).astype(np.float32), self.suppressants)
-
-        # ---- transitions/capacity.py:39-66 (bucketize right=False: first i with r <= cum[i])
-        size_index = np.searchsorted(self.capacity_cum, u_agent[3], side='left')
-        new_max = self.capacities[np.minimum(size_index, len(self.capacities) - 1)]
-        switch = increase & (u_agent[4] < self.p_tank_switch) if sc.tank_switch else increase
-        extra = (self.suppressants - self.capacity).astype(np.float32)
-        self.capacity = np.where(switch, new_max, self.capacity)
-        self.suppressants = np.where(switch, (new_max + extra).astype(np.float32), self.suppressants)
-
-        fires = self.fires.reshape(B, HW)
-        intensity = self.intensity.reshape(B, HW)
-        fuel = self.fuel.reshape(B, HW)
-        u_field = u_field.reshape(3, B, HW)
-
-        # ---- transitions/fire_increase.py:43-95
-        required = np.where(fires >= 0, fires, 0).astype(np.float32)
-        diff = required - attack
-        burning = (fires > 0) & (intensity > 0)
-        unmet = (diff > 0) & burning
-        almost = unmet & (intensity == self.S - 2)
-        prob = np.zeros((B, HW), np.float32)
-        prob[unmet & ~almost] = self.p_increase if sc.fire_increase else F32(1.0)
-        prob[almost] = self.p_burnout if sc.special_burnout_probability else self.p_increase
-        prob = np.clip(prob, 0, 1)
-        grow = u_field[0] < prob
-        intensity[grow] += 1
-        burned = grow & (intensity >= self.S - 1)
-        fires[burned] *= -1
-        fuel[burned] = np.maximum(fuel[burned] - 1, 0)
-
-        # ---- transitions/fire_decrease.py:36-80 (sees the post-increase state; no FMA: mul then add in fp32)
-        required = np.where(fires >= 0, fires, 0).astype(np.float32)
-        diff = required - attack
-        burning = (fires > 0) & (intensity > 0)
-        met = (diff <= 0) & burning
-        prob = np.zeros((B, HW), np.float32)
-        if sc.fire_decrease:
-            prob[met] = (self.p_decrease + (F32(-1) * diff[met]) * self.decrease_bonus).astype(np.float32)
-        else:
-            prob[met] = 1.0
-        prob = np.clip(prob, 0, 1)
-        shrink = u_field[1] < prob
-        intensity[shrink] -= 1
-        put_out = shrink & (intensity <= 0)
-        fires[put_out] *= -1
-        fuel[put_out] -= 1
-
-        # ---- transitions/fire_spreads.py:33-59 (sees the post-decrease state)
-        burning = ((fires > 0) & (intensity > 0)).reshape(B, H, W)
-        padded = np.pad(burning, ((0, 0), (1, 1), (1, 1)))
-        pattern = (padded[:, 0:H, 1:W + 1].astype(np.int32) | (padded[:, 1:H + 1, 0:W].astype(np.int32) << 1) |
-                   (padded[:, 1:H + 1, 2:W + 2].astype(np.int32) << 2) | (padded[:, 2:H + 2, 1:W + 1].astype(np.int32) << 3))
-        prob = self.spread_lut[pattern.reshape(B, HW)]
-        unlit = (fires < 0) & (intensity == 0)
-        if sc.fire_fuel:
-            unlit &= fuel > 0
-        prob = np.where(unlit, (prob + self.p_random).astype(np.float32), F32(0))
-        ignite = u_field[2] < prob
-        fires[ignite] *= -1
-        intensity[ignite] = np.broadcast_to(self.ignition_temp.reshape(1, HW), (B, HW))[ignite]
+        # ---- fire transitions, each on the state left by the previous one (wildfire.py:516-532)
+        fires, intensity, fuel = self.fires, self.intensity, self.fuel
+        attack3 = attack.reshape(B, H, W)
+        burned = fire_increase(fires, intensity, fuel, attack3, u_field[0], self.S, sc.fire_increase, self.p_increase,
+                               sc.special_burnout_probability, self.p_burnout)
+        put_out = fire_decrease(fires, intensity, fuel, attack3, u_field[1], sc.fire_decrease, self.p_decrease,
+                                self.decrease_bonus)
+        fire_spread(fires, intensity, fuel, u_field[2], self.spread_lut, self.p_random, self.ignition_temp, sc.fire_fuel)
+        fires, intensity, fuel = (x.reshape(B, HW) for x in (fires, intensity, fuel))
+        burned, put_out = burned.reshape(B, HW), put_out.reshape(B, HW)
 
         # ---- rewards, wildfire.py:534-557
         cell_reward = np.broadcast_to(self.fire_rewards.reshape(1, HW), (B, HW))

@@ -1,0 +1,99 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol include/frz.h declares, the ctypes mirrors
+have the C layout, and host-detectable errors follow the status / frz_last_error convention (no GPU needed)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from free_range_zoo_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STRUCTS = {
+    'FrzControl': _lib.Control,
+    'FrzWildfireParams': _lib.WildfireParams,
+    'FrzWildfireBuffers': _lib.WildfireBuffers,
+    'FrzCyberParams': _lib.CyberParams,
+    'FrzCyberBuffers': _lib.CyberBuffers,
+    'FrzRideshareParams': _lib.RideshareParams,
+    'FrzRideshareBuffers': _lib.RideshareBuffers,
+}
+
+
+@pytest.fixture(scope='module')
+def lib():
+    if not os.path.exists(_lib.LIBRARY_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _lib.library()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    declared = _lib.exported_symbols()
+    assert len(declared) == 15  # 3 library-wide + 4 per domain
+    missing = [name for name in declared if not hasattr(lib, name)]
+    assert not missing, missing
+    assert lib.frz_version() == 1
+
+
+def test_ctypes_mirrors_match_the_c_layout(tmp_path):
+    """Compile a probe against include/frz.h with gcc and compare sizeof / offsetof with the ctypes structures."""
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "frz.h"', 'int main(void) {']
+    for c_name, mirror in STRUCTS.items():
+        lines.append(f'  printf("{c_name} %zu\\n", sizeof({c_name}));')
+        for field, _ in mirror._fields_:
+            lines.append(f'  printf("{c_name}.{field} %zu\\n", offsetof({c_name}, {field}));')
+    lines += ['  return 0;', '}']
+    source = tmp_path / 'probe.c'
+    source.write_text('\n'.join(lines))
+    binary = tmp_path / 'probe'
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(source), '-o', str(binary)], check=True)
+    layout = dict(line.split() for line in subprocess.run([str(binary)], capture_output=True, text=True,
+                                                          check=True).stdout.splitlines())
+    for c_name, mirror in STRUCTS.items():
+        assert int(layout[c_name]) == ctypes.sizeof(mirror), c_name
+        for field, _ in mirror._fields_:
+            assert int(layout[f'{c_name}.{field}']) == getattr(mirror, field).offset, f'{c_name}.{field}'
+
+
+def test_null_and_shape_errors_are_reported_without_a_gpu(lib):
+    params, io = _lib.WildfireParams(), _lib.WildfireBuffers()
+    assert lib.frz_wildfire_step(None, None, 4, None) == 1  # FRZ_ERR_NULL
+    assert b'NULL' in lib.frz_last_error()
+    assert lib.frz_wildfire_step(ctypes.byref(params), ctypes.byref(io), 4, None) == 1  # control / fires are NULL
+    cy_params, cy_io = _lib.CyberParams(), _lib.CyberBuffers()
+    assert lib.frz_cyber_step(ctypes.byref(cy_params), ctypes.byref(cy_io), 4, None) == 1
+    rs_params, rs_io = _lib.RideshareParams(), _lib.RideshareBuffers()
+    assert lib.frz_rideshare_step(ctypes.byref(rs_params), ctypes.byref(rs_io), 4, None) == 1
+    # non-NULL pointers but an unsupported shape -> FRZ_ERR_SHAPE before anything is launched
+    dummy = ctypes.create_string_buffer(64)
+    address = ctypes.addressof(dummy)
+    io.control, io.fires, io.actions = address, address, address
+    params.height, params.width, params.num_agents = 40, 40, 3  # 1600 cells > FRZ_MAX_CELLS
+    assert lib.frz_wildfire_step(ctypes.byref(params), ctypes.byref(io), 4, None) == 2  # FRZ_ERR_SHAPE
+    assert b'unsupported shape' in lib.frz_last_error()
+    assert lib.frz_wildfire_step(ctypes.byref(params), ctypes.byref(io), 0, None) == 2
+    with pytest.raises(RuntimeError, match='status 2'):
+        _lib.check(2, 'probe')
+
+
+def test_there_is_no_cpu_fallback():
+    import torch
+
+    from free_range_zoo_b200 import presets
+    from free_range_zoo_b200.envs import cybersecurity_v0, rideshare_v0, wildfire_v0
+    for module, preset in ((wildfire_v0, presets.wildfire_profile), (rideshare_v0, presets.rideshare_profile),
+                           (cybersecurity_v0, presets.cyber_profile)):
+        with pytest.raises(RuntimeError, match='no CPU fallback'):
+            module.parallel_env(parallel_envs=2, configuration=preset(), device=torch.device('cpu'))
+
+
+def test_product_code_never_imports_the_oracle():
+    offenders = []
+    for folder, _, files in os.walk(os.path.join(ROOT, 'free_range_zoo_b200')):
+        for name in files:
+            if name.endswith('.py'):
+                text = open(os.path.join(folder, name)).read()
+                if 'import oracle' in text or 'from oracle' in text:
+                    offenders.append(os.path.join(folder, name))
+    assert not offenders, offenders
