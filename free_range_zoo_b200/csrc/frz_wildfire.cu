@@ -50,21 +50,31 @@ __device__ __forceinline__ int group_sum(int v) {
   return v;
 }
 
+// Shared memory of one group (one environment in flight):
+//   float    attack[G * CPL]   attack power per cell, accumulated in agent order
+//   uint32_t avail[A * NW]     per agent: cells it may fight (bit c = cell c), published for the mask builder
+//   uint8_t  task_cell[G*CPL]  env-local task index -> cell (inverse of the lit-rank popcount)
+__host__ __device__ constexpr int group_smem_words(int cells, int agents, int words) {
+  return cells + agents * words + cells / 4;
+}
+
 template <int G, int CPL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (G * CPL > 128) ? 1 : 3)
 wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_constant__ FrzWildfireBuffers io,
                      const int B, const int mode) {
   constexpr int kGroupsPerWarp = 32 / G;
-  constexpr int NW = (G * CPL + 31) / 32;
+  constexpr int kCells = G * CPL;
+  constexpr int NW = (kCells + 31) / 32;
+  constexpr int kCalls = (3 * CPL + 3) / 4;  // Philox calls per lane for the 3 uniforms of each of its cells
   static_assert(G == 32 || CPL == 1, "sub-warp groups hold one cell per lane");
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(16) uint32_t smem[];
 
   const int lane = threadIdx.x & 31;
   const int sub = lane % G;
   const int group_base = lane - sub;
   const uint32_t group_mask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
   const uint32_t lanes_below = (1u << sub) - 1u;
-  const int HW = p.height * p.width;
+  const int H = p.height, W = p.width, HW = H * W;
   const int A = p.num_agents;
   const int E = p.num_equipment_states;
   const uint32_t flags = p.flags;
@@ -72,6 +82,13 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   const int group_in_cta = (threadIdx.x >> 5) * kGroupsPerWarp + lane / G;
   const bool show_bad = flags & FRZ_WF_SHOW_BAD_ACTIONS;
   const bool use_fuel = flags & FRZ_WF_FIRE_FUEL;
+  const int mask_stride = io.mask_stride, mask_words_row = mask_stride >> 2;
+  const int table_words = io.mask_words;
+
+  uint32_t* region = smem + size_t(group_in_cta) * group_smem_words(kCells, A, NW);
+  float* attack_s = reinterpret_cast<float*>(region);
+  uint32_t* avail_s = region + kCells;
+  uint8_t* task_cell_s = reinterpret_cast<uint8_t*>(region + kCells + A * NW);
 
   FrzControl* control = io.control;
   const uint64_t step = control->step;
@@ -82,28 +99,19 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   // (utils/env.py:212); the flags were published by the previous launch.
   const bool skip = (mode == kStep) && ((alive_prev & 3u) != 3u);
 
-  // per-lane constants: the cells and the agent this lane owns are the same for every environment it processes
-  int cell[CPL], cy[CPL], cx[CPL], ignition[CPL];
-  float creward[CPL];
-  bool cvalid[CPL];
+  // per-lane constants: packed (y, x) and the "has a N/W/E/S neighbour" bits of the cells this lane owns
+  int yx[CPL];
+  uint32_t edge[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) {
-    cell[i] = i * G + sub;
-    cvalid[i] = cell[i] < HW;
-    cy[i] = cell[i] / p.width;
-    cx[i] = cell[i] - cy[i] * p.width;
-    creward[i] = cvalid[i] ? io.cell_reward[cell[i]] : 0.f;
-    ignition[i] = cvalid[i] ? io.cell_ignition[cell[i]] : 0;
+    const int c = i * G + sub, y = c / W, x = c - y * W;
+    yx[i] = (y << 16) | x;
+    edge[i] = c < HW ? (uint32_t(y > 0) | (uint32_t(x > 0) << 1) | (uint32_t(x < W - 1) << 2) | (uint32_t(y < H - 1) << 3)) : 0u;
   }
   const bool is_agent = sub < A;
   const float base_power = is_agent ? p.agent_power[sub] : 0.f;
   const float agent_yf = is_agent ? float(p.agent_y[sub]) : 0.f;
   const float agent_xf = is_agent ? float(p.agent_x[sub]) : 0.f;
-
-  const int mask_stride = io.mask_stride;
-  const int region_words = (A * mask_stride) >> 2;
-  uint32_t* region = reinterpret_cast<uint32_t*>(smem) + size_t(group_in_cta) * region_words;
-  unsigned char* region_bytes = reinterpret_cast<unsigned char*>(region);
 
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
 
@@ -119,9 +127,11 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       int fires[CPL], inten[CPL], fuel[CPL];
 #pragma unroll
       for (int i = 0; i < CPL; ++i) {
-        fires[i] = cvalid[i] ? io.fires[cell_row + cell[i]] : 0;
-        inten[i] = cvalid[i] ? io.intensity[cell_row + cell[i]] : 0;
-        fuel[i] = cvalid[i] ? io.fuel[cell_row + cell[i]] : 0;
+        const int c = i * G + sub;
+        const bool in_grid = c < HW;
+        fires[i] = in_grid ? io.fires[cell_row + c] : 0;
+        inten[i] = in_grid ? io.intensity[cell_row + c] : 0;
+        fuel[i] = in_grid ? io.fuel[cell_row + c] : 0;
       }
       float supp = 0.f, cap = 0.f;
       int equip = 0;
@@ -132,11 +142,15 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       }
 
       uint32_t litw[NW];
+      int n_before = 0;  // tasks published by the previous launch: rows / mask bytes beyond are already padding
 #pragma unroll
       for (int i = 0; i < CPL; ++i) {
         const uint32_t ballot = __ballot_sync(kFullMask, fires[i] > 0);
-        if (G == 32) litw[i] = ballot; else litw[0] = (ballot >> group_base) & group_mask;
+        const uint32_t word = (G == 32) ? ballot : ((ballot >> group_base) & group_mask);
+        litw[(G == 32) ? i : 0] = word;
+        n_before += __popc(word);
       }
+      if (mode != kStep) n_before = HW;  // refresh / reset: (re)write every row
 
       float reward = 0.f, cumulative = 0.f;
       int moves = 0, total_burnouts = 0, n_burned = 0, n_putout = 0;
@@ -157,19 +171,16 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
 
         // tasks this agent could fight at the start of the step == what update_actions published after the previous
         // step (wildfire.py:587-666): lit & in Chebyshev range (equipment bonus folded in) & has suppressant
-        uint32_t availw[NW];
-        {
-          const uint32_t* rm = io.range_mask + (size_t(is_agent ? sub : 0) * E + equip) * io.mask_words;
-#pragma unroll
-          for (int w = 0; w < NW; ++w)
-            availw[w] = (is_agent && supp > 0.f && w < io.mask_words) ? (litw[w] & rm[w]) : 0u;
-        }
         const bool refill = is_agent && act_id == -1;  // wildfire.py:431
         int target = -1;
         bool bad = false;
         // an agent without a single task in ANY environment is skipped by the reference's decode loop
         // (wildfire.py:434): no attack, no bad-action penalty -- only its refill flag is recorded
         if (is_agent && !refill && ((agents_with_tasks >> sub) & 1u)) {
+          const uint32_t* rm = io.range_mask + (size_t(sub) * E + equip) * table_words;
+          uint32_t availw[NW];
+#pragma unroll
+          for (int w = 0; w < NW; ++w) availw[w] = (supp > 0.f && w < table_words) ? (litw[w] & rm[w]) : 0u;
           int k = act_k, found = -1;
           if (k >= 0) {
 #pragma unroll
@@ -188,32 +199,52 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         const bool user = target >= 0;
         const float power = base_power + p.equipment_power_bonus[equip];  // wildfire.py:455-457
 
-        // attack power per cell, accumulated in agent order (wildfire.py:470)
-        float attack[CPL];
+        // attack power per cell, accumulated in agent order through shared memory (wildfire.py:470)
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) attack[i] = 0.f;
+        for (int i = 0; i < CPL; ++i) attack_s[i * G + sub] = 0.f;
+        __syncwarp();
         for (int a = 0; a < A; ++a) {
-          const int t = __shfl_sync(kFullMask, target, a, G);
-          const float pw = __shfl_sync(kFullMask, power, a, G);
-#pragma unroll
-          for (int i = 0; i < CPL; ++i)
-            if (t == cell[i]) attack[i] = __fadd_rn(attack[i], pw);
+          if (sub == a && user) attack_s[target] = __fadd_rn(attack_s[target], power);
+          __syncwarp();
         }
 
         // ---------------------------------------------------------------- randomness
         const uint32_t env_lo = uint32_t(p.env_offset + e), env_hi = uint32_t(uint64_t(p.env_offset + e) >> 32);
+        const uint32_t step_lo = uint32_t(step), step_hi = uint32_t(step >> 32) ^ env_hi;
         float ua[5];
         if (io.agent_uniforms != nullptr) {
 #pragma unroll
           for (int ev = 0; ev < 5; ++ev)
             ua[ev] = is_agent ? io.agent_uniforms[(size_t(ev) * B + e) * A + sub] : 1.f;
         } else {
-          const uint4 r = philox(env_lo, uint32_t(step), 0x80000000u | uint32_t(sub), uint32_t(step >> 32) ^ env_hi);
+          const uint4 r = philox(env_lo, step_lo, 0x80000000u | uint32_t(sub), step_hi);
           ua[0] = u01(r.x);
           ua[1] = u01(r.y);
           ua[2] = u01(r.z);
           ua[3] = u01(r.w);
           ua[4] = u01(((r.x & 0xffu) << 24) | ((r.y & 0xffu) << 16) | ((r.z & 0xffu) << 8));
+        }
+        float uf[3 * CPL];  // uf[3*i + event]: fire increase, fire decrease, fire spread of cell i
+        if (io.field_uniforms != nullptr) {
+          const size_t plane = size_t(B) * HW;
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) {
+            const int c = i * G + sub;
+#pragma unroll
+            for (int ev = 0; ev < 3; ++ev) uf[3 * i + ev] = c < HW ? io.field_uniforms[ev * plane + cell_row + c] : 1.f;
+          }
+        } else {
+          uint32_t bits[4 * kCalls];
+#pragma unroll
+          for (int k = 0; k < kCalls; ++k) {
+            const uint4 r = philox(env_lo, step_lo, uint32_t(k * G + sub), step_hi);
+            bits[4 * k] = r.x;
+            bits[4 * k + 1] = r.y;
+            bits[4 * k + 2] = r.z;
+            bits[4 * k + 3] = r.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 3 * CPL; ++j) uf[j] = u01(bits[j]);
         }
 
         // ---------------------------------------------------------------- agent transitions
@@ -249,60 +280,48 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
 
         // ---------------------------------------------------------------- fire increase + decrease per cell
         const int burned_state = p.num_fire_states - 1, almost_state = p.num_fire_states - 2;
-        bool burned[CPL], putout[CPL];
-        float uf2[CPL];
+        const float p_grow = (flags & FRZ_WF_STOCH_FIRE_INCREASE) ? fminf(fmaxf(p.p_increase, 0.f), 1.f) : 1.f;
+        const float p_almost = fminf(fmaxf((flags & FRZ_WF_SPECIAL_BURNOUT) ? p.p_burnout : p.p_increase, 0.f), 1.f);
+        uint32_t burned_bits = 0, putout_bits = 0;  // bit i = this lane's cell i
         uint32_t burnw[NW];
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
-          float u0, u1;
-          if (io.field_uniforms != nullptr) {
-            const size_t at = size_t(e) * HW + cell[i], plane = size_t(B) * HW;
-            u0 = cvalid[i] ? io.field_uniforms[at] : 1.f;
-            u1 = cvalid[i] ? io.field_uniforms[plane + at] : 1.f;
-            uf2[i] = cvalid[i] ? io.field_uniforms[2 * plane + at] : 1.f;
-          } else {
-            const uint4 r = philox(env_lo, uint32_t(step), uint32_t(cell[i]), uint32_t(step >> 32) ^ env_hi);
-            u0 = u01(r.x);
-            u1 = u01(r.y);
-            uf2[i] = u01(r.z);
-          }
+          const float attack = attack_s[i * G + sub];
           int f = fires[i], it = inten[i], fu = fuel[i];
           // fire_increase.py:43-95
-          float diff = __fadd_rn(f >= 0 ? float(f) : 0.f, -attack[i]);
+          float diff = __fadd_rn(f >= 0 ? float(f) : 0.f, -attack);
           bool burning = f > 0 && it > 0;
           const bool unmet = diff > 0.f && burning;
-          const bool almost = unmet && it == almost_state;
-          float prob = 0.f;
-          if (unmet && !almost) prob = (flags & FRZ_WF_STOCH_FIRE_INCREASE) ? p.p_increase : 1.f;
-          if (almost) prob = (flags & FRZ_WF_SPECIAL_BURNOUT) ? p.p_burnout : p.p_increase;
-          prob = fminf(fmaxf(prob, 0.f), 1.f);
-          const bool grow = u0 < prob;
+          const float prob_up = unmet ? (it == almost_state ? p_almost : p_grow) : 0.f;
+          const bool grow = uf[3 * i] < prob_up;
           if (grow) it += 1;
-          burned[i] = grow && it >= burned_state;
-          if (burned[i]) {
+          const bool burned = grow && it >= burned_state;
+          if (burned) {
             f = -f;
             fu = max(fu - 1, 0);
+            burned_bits |= 1u << i;
           }
           // fire_decrease.py:36-80 on the post-increase state; mul and add rounded separately like the reference
-          diff = __fadd_rn(f >= 0 ? float(f) : 0.f, -attack[i]);
+          diff = __fadd_rn(f >= 0 ? float(f) : 0.f, -attack);
           burning = f > 0 && it > 0;
           const bool met = diff <= 0.f && burning;
-          prob = 0.f;
+          float prob_down = 0.f;
           if (met)
-            prob = (flags & FRZ_WF_STOCH_FIRE_DECREASE) ? __fadd_rn(p.p_decrease, __fmul_rn(-diff, p.decrease_bonus)) : 1.f;
-          prob = fminf(fmaxf(prob, 0.f), 1.f);
-          const bool shrink = u1 < prob;
+            prob_down = (flags & FRZ_WF_STOCH_FIRE_DECREASE) ? __fadd_rn(p.p_decrease, __fmul_rn(-diff, p.decrease_bonus)) : 1.f;
+          prob_down = fminf(fmaxf(prob_down, 0.f), 1.f);
+          const bool shrink = uf[3 * i + 1] < prob_down;
           if (shrink) it -= 1;
-          putout[i] = shrink && it <= 0;
-          if (putout[i]) {
+          const bool put = shrink && it <= 0;
+          if (put) {
             f = -f;
             fu -= 1;
+            putout_bits |= 1u << i;
           }
           fires[i] = f;
           inten[i] = it;
           fuel[i] = fu;
           const uint32_t ballot = __ballot_sync(kFullMask, f > 0 && it > 0);
-          if (G == 32) burnw[i] = ballot; else burnw[0] = (ballot >> group_base) & group_mask;
+          burnw[(G == 32) ? i : 0] = (G == 32) ? ballot : ((ballot >> group_base) & group_mask);
         }
 
         // ---------------------------------------------------------------- fire spread (fire_spreads.py:33-59)
@@ -311,49 +330,61 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         uint32_t putw[NW];
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
+          const int c = i * G + sub;
           int f = fires[i], it = inten[i];
-          if (cvalid[i]) {
-            int pattern = 0;
-            if (cy[i] > 0 && bit_at<NW>(burnw, cell[i] - p.width)) pattern |= 1;
-            if (cx[i] > 0 && bit_at<NW>(burnw, cell[i] - 1)) pattern |= 2;
-            if (cx[i] < p.width - 1 && bit_at<NW>(burnw, cell[i] + 1)) pattern |= 4;
-            if (cy[i] < p.height - 1 && bit_at<NW>(burnw, cell[i] + p.width)) pattern |= 8;
-            const bool unlit = f < 0 && it == 0 && (!use_fuel || fuel[i] > 0);
+          const bool unlit = f < 0 && it == 0 && (!use_fuel || fuel[i] > 0);
+          if (__any_sync(kFullMask, unlit)) {
+            // burning-neighbour pattern of cell c: bit0 N (c-W), bit1 W (c-1), bit2 E (c+1), bit3 S (c+W)
+            uint32_t pattern;
+            const uint32_t cur = burnw[(G == 32) ? i : 0];
+            const uint32_t prev = (G == 32 && i > 0) ? burnw[(G == 32 && i > 0) ? i - 1 : 0] : 0u;
+            const uint32_t next = (G == 32 && i + 1 < NW) ? burnw[(G == 32 && i + 1 < NW) ? i + 1 : 0] : 0u;
+            if (W < 32) {
+              const uint32_t north = __funnelshift_l(prev, cur, W), south = __funnelshift_r(cur, next, W);
+              const uint32_t west = __funnelshift_l(prev, cur, 1), east = __funnelshift_r(cur, next, 1);
+              pattern = ((north >> sub) & 1u) | (((west >> sub) & 1u) << 1) | (((east >> sub) & 1u) << 2) |
+                        (((south >> sub) & 1u) << 3);
+            } else {
+              pattern = uint32_t(c >= W && bit_at<NW>(burnw, c - W)) | (uint32_t(c >= 1 && bit_at<NW>(burnw, c - 1)) << 1) |
+                        (uint32_t(c + 1 < kCells && bit_at<NW>(burnw, min(c + 1, kCells - 1))) << 2) |
+                        (uint32_t(c + W < kCells && bit_at<NW>(burnw, min(c + W, kCells - 1))) << 3);
+            }
+            pattern &= edge[i];
             const float prob = unlit ? __fadd_rn(p.spread_lut[pattern], p.p_random_ignition) : 0.f;
-            if (uf2[i] < prob) {
+            if (uf[3 * i + 2] < prob) {
               f = -f;
-              it = ignition[i];
+              it = io.cell_ignition[c];
             }
           }
           fires[i] = f;
           inten[i] = it;
-          if (putout[i]) my_put_reward += creward[i];
-          if (burned[i]) my_burn_reward += creward[i];
+          const bool put = (putout_bits >> i) & 1u, burned = (burned_bits >> i) & 1u;
+          if (put) my_put_reward += io.cell_reward[c];
+          if (burned) my_burn_reward += io.cell_reward[c];
           my_fuel += fuel[i];
           const uint32_t lit_ballot = __ballot_sync(kFullMask, f > 0);
-          const uint32_t put_ballot = __ballot_sync(kFullMask, putout[i]);
-          const uint32_t burn_ballot = __ballot_sync(kFullMask, burned[i]);
-          if (G == 32) {
-            litw[i] = lit_ballot;
-            putw[i] = put_ballot;
-          } else {
-            litw[0] = (lit_ballot >> group_base) & group_mask;
-            putw[0] = (put_ballot >> group_base) & group_mask;
-          }
-          n_putout += __popc((put_ballot >> group_base) & group_mask);
-          n_burned += __popc((burn_ballot >> group_base) & group_mask);
+          const uint32_t put_ballot = (__ballot_sync(kFullMask, put) >> group_base) & group_mask;
+          const uint32_t burn_ballot = (__ballot_sync(kFullMask, burned) >> group_base) & group_mask;
+          litw[(G == 32) ? i : 0] = (G == 32) ? lit_ballot : ((lit_ballot >> group_base) & group_mask);
+          putw[(G == 32) ? i : 0] = put_ballot;
+          n_putout += __popc(put_ballot);
+          n_burned += __popc(burn_ballot);
         }
 
         // ---------------------------------------------------------------- rewards + termination (wildfire.py:534-582)
-        const float put_total = group_sum<G>(my_put_reward);
-        const float burn_total = group_sum<G>(my_burn_reward);
+        // (the reductions are skipped when no group of the warp needs them; the test must be warp-uniform)
+        float put_total = 0.f, burn_total = 0.f;
+        if (__any_sync(kFullMask, n_putout > 0) && !(flags & FRZ_WF_LOCALIZE_PUTOUTS))
+          put_total = group_sum<G>(my_put_reward);
+        if (__any_sync(kFullMask, n_burned > 0) && (flags & FRZ_WF_BURNOUT_SCALED))
+          burn_total = group_sum<G>(my_burn_reward);
         const float penalty_total =
             (flags & FRZ_WF_BURNOUT_SCALED) ? -burn_total : __fmul_rn(p.burnout_penalty, float(n_burned));
         uint32_t any_lit = 0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) any_lit |= litw[w];
         bool dead = any_lit == 0;
-        if (use_fuel) dead = dead && group_sum<G>(my_fuel) <= 0;
+        if (use_fuel && __any_sync(kFullMask, dead)) dead = dead && group_sum<G>(my_fuel) <= 0;
         if (dead) {  // wildfire.py:570
 #pragma unroll
           for (int i = 0; i < CPL; ++i) fires[i] = 0;
@@ -380,53 +411,64 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       }
 
       // ------------------------------------------------------------------ update_actions / update_observations
-      int lit_before[CPL];  // env-local task index of this lane's cell if it is lit
       int n_lit = 0;
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) {
-        const uint32_t word = (G == 32) ? litw[i] : litw[0];
-        lit_before[i] = n_lit + __popc(word & lanes_below);
-        n_lit += __popc(word);
-      }
-      uint32_t availw[NW];
+      for (int w = 0; w < NW; ++w) n_lit += __popc(litw[w]);
+      const int n_rows = max(n_lit, n_before);  // rows / mask bytes that may differ from their padding value
+
+      // publish the agents' available-cell sets and the task -> cell map for the mask builder
       int n_avail = 0;
-      {
-        const uint32_t* rm = io.range_mask + (size_t(is_agent ? sub : 0) * E + max(equip, 0)) * io.mask_words;
+      if (is_agent) {
+        const uint32_t* rm = io.range_mask + (size_t(sub) * E + max(equip, 0)) * table_words;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
-          availw[w] = (is_agent && supp > 0.f && w < io.mask_words) ? (litw[w] & rm[w]) : 0u;
-          n_avail += __popc(availw[w]);
+          const uint32_t word = (supp > 0.f && w < table_words) ? (litw[w] & rm[w]) : 0u;
+          avail_s[sub * NW + w] = word;
+          n_avail += __popc(word);
         }
       }
-
-      // action mask [A, mask_stride] bytes, indexed by env-local task: staged in shared memory so that the global
-      // store is one contiguous, word-coalesced row per environment
-      for (int j = sub; j < region_words; j += G) region[j] = 0u;
-      __syncwarp();
-      for (int a = 0; a < A; ++a) {
-        uint32_t aw[NW];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) aw[w] = __shfl_sync(kFullMask, availw[w], a, G);
+      int4* task_row = reinterpret_cast<int4*>(io.task_obs) + cell_row;
+      {
+        int rank = 0;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
-          const uint32_t word = (G == 32) ? aw[i] : aw[0];
-          if ((word >> sub) & 1u) region_bytes[a * mask_stride + lit_before[i]] = 1;
+          const uint32_t word = litw[(G == 32) ? i : 0];
+          if ((word >> sub) & 1u) {
+            const int t = rank + __popc(word & lanes_below);  // env-local task index = rank in row-major lit order
+            task_cell_s[t] = uint8_t(i * G + sub);
+            if (valid) task_row[t] = make_int4(yx[i] >> 16, yx[i] & 0xffff, fires[i], inten[i]);
+          }
+          rank += __popc(word);
         }
       }
       __syncwarp();
 
       if (valid) {
-        uint32_t* mask_row = reinterpret_cast<uint32_t*>(io.action_mask + size_t(env) * A * mask_stride);
-        for (int j = sub; j < region_words; j += G) mask_row[j] = region[j];
+        // padding rows only where the previous launch had real rows
+        for (int t = n_lit + sub; t < n_before; t += G) task_row[t] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
 
-        int4* task_row = reinterpret_cast<int4*>(io.task_obs) + cell_row;
+        // action mask [A, mask_stride] bytes indexed by env-local task; each lane assembles 4 tasks into one word
+        uint32_t* mask_row = reinterpret_cast<uint32_t*>(io.action_mask + size_t(env) * A * mask_stride);
+        for (int q = sub; 4 * q < n_rows; q += G) {
+          const uint32_t cells4 = reinterpret_cast<const uint32_t*>(task_cell_s)[q];
+          uint32_t word_of[4], shift_of[4], keep = 0;
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-          const uint32_t word = (G == 32) ? litw[i] : litw[0];
-          if ((word >> sub) & 1u) task_row[lit_before[i]] = make_int4(cy[i], cx[i], fires[i], inten[i]);
-          const int slot = i * G + sub;  // padding rows
-          if (slot >= n_lit && slot < HW) task_row[slot] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t c = (cells4 >> (8 * j)) & 0xffu;
+            const bool real = 4 * q + j < n_lit;
+            word_of[j] = real ? (c >> 5) : 0u;
+            shift_of[j] = c & 31u;
+            keep |= real ? (1u << (8 * j)) : 0u;
+          }
+          for (int a = 0; a < A; ++a) {
+            const uint32_t* aw = avail_s + a * NW;
+            uint32_t out = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out |= ((aw[NW == 1 ? 0 : word_of[j]] >> shift_of[j]) & 1u) << (8 * j);
+            mask_row[a * mask_words_row + q] = out & keep;
+          }
         }
+
         if (is_agent) {
           io.agent_task_count[agent_row + sub] = n_avail;
           if (n_avail > 0) agent_bits |= 1u << sub;
@@ -437,10 +479,11 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         if (mode == kStep) {
 #pragma unroll
           for (int i = 0; i < CPL; ++i) {
-            if (cvalid[i]) {
-              io.fires[cell_row + cell[i]] = fires[i];
-              io.intensity[cell_row + cell[i]] = inten[i];
-              io.fuel[cell_row + cell[i]] = fuel[i];
+            const int c = i * G + sub;
+            if (c < HW) {
+              io.fires[cell_row + c] = fires[i];
+              io.intensity[cell_row + c] = inten[i];
+              io.fuel[cell_row + c] = fuel[i];
             }
           }
           if (is_agent) {
@@ -541,7 +584,7 @@ int launch_step(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B,
   static int ctas_per_sm = 0, sm_count = 0;
   static size_t cached_smem = ~size_t(0);
   const int groups_per_cta = (kThreads / 32) * (32 / G);
-  const size_t smem = size_t(groups_per_cta) * p.num_agents * io.mask_stride;
+  const size_t smem = size_t(groups_per_cta) * group_smem_words(G * CPL, p.num_agents, (G * CPL + 31) / 32) * sizeof(uint32_t);
   auto kernel = wildfire_step_kernel<G, CPL>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
