@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(_HERE, 'csrc', 'libfrz.so')
+# FRZ_LIBRARY selects an alternative build of the same library (kernel tuning experiments); never a fallback
+LIBRARY_PATH = os.environ.get('FRZ_LIBRARY') or os.path.join(_HERE, 'csrc', 'libfrz.so')
 
 MAX_AGENTS = 32
 MAX_EQUIPMENT = 8
@@ -66,7 +67,7 @@ _WF_POINTERS = ('fires', 'intensity', 'fuel', 'suppressants', 'capacity', 'equip
                 'init_fuel', 'init_suppressants', 'init_capacity', 'init_equipment', 'actions', 'rewards',
                 'cumulative_rewards', 'terminated', 'truncated', 'num_moves', 'num_burnouts', 'burnouts', 'putouts',
                 'env_task_count', 'agent_task_count', 'action_mask', 'self_obs', 'task_obs', 'cell_reward',
-                'cell_ignition', 'range_mask', 'control', 'field_uniforms', 'agent_uniforms')
+                'cell_ignition', 'range_mask', 'cell_agents', 'control', 'field_uniforms', 'agent_uniforms')
 
 
 class WildfireBuffers(C.Structure):

@@ -50,22 +50,27 @@ __device__ __forceinline__ int group_sum(int v) {
   return v;
 }
 
-// Shared memory of one group (one environment in flight):
-//   float    attack[G * CPL]   attack power per cell, accumulated in agent order
-//   uint32_t avail[A * NW]     per agent: cells it may fight (bit c = cell c), published for the mask builder
-//   uint8_t  task_cell[G*CPL]  env-local task index -> cell (inverse of the lit-rank popcount)
-__host__ __device__ constexpr int group_smem_words(int cells, int agents, int words) {
-  return cells + agents * words + cells / 4;
-}
+// Shared memory: one table shared by the CTA, then one region per group (= per environment in flight)
+//   uint32_t cell_agents[E * kCells]   static: bit a = agent a reaches cell c when its equipment is in state e
+//   per group: float attack[kCells]    attack power per cell, accumulated in agent order
+//              uint32_t task_agents[kCells]  env-local task t -> bitmask of the agents that may fight it
+__host__ __device__ constexpr int group_smem_words(int cells) { return 2 * cells; }
+
+#ifndef FRZ_WF_MIN_BLOCKS
+#define FRZ_WF_MIN_BLOCKS 2
+#endif
 
 template <int G, int CPL>
-__global__ void __launch_bounds__(kThreads, (G * CPL > 128) ? 1 : 3)
+__global__ void __launch_bounds__(kThreads, (G * CPL > 128) ? 1 : FRZ_WF_MIN_BLOCKS)
 wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_constant__ FrzWildfireBuffers io,
                      const int B, const int mode) {
   constexpr int kGroupsPerWarp = 32 / G;
   constexpr int kCells = G * CPL;
   constexpr int NW = (kCells + 31) / 32;
-  constexpr int kCalls = (3 * CPL + 3) / 4;  // Philox calls per lane for the 3 uniforms of each of its cells
+  // Philox calls per lane: 3 x 24-bit uniforms per cell; with >= 4 cells per lane the 12 spare low bytes of the first
+  // twelve words also yield the agent's four 24-bit uniforms, otherwise the agent needs a call of its own
+  constexpr int kCalls = (3 * CPL + 3) / 4;
+  constexpr bool kAgentFromSpare = CPL >= 4;
   static_assert(G == 32 || CPL == 1, "sub-warp groups hold one cell per lane");
   extern __shared__ __align__(16) uint32_t smem[];
 
@@ -85,10 +90,15 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   const int mask_stride = io.mask_stride, mask_words_row = mask_stride >> 2;
   const int table_words = io.mask_words;
 
-  uint32_t* region = smem + size_t(group_in_cta) * group_smem_words(kCells, A, NW);
+  uint32_t* cell_agents_s = smem;
+  uint32_t* region = smem + E * kCells + size_t(group_in_cta) * group_smem_words(kCells);
   float* attack_s = reinterpret_cast<float*>(region);
-  uint32_t* avail_s = region + kCells;
-  uint8_t* task_cell_s = reinterpret_cast<uint8_t*>(region + kCells + A * NW);
+  uint32_t* task_agents_s = region + kCells;
+  for (int i = threadIdx.x; i < E * kCells; i += kThreads) {
+    const int e = i / kCells, c = i - e * kCells;
+    cell_agents_s[i] = c < HW ? io.cell_agents[e * HW + c] : 0u;
+  }
+  __syncthreads();
 
   FrzControl* control = io.control;
   const uint64_t step = control->step;
@@ -119,9 +129,13 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
     for (int env0 = blockIdx.x * groups_per_cta; env0 < B; env0 += gridDim.x * groups_per_cta) {
       const int env = env0 + group_in_cta;
       const bool valid = env < B;
+      if (G == 32 && !valid) continue;  // the whole warp is past the end (sub-warp groups stay for the warp syncs)
       const int e = valid ? env : B - 1;
       const size_t cell_row = size_t(e) * HW;
       const size_t agent_row = size_t(e) * A;
+      int* const fires_row = io.fires + cell_row;
+      int* const inten_row = io.intensity + cell_row;
+      int* const fuel_row = io.fuel + cell_row;
 
       // ------------------------------------------------------------------ load
       int fires[CPL], inten[CPL], fuel[CPL];
@@ -129,9 +143,9 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       for (int i = 0; i < CPL; ++i) {
         const int c = i * G + sub;
         const bool in_grid = c < HW;
-        fires[i] = in_grid ? io.fires[cell_row + c] : 0;
-        inten[i] = in_grid ? io.intensity[cell_row + c] : 0;
-        fuel[i] = in_grid ? io.fuel[cell_row + c] : 0;
+        fires[i] = in_grid ? fires_row[c] : 0;
+        inten[i] = in_grid ? inten_row[c] : 0;
+        fuel[i] = in_grid ? fuel_row[c] : 0;
       }
       float supp = 0.f, cap = 0.f;
       int equip = 0;
@@ -211,20 +225,14 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         // ---------------------------------------------------------------- randomness
         const uint32_t env_lo = uint32_t(p.env_offset + e), env_hi = uint32_t(uint64_t(p.env_offset + e) >> 32);
         const uint32_t step_lo = uint32_t(step), step_hi = uint32_t(step >> 32) ^ env_hi;
-        float ua[5];
+        // Agent events: 0 suppressant decrease, 1 equipment, 2 refill, 3 capacity pick, 4 tank switch (wildfire.py:492-513).
+        // "decrease" needs a fight action and "refill" a refill action, so in Philox mode events 0 and 2 share one draw.
+        float ua[5], uf[3 * CPL];  // uf[3*i + event]: fire increase, fire decrease, fire spread of this lane's cell i
         if (io.agent_uniforms != nullptr) {
 #pragma unroll
           for (int ev = 0; ev < 5; ++ev)
             ua[ev] = is_agent ? io.agent_uniforms[(size_t(ev) * B + e) * A + sub] : 1.f;
-        } else {
-          const uint4 r = philox(env_lo, step_lo, 0x80000000u | uint32_t(sub), step_hi);
-          ua[0] = u01(r.x);
-          ua[1] = u01(r.y);
-          ua[2] = u01(r.z);
-          ua[3] = u01(r.w);
-          ua[4] = u01(((r.x & 0xffu) << 24) | ((r.y & 0xffu) << 16) | ((r.z & 0xffu) << 8));
         }
-        float uf[3 * CPL];  // uf[3*i + event]: fire increase, fire decrease, fire spread of cell i
         if (io.field_uniforms != nullptr) {
           const size_t plane = size_t(B) * HW;
 #pragma unroll
@@ -233,7 +241,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
 #pragma unroll
             for (int ev = 0; ev < 3; ++ev) uf[3 * i + ev] = c < HW ? io.field_uniforms[ev * plane + cell_row + c] : 1.f;
           }
-        } else {
+        }
+        if (io.field_uniforms == nullptr || io.agent_uniforms == nullptr) {
           uint32_t bits[4 * kCalls];
 #pragma unroll
           for (int k = 0; k < kCalls; ++k) {
@@ -243,8 +252,29 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             bits[4 * k + 2] = r.z;
             bits[4 * k + 3] = r.w;
           }
+          if (io.field_uniforms == nullptr) {
 #pragma unroll
-          for (int j = 0; j < 3 * CPL; ++j) uf[j] = u01(bits[j]);
+            for (int j = 0; j < 3 * CPL; ++j) uf[j] = u01(bits[j]);
+          }
+          if (io.agent_uniforms == nullptr) {
+            uint32_t words[4];
+            if (kAgentFromSpare) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                words[j] = ((bits[(3 * j) % (4 * kCalls)] & 0xffu) << 24) | ((bits[(3 * j + 1) % (4 * kCalls)] & 0xffu) << 16) |
+                           ((bits[(3 * j + 2) % (4 * kCalls)] & 0xffu) << 8);
+            } else {
+              const uint4 r = philox(env_lo, step_lo, 0x80000000u | uint32_t(sub), step_hi);
+              words[0] = r.x;
+              words[1] = r.y;
+              words[2] = r.z;
+              words[3] = r.w;
+            }
+            ua[0] = ua[2] = u01(words[0]);
+            ua[1] = u01(words[1]);
+            ua[3] = u01(words[2]);
+            ua[4] = u01(words[3]);
+          }
         }
 
         // ---------------------------------------------------------------- agent transitions
@@ -416,16 +446,21 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       for (int w = 0; w < NW; ++w) n_lit += __popc(litw[w]);
       const int n_rows = max(n_lit, n_before);  // rows / mask bytes that may differ from their padding value
 
-      // publish the agents' available-cell sets and the task -> cell map for the mask builder
+      // agents able to act right now, grouped by equipment state: a cell's fighters are the union over equipment
+      // states of (agents that reach the cell in that state) & (agents in that state with suppressant left)
       int n_avail = 0;
       if (is_agent) {
         const uint32_t* rm = io.range_mask + (size_t(sub) * E + max(equip, 0)) * table_words;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          const uint32_t word = (supp > 0.f && w < table_words) ? (litw[w] & rm[w]) : 0u;
-          avail_s[sub * NW + w] = word;
-          n_avail += __popc(word);
-        }
+        for (int w = 0; w < NW; ++w) n_avail += (supp > 0.f && w < table_words) ? __popc(litw[w] & rm[w]) : 0;
+      }
+      uint32_t fighters[CPL];
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) fighters[i] = 0u;
+      for (int q = 0; q < E; ++q) {
+        const uint32_t ready = (__ballot_sync(kFullMask, is_agent && supp > 0.f && equip == q) >> group_base) & group_mask;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) fighters[i] |= cell_agents_s[q * kCells + i * G + sub] & ready;
       }
       int4* task_row = reinterpret_cast<int4*>(io.task_obs) + cell_row;
       {
@@ -435,7 +470,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           const uint32_t word = litw[(G == 32) ? i : 0];
           if ((word >> sub) & 1u) {
             const int t = rank + __popc(word & lanes_below);  // env-local task index = rank in row-major lit order
-            task_cell_s[t] = uint8_t(i * G + sub);
+            task_agents_s[t] = fighters[i];
             if (valid) task_row[t] = make_int4(yx[i] >> 16, yx[i] & 0xffff, fires[i], inten[i]);
           }
           rank += __popc(word);
@@ -447,25 +482,30 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         // padding rows only where the previous launch had real rows
         for (int t = n_lit + sub; t < n_before; t += G) task_row[t] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
 
-        // action mask [A, mask_stride] bytes indexed by env-local task; each lane assembles 4 tasks into one word
+        // action mask [A, mask_stride] bytes indexed by env-local task: a lane takes 4 tasks, transposes their agent
+        // bitmasks into byte planes (8 agents per plane) and emits one 4-byte word per agent -> coalesced row stores
         uint32_t* mask_row = reinterpret_cast<uint32_t*>(io.action_mask + size_t(env) * A * mask_stride);
         for (int q = sub; 4 * q < n_rows; q += G) {
-          const uint32_t cells4 = reinterpret_cast<const uint32_t*>(task_cell_s)[q];
-          uint32_t word_of[4], shift_of[4], keep = 0;
+          uint4 m = *reinterpret_cast<const uint4*>(task_agents_s + 4 * q);
+          m.x = 4 * q < n_lit ? m.x : 0u;
+          m.y = 4 * q + 1 < n_lit ? m.y : 0u;
+          m.z = 4 * q + 2 < n_lit ? m.z : 0u;
+          m.w = 4 * q + 3 < n_lit ? m.w : 0u;
+          const uint32_t lo01 = __byte_perm(m.x, m.y, 0x5140), lo23 = __byte_perm(m.z, m.w, 0x5140);
+          const uint32_t hi01 = __byte_perm(m.x, m.y, 0x7362), hi23 = __byte_perm(m.z, m.w, 0x7362);
+          uint32_t plane[4];
+          plane[0] = __byte_perm(lo01, lo23, 0x5410);
+          plane[1] = __byte_perm(lo01, lo23, 0x7632);
+          plane[2] = __byte_perm(hi01, hi23, 0x5410);
+          plane[3] = __byte_perm(hi01, hi23, 0x7632);
+          uint32_t* out = mask_row + q;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t c = (cells4 >> (8 * j)) & 0xffu;
-            const bool real = 4 * q + j < n_lit;
-            word_of[j] = real ? (c >> 5) : 0u;
-            shift_of[j] = c & 31u;
-            keep |= real ? (1u << (8 * j)) : 0u;
-          }
-          for (int a = 0; a < A; ++a) {
-            const uint32_t* aw = avail_s + a * NW;
-            uint32_t out = 0;
+          for (int k = 0; k < 4; ++k) {
+            if (8 * k < A) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) out |= ((aw[NW == 1 ? 0 : word_of[j]] >> shift_of[j]) & 1u) << (8 * j);
-            mask_row[a * mask_words_row + q] = out & keep;
+              for (int b = 0; b < 8; ++b)
+                if (8 * k + b < A) out[(8 * k + b) * mask_words_row] = (plane[k] >> b) & 0x01010101u;
+            }
           }
         }
 
@@ -481,9 +521,9 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           for (int i = 0; i < CPL; ++i) {
             const int c = i * G + sub;
             if (c < HW) {
-              io.fires[cell_row + c] = fires[i];
-              io.intensity[cell_row + c] = inten[i];
-              io.fuel[cell_row + c] = fuel[i];
+              fires_row[c] = fires[i];
+              inten_row[c] = inten[i];
+              fuel_row[c] = fuel[i];
             }
           }
           if (is_agent) {
@@ -584,7 +624,8 @@ int launch_step(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B,
   static int ctas_per_sm = 0, sm_count = 0;
   static size_t cached_smem = ~size_t(0);
   const int groups_per_cta = (kThreads / 32) * (32 / G);
-  const size_t smem = size_t(groups_per_cta) * group_smem_words(G * CPL, p.num_agents, (G * CPL + 31) / 32) * sizeof(uint32_t);
+  const size_t smem =
+      (size_t(p.num_equipment_states) * G * CPL + size_t(groups_per_cta) * group_smem_words(G * CPL)) * sizeof(uint32_t);
   auto kernel = wildfire_step_kernel<G, CPL>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
@@ -608,7 +649,8 @@ int launch_step(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B,
 }
 
 int dispatch(const FrzWildfireParams* p, const FrzWildfireBuffers* io, int B, int mode, void* stream) {
-  if (p == nullptr || io == nullptr || io->control == nullptr || io->fires == nullptr) {
+  if (p == nullptr || io == nullptr || io->control == nullptr || io->fires == nullptr || io->cell_agents == nullptr ||
+      io->range_mask == nullptr) {
     set_error("frz_wildfire: NULL params / buffers");
     return FRZ_ERR_NULL;
   }

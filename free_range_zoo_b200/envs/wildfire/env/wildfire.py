@@ -131,6 +131,18 @@ def flatten_configuration(config, max_steps, show_bad_actions: bool, env_offset:
     return p, _np(rc.fire_rewards, np.float32).reshape(-1), _np(fc.ignition_temp, np.int32).reshape(-1), range_mask
 
 
+def transpose_range_mask(range_mask: np.ndarray, cells: int) -> np.ndarray:
+    """[A, E, words] (bit c of agent a's row) -> [E, cells] (bit a of cell c's word): who reaches a cell."""
+    agents, states, _ = range_mask.shape
+    cell_agents = np.zeros((states, cells), dtype=np.uint32)
+    for a in range(agents):
+        for e in range(states):
+            for c in range(cells):
+                if int(range_mask[a, e, c >> 5]) >> (c & 31) & 1:
+                    cell_agents[e, c] |= np.uint32(1 << a)
+    return cell_agents
+
+
 class raw_env(BatchedAECEnv):
     """Wildfire environment whose step is one fused CUDA kernel."""
 
@@ -187,6 +199,7 @@ class raw_env(BatchedAECEnv):
         self._cell_reward = torch.from_numpy(cell_reward).to(dev)
         self._cell_ignition = torch.from_numpy(cell_ignition).to(dev)
         self._range_mask = torch.from_numpy(range_mask.view(np.int32)).to(dev)
+        self._cell_agents = torch.from_numpy(transpose_range_mask(range_mask, HW).view(np.int32)).to(dev)
         self._uniforms = (None, None)
         self._io = self._bind_buffers()
 
@@ -203,6 +216,7 @@ class raw_env(BatchedAECEnv):
             env_task_count=self.environment_task_count, agent_task_count=self._agent_task_count,
             action_mask=self._action_mask, self_obs=self._self_obs, task_obs=self._task_obs,
             cell_reward=self._cell_reward, cell_ignition=self._cell_ignition, range_mask=self._range_mask,
+            cell_agents=self._cell_agents,
             control=self._control, field_uniforms=self._uniforms[0], agent_uniforms=self._uniforms[1])
         for name, tensor in tensors.items():
             if tensor is not None:

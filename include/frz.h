@@ -147,6 +147,7 @@ typedef struct {
   const int32_t* cell_ignition;/* [H*W] fire_config.ignition_temp */
   const uint32_t* range_mask;  /* [A, E, mask_words] bit c set iff cell c is within the agent's Chebyshev range when
                                   its equipment is in state e (wildfire.py:606-616, utils/in_range_check.py:5-23) */
+  const uint32_t* cell_agents; /* [E, H*W] the same relation transposed: bit a set iff agent a reaches cell c in state e */
   /* randomness */
   FrzControl* control;
   const float* field_uniforms; /* nullable: injected uniforms [3, B, H, W] (wildfire.py:409) instead of Philox */

@@ -23,9 +23,11 @@ def main():
         elif record[0] == 'Line No':
             header = record
         elif header and record[0].isdigit():
-            get = lambda name: record[header.index(name)]
-            rows.append((current_file, int(record[0]), record[1].strip(), int(get('Instructions Executed') or 0),
-                         int(get('# Samples') or 0)))
+            def get(name):
+                value = record[header.index(name)]
+                return int(value) if value.isdigit() else 0
+
+            rows.append((current_file, int(record[0]), record[1].strip(), get('Instructions Executed'), get('# Samples')))
     total_inst = sum(r[3] for r in rows) or 1
     total_samples = sum(r[4] for r in rows) or 1
     print(f'total warp instructions {total_inst}, stall samples {total_samples}')
