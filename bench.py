@@ -2,20 +2,23 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload wildfire_c4] [--impl engine|reference]
 
-A "step" is one environment step of ALL ``parallel_envs`` environments with random legal actions.  At N=1 the workload
-is BASELINE.json configs[3] -- wildfire 10x10 / 10 agents, agent+task+frame openness, parallel_envs=65,536 -- the
-configuration the headline target (>= 50x the host-CPU path, >= 60 % of HBM roofline) is quoted on.  For N>1 (launched
-by ``python -m torch.distributed.run``) every rank steps its own 65,536-env shard (weak scaling, no step-path
-collective; the global env index keys the RNG so trajectories do not depend on N) and NCCL is used only for the
-barrier / max-over-ranks timing / statistics all-reduce.
+A "step" is one environment step of ALL ``parallel_envs`` environments with random legal actions.  At N=1 the default
+workload is BASELINE.json configs[3] -- wildfire 10x10 / 10 agents, agent+task+frame openness, parallel_envs=65,536 --
+the configuration the headline target (>= 50x the host-CPU path, >= 60 % of HBM roofline) is quoted on.  The other
+named configs (``--workload wildfire_c1 | rideshare_c2 | cyber_c3``) can be measured the same way.  For N>1 (launched
+by ``python -m torch.distributed.run``) every rank steps its own shard of ``parallel_envs`` environments (weak
+scaling, no step-path collective; the global env index keys the RNG so trajectories do not depend on N); NCCL is used
+only for the barrier, the max-over-ranks timing and the episode-statistics all-reduce.
 
 One JSON line is printed by rank 0:
-  value     whole-job env-steps/s, inputs resident in HBM, [sample_actions -> step] captured in one CUDA graph
-  roofline  the step kernel alone: algorithmic bytes per launch / CUDA-event duration vs measured HBM peak
-  e2e       same metric through the public Parallel API with HOST buffers: pinned actions H2D + step + rewards/dones D2H
-  cpu_baseline  the CPU oracle port of the same workload on the box's host cores (bounded sample)
-``--impl reference`` times the CPU oracle port (the reference's algorithm restated in numpy: the Python reference
-cannot travel to the GPU box) on all host cores and prints the same line shape.
+  value         whole-job env-steps/s, inputs resident in HBM, [sample_actions -> step] captured in one CUDA graph
+  roofline      the step kernel alone: algorithmic bytes per launch / CUDA-event duration of the
+                launch, against the measured HBM copy bandwidth of MEASURED_PEAKS.json
+  e2e           the same metric through the public Parallel API with HOST buffers: pinned actions H2D + step +
+                rewards / dones D2H + stream sync, every step
+  cpu_baseline  the CPU oracle port of the same workload on the box's host cores (bounded sample, rank 0, N=1)
+``--impl reference`` times the CPU oracle port (the reference's algorithm restated in numpy -- the Python reference
+and its uninstallable dependencies cannot travel to the GPU box) on all host cores and prints the same line shape.
 """
 from __future__ import annotations
 
@@ -30,17 +33,38 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# name: domain, preset, parallel_envs per GPU, env kwargs
 WORKLOADS = {
-    # name: (domain, preset, parallel_envs per GPU, max_steps, algorithmic bytes per env-step, agents)
-    'wildfire_c4': ('wildfire', 'wildfire_large', 65536, 1 << 30, 5600, 10),
-    'wildfire_c1': ('wildfire', 'wildfire_3x3', 1024, 1 << 30, 581, 3),
+    'wildfire_c4': dict(domain='wildfire', preset='wildfire_large', envs=65536, kwargs={}),
+    'wildfire_c1': dict(domain='wildfire', preset='wildfire_3x3', envs=1024, kwargs={}),
+    'rideshare_c2': dict(domain='rideshare', preset='rideshare_c2', envs=16384, kwargs={}),
+    'cyber_c3': dict(domain='cybersecurity', preset='cyber_c3', envs=16384,
+                     kwargs=dict(show_bad_actions=False, partially_observable=True)),
 }
+KERNELS = {'wildfire': 'wildfire_step_kernel', 'rideshare': 'rideshare_step_kernel', 'cybersecurity': 'cyber_step_kernel'}
+
+
+def algorithmic_bytes(domain: str, raw) -> float:
+    """ALGORITHMIC bytes per env-step (restated in DESIGN.md section 4): every live tensor read
+    once and written once in the reference's dtypes, outputs written once, padded int32 observations, u8 masks."""
+    if domain == 'wildfire':
+        HW, A = raw.max_y * raw.max_x, len(raw.agents)
+        state = 12 * HW + 12 * A
+        return 2 * state + 8 * A + 4 * A + 2 * A + 16 + 16 * A + 16 * HW + 4 + A * HW + 4 * A
+    if domain == 'cybersecurity':
+        N, att, dfd = raw._n_nodes, raw._n_att, raw._n_def
+        n = att + dfd
+        state = 4 * N + 4 * dfd + n
+        return 2 * state + 8 * n + 4 * n + 2 * n + 4 + (8 * att + 12 * dfd) + 8 * N + dfd + n
+    A, K = len(raw.agents), raw._capacity
+    present = float(raw.environment_task_count.float().mean().item())  # measured mean passengers per environment
+    return 2 * (8 * A + 44 * present) + 8 * A + 4 * A + 2 + 4 + 16 * A + 32 * present + A * K + 4 * (A + 1)
 
 
 def measured_peak_gbs():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
-        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
@@ -62,7 +86,7 @@ class ClockSampler:
                     self.samples.append([field.strip() for field in out.split(',')])
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._thread = threading.Thread(target=self._run, daemon=True)
@@ -89,62 +113,101 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ CPU arm
 
 
-def _oracle_worker(args):
-    domain, preset_name, envs, steps, seed = args
+def _oracle_rollout(job):
+    """Worker: steps one oracle batch and returns the seconds spent inside ``oracle.step`` (action sampling and the
+    generation of the injected uniforms are excluded, as SURVEY.md section 8d prescribes for both sides)."""
+    workload, envs, steps, seed = job
     import numpy as np
-    from free_range_zoo_b200 import presets
-    from oracle.wildfire import WildfireOracle
-    config = getattr(presets, preset_name)()
-    oracle = WildfireOracle(config, envs, 1 << 30)
-    oracle.reset()
-    rng = np.random.default_rng(seed)
-    H, W, A = oracle.H, oracle.W, oracle.A
 
-    def one_step():
-        counts = oracle.agent_task_count
-        k = np.minimum((rng.random(counts.shape) * (counts + 1)).astype(np.int64), counts)
-        actions = np.stack([k, np.where(k == counts, -1, 0)], axis=2).astype(np.int32)
-        u_field = rng.random((3, envs, H, W), dtype=np.float32)
-        u_agent = rng.random((5, envs, A), dtype=np.float32)
-        start = time.perf_counter()  # action sampling and uniform generation are excluded, like SURVEY 8(d)
-        oracle.step(actions, u_field, u_agent)
-        return time.perf_counter() - start
+    from free_range_zoo_b200 import presets
+    spec = WORKLOADS[workload]
+    config = getattr(presets, spec['preset'])()
+    rng = np.random.default_rng(seed)
+    if spec['domain'] == 'wildfire':
+        from oracle.wildfire import WildfireOracle
+        oracle = WildfireOracle(config, envs, 1 << 30, **spec['kwargs'])
+        oracle.reset()
+        H, W, A = oracle.H, oracle.W, oracle.A
+
+        def one_step():
+            counts = oracle.agent_task_count
+            k = np.minimum((rng.random(counts.shape) * (counts + 1)).astype(np.int64), counts)
+            actions = np.stack([k, np.where(k == counts, -1, 0)], axis=2).astype(np.int32)
+            uniforms = (rng.random((3, envs, H, W), dtype=np.float32), rng.random((5, envs, A), dtype=np.float32))
+            start = time.perf_counter()
+            oracle.step(actions, *uniforms)
+            return time.perf_counter() - start
+    elif spec['domain'] == 'cybersecurity':
+        from oracle.cybersecurity import CybersecurityOracle
+        oracle = CybersecurityOracle(config, envs, 1 << 30, **spec['kwargs'])
+        oracle.reset()
+
+        def one_step():
+            n = oracle.n_agents
+            count = oracle.agent_task_count
+            k = np.minimum((rng.random(count.shape) * (count + 1)).astype(np.int64), count)
+            actions = np.stack([k, np.where(k == count, -1, 0)], axis=2).astype(np.int32)  # attack / move or noop
+            uniforms = (rng.random((1, envs, oracle.N), dtype=np.float32), rng.random((1, envs, n), dtype=np.float32))
+            start = time.perf_counter()
+            oracle.step(actions, *uniforms)
+            return time.perf_counter() - start
+    else:
+        from oracle.rideshare import RideshareOracle
+        oracle = RideshareOracle(config, envs, 1 << 30)
+        oracle.reset()
+
+        def one_step():
+            actions = np.zeros((envs, oracle.A, 2), np.int32)
+            for b in range(envs):
+                for a in range(oracle.A):
+                    mine = oracle._task_list(b, a)
+                    k = min(int(rng.random() * (len(mine) + 1)), len(mine))
+                    actions[b, a] = (k, -1) if k == len(mine) else (k, oracle.tables[b][mine[k]][6])
+            start = time.perf_counter()
+            oracle.step(actions)
+            return time.perf_counter() - start
 
     one_step()
     return sum(one_step() for _ in range(steps))
 
 
-def cpu_oracle_throughput(workload: str, processes: int, envs_per_process: int, steps: int):
-    """env-steps/s of the numpy oracle, `processes` workers each stepping its own batch (max over workers)."""
+def cpu_oracle_throughput(workload: str, processes: int, envs_per_process: int, steps: int) -> float:
+    """env-steps/s of the CPU oracle: ``processes`` workers, each stepping its own batch (slowest worker counts)."""
     import multiprocessing as mp
-    domain, preset_name = WORKLOADS[workload][:2]
-    jobs = [(domain, preset_name, envs_per_process, steps, 100 + i) for i in range(processes)]
+    jobs = [(workload, envs_per_process, steps, 100 + i) for i in range(processes)]
     if processes == 1:
-        seconds = [_oracle_worker(jobs[0])]
+        seconds = [_oracle_rollout(jobs[0])]
     else:
         with mp.get_context('fork').Pool(processes) as pool:
-            seconds = pool.map(_oracle_worker, jobs)
+            seconds = pool.map(_oracle_rollout, jobs)
     return processes * envs_per_process * steps / max(seconds)
 
 
+def cpu_sample_size(workload: str):
+    """(envs per process, steps): a bounded sample (tens of seconds at most) of the same workload."""
+    return {'wildfire': (1024, 10), 'cybersecurity': (4096, 20), 'rideshare': (128, 10)}[WORKLOADS[workload]['domain']]
+
+
 def run_reference(args):
-    """--impl reference: the CPU oracle port on all host cores (rank 0 only)."""
+    """--impl reference: the CPU oracle port on all host cores (rank 0 only; other ranks exit without work)."""
     if int(os.environ.get('RANK', '0')) != 0:
         return
-    domain, preset_name, B, _, _, agents = WORKLOADS[args.workload]
+    spec = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    envs_per_process, steps = 1024, max(1, min(args.steps, 5))
-    cpu_oracle_throughput(args.workload, cores, envs_per_process, max(1, min(args.warmup, 1)))
+    envs_per_process, sample_steps = cpu_sample_size(args.workload)
+    steps = max(1, min(args.steps, sample_steps))
+    cpu_oracle_throughput(args.workload, cores, envs_per_process, 1)  # warm-up (page-in, numpy import per worker)
     start = time.perf_counter()
     value = cpu_oracle_throughput(args.workload, cores, envs_per_process, steps)
     wall = time.perf_counter() - start
-    sample = (f'{cores} processes x {envs_per_process} envs x {steps} steps of {args.workload} '
-              f'(numpy oracle port, oracle/wildfire.py; step() only)')
+    sample = (f'{cores} processes x {envs_per_process} envs x {steps} steps of {args.workload}; numpy oracle port '
+              f'(oracle/{spec["domain"]}.py) of the reference CPU path; step() only, action sampling excluded')
     line = {
         'impl': 'reference', 'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * cores * envs_per_process / value,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32+f32', 'data': 'synthetic',
-        'config': {'workload': args.workload, 'parallel_envs_sampled': cores * envs_per_process, 'agents': agents},
+        'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * cores * envs_per_process / value, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32+f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'domain': spec['domain'], 'preset': spec['preset'],
+                   'parallel_envs_sampled': cores * envs_per_process},
         'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'wall_s': wall,
@@ -156,11 +219,13 @@ def run_reference(args):
 
 
 def run_engine(args):
+    import importlib
+
     import torch
     import torch.distributed as dist
 
     from free_range_zoo_b200 import presets
-    from free_range_zoo_b200.envs import wildfire_v0
+    from free_range_zoo_b200.distributed import all_reduce_statistics, episode_statistics
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -170,13 +235,15 @@ def run_engine(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
 
-    domain, preset_name, B, max_steps, bytes_per_env, agents = WORKLOADS[args.workload]
-    if args.parallel_envs:
-        B = args.parallel_envs
-    config = getattr(presets, preset_name)()
-    env = wildfire_v0.parallel_env(parallel_envs=B, max_steps=max_steps, configuration=config, device=device,
-                                   env_offset=rank * B)
+    spec = WORKLOADS[args.workload]
+    domain = spec['domain']
+    B = args.parallel_envs or spec['envs']
+    config = getattr(presets, spec['preset'])()
+    module = importlib.import_module(f'free_range_zoo_b200.envs.{domain}_v0')
+    env = module.parallel_env(parallel_envs=B, max_steps=1 << 30, configuration=config, device=device,
+                              env_offset=rank * B, **spec['kwargs'])
     raw = env.unwrapped
+    agents = len(raw.agents)
     K, W = args.steps, max(3, args.warmup)
     SEED, SAMPLER = 2026, 2026
 
@@ -209,7 +276,7 @@ def run_engine(args):
     graph_ms = max_over_ranks(start.elapsed_time(stop))
     value = world * B * K / (graph_ms * 1e-3)
 
-    # ---- (2) the step kernel alone, CUDA events around each launch on the launching stream
+    # ---- (2) the step kernel alone: CUDA events around each launch on the launching stream
     pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for _ in range(W):
         raw.sample_actions(SAMPLER)
@@ -222,12 +289,13 @@ def run_engine(args):
         after.record()
     barrier()
     kernel_ms = sum(b.elapsed_time(a) for b, a in pairs) / K
+    bytes_per_env = algorithmic_bytes(domain, raw)
     peak, peak_kind = measured_peak_gbs()
     achieved = bytes_per_env * B / (kernel_ms * 1e-3) / 1e9
     raw.check_errors()
 
-    # ---- (3) end to end through the public Parallel API with host buffers
-    # legal actions for every step are produced by a recorded dry run of the same seeded rollout
+    # ---- (3) end to end through the public Parallel API with host buffers.  Legal actions for every step come from
+    # a recorded dry run of the same seeded rollout (the engine is deterministic, so they stay legal on replay).
     host_actions = torch.empty((W + K, B, agents, 2), dtype=torch.int32).pin_memory()
     env.reset(seed=SEED)
     for t in range(W + K):
@@ -237,7 +305,7 @@ def run_engine(args):
     torch.cuda.synchronize(device)
     host_rewards = torch.empty((B, agents), dtype=torch.float32).pin_memory()
     host_done = torch.empty((2, B), dtype=torch.uint8).pin_memory()
-    staged = raw._actions  # the engine's own device action table: H2D lands where the kernel reads
+    staged = raw._actions  # the engine's own device action table: the H2D copy lands where the kernel reads
     env.reset(seed=SEED)
 
     def e2e_step(t):
@@ -261,49 +329,45 @@ def run_engine(args):
     h2d = staged.numel() * 4
     d2h = host_rewards.numel() * 4 + host_done.numel()
 
-    # ---- episode statistics: the only collective, off the step path (SURVEY 8e)
-    stats = torch.stack([raw._cumulative.sum().double(), raw.terminated.sum().double(), raw.num_moves.sum().double()])
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    # ---- episode statistics: the only collective, off the step path (SURVEY.md section 8e)
+    stats = all_reduce_statistics(episode_statistics(raw._cumulative, raw.terminated, raw.truncated, raw.num_moves))
 
-    line = None
     if rank == 0:
-        cores = 1
-        cpu_envs, cpu_steps = 1024, 10
-        cpu_value = cpu_oracle_throughput(args.workload, cores, cpu_envs, cpu_steps) if world == 1 else None
         line = {
             'metric': 'env-steps/sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': graph_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'int32+f32', 'data': 'synthetic',
             'config': {
-                'workload': args.workload, 'domain': domain, 'preset': preset_name, 'parallel_envs_per_gpu': B,
+                'workload': args.workload, 'domain': domain, 'preset': spec['preset'], 'parallel_envs_per_gpu': B,
                 'parallel_envs_total': world * B, 'agents': agents, 'agent_steps_per_s': value * agents,
                 'actions': 'uniform random legal actions sampled on device (Philox), inside the timed region',
-                'l2': f'state+outputs per step = {bytes_per_env * B / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)'
-                if bytes_per_env * B > 126e6 else 'working set fits in L2 (launch-latency-bound config)',
+                'l2': (f'state+outputs per step = {bytes_per_env * B / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)'
+                       if bytes_per_env * B > 126e6 else
+                       f'working set {bytes_per_env * B / 1e6:.1f} MB fits in L2: launch-latency-bound configuration'),
                 'parallelism': f'dp{world} (env-batch sharding, no step-path collective)',
             },
             'roofline': {
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_kind': peak_kind, 'kernel': 'wildfire_step_kernel',
-                'kernel_ms': kernel_ms, 'algorithmic_bytes_per_env_step': bytes_per_env,
+                'traffic': None, 'peak_kind': peak_kind, 'kernel': KERNELS[domain], 'kernel_ms': kernel_ms,
+                'algorithmic_bytes_per_env_step': bytes_per_env,
             },
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_ms / K},
             'gpu_launches': 2 * K,
             'clocks': clocks.summary(),
-            'stats': {'cumulative_reward_sum': float(stats[0]), 'terminated_envs': float(stats[1]),
-                      'env_steps_executed': float(stats[2])},
+            'stats': {'env_steps_executed': float(stats[0]), 'terminated_envs': float(stats[1]),
+                      'truncated_envs': float(stats[2]), 'cumulative_reward_sum': float(stats[3:].sum())},
         }
-        if cpu_value is not None:
+        if world == 1:
+            envs_per_process, cpu_steps = cpu_sample_size(args.workload)
+            cpu_value = cpu_oracle_throughput(args.workload, 1, envs_per_process, cpu_steps)
             line['cpu_baseline'] = {
-                'value': cpu_value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                'sample': f'{cpu_envs} envs x {cpu_steps} steps of {args.workload}, numpy oracle port (oracle/wildfire.py), '
-                          f'1 process; step() only, action sampling excluded'}
+                'value': cpu_value, 'unit': 'env-steps/s', 'cores': 1, 'kind': 'port',
+                'sample': f'{envs_per_process} envs x {cpu_steps} steps of {args.workload}, CPU oracle port '
+                          f'(oracle/{domain}.py), 1 process; step() only, action sampling excluded'}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    return line
 
 
 def main():
