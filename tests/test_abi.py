@@ -68,7 +68,7 @@ def test_null_and_shape_errors_are_reported_without_a_gpu(lib):
     # non-NULL pointers but an unsupported shape -> FRZ_ERR_SHAPE before anything is launched
     dummy = ctypes.create_string_buffer(64)
     address = ctypes.addressof(dummy)
-    io.control, io.fires, io.actions = address, address, address
+    io.control, io.fires, io.actions, io.cell_agents, io.range_mask = (address,) * 5
     params.height, params.width, params.num_agents = 40, 40, 3  # 1600 cells > FRZ_MAX_CELLS
     assert lib.frz_wildfire_step(ctypes.byref(params), ctypes.byref(io), 4, None) == 2  # FRZ_ERR_SHAPE
     assert b'unsupported shape' in lib.frz_last_error()
