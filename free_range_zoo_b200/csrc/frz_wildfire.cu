@@ -50,14 +50,31 @@ __device__ __forceinline__ int group_sum(int v) {
   return v;
 }
 
-// Shared memory: one table shared by the CTA, then one region per group (= per environment in flight)
-//   uint32_t cell_agents[E * kCells]   static: bit a = agent a reaches cell c when its equipment is in state e
-//   per group: float attack[kCells]    attack power per cell, accumulated in agent order
-//              uint32_t task_agents[kCells]  env-local task t -> bitmask of the agents that may fight it
+// ballot restricted to the G lanes of this lane's group; bit j = lane j of the group
+template <int G>
+__device__ __forceinline__ uint32_t group_ballot(bool pred, int group_base, uint32_t group_mask) {
+  const uint32_t ballot = __ballot_sync(kFullMask, pred);
+  return (G == 32) ? ballot : ((ballot >> group_base) & group_mask);
+}
+
+// Shared memory of one CTA (32-bit words):
+//   static, filled once per CTA from the configuration tables
+//     cell_agents[E][kCells]   bit a = agent a reaches cell c when its equipment is in state e
+//     range_mask[A][E][NW]     bit c = cell c is within agent a's reach in equipment state e
+//     cell_static[kCells]      y | x << 8 | has-west-neighbour << 16 | has-east-neighbour << 17
+//     cell_ignition[kCells]    fire_config.ignition_temp
+//     cell_reward[kCells]      reward_config.fire_rewards (fp32)
+//   per group (= per environment in flight)
+//     attack[kCells]           fp32 attack power per cell; all zero between environments
+//     task_agents[kCells]      env-local task t -> bitmask of the agents that may fight it
 __host__ __device__ constexpr int group_smem_words(int cells) { return 2 * cells; }
+__host__ __device__ inline int static_smem_words(int cells, int agents, int states) {
+  const int words = (cells + 31) / 32;
+  return states * cells + ((agents * states * words + 3) & ~3) + 3 * cells;
+}
 
 #ifndef FRZ_WF_MIN_BLOCKS
-#define FRZ_WF_MIN_BLOCKS 2
+#define FRZ_WF_MIN_BLOCKS 3
 #endif
 
 template <int G, int CPL>
@@ -75,32 +92,54 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   extern __shared__ __align__(16) uint32_t smem[];
 
   const int lane = threadIdx.x & 31;
+  // broadcast from lane 0: tells the compiler the warp index (and everything derived from it: the environment loop,
+  // its trip count, every ballot word) is warp-uniform, so control flow stays convergent and votes need no re-sync
+  const int warp_in_cta = __shfl_sync(kFullMask, int(threadIdx.x >> 5), 0);
   const int sub = lane % G;
   const int group_base = lane - sub;
   const uint32_t group_mask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
-  const uint32_t lanes_below = (1u << sub) - 1u;
+  const uint32_t lane_bit = 1u << sub;
+  const uint32_t lanes_below = lane_bit - 1u;
   const int H = p.height, W = p.width, HW = H * W;
   const int A = p.num_agents;
   const int E = p.num_equipment_states;
   const uint32_t flags = p.flags;
-  const int groups_per_cta = (kThreads / 32) * kGroupsPerWarp;
-  const int group_in_cta = (threadIdx.x >> 5) * kGroupsPerWarp + lane / G;
   const bool show_bad = flags & FRZ_WF_SHOW_BAD_ACTIONS;
   const bool use_fuel = flags & FRZ_WF_FIRE_FUEL;
-  const int mask_stride = io.mask_stride, mask_words_row = mask_stride >> 2;
+  const int mask_words_row = io.mask_stride >> 2;
   const int table_words = io.mask_words;
 
-  uint32_t* cell_agents_s = smem;
-  uint32_t* region = smem + E * kCells + size_t(group_in_cta) * group_smem_words(kCells);
-  float* attack_s = reinterpret_cast<float*>(region);
-  uint32_t* task_agents_s = region + kCells;
+  uint32_t* const cell_agents_s = smem;
+  uint32_t* const range_mask_s = cell_agents_s + E * kCells;
+  uint32_t* const cell_static_s = range_mask_s + ((A * E * NW + 3) & ~3);
+  int* const cell_ignition_s = reinterpret_cast<int*>(cell_static_s + kCells);
+  float* const cell_reward_s = reinterpret_cast<float*>(cell_static_s + 2 * kCells);
+  uint32_t* const region = cell_static_s + 3 * kCells +
+                           (warp_in_cta * kGroupsPerWarp + lane / G) * group_smem_words(kCells);
+  float* const attack_s = reinterpret_cast<float*>(region);
+  uint32_t* const task_agents_s = region + kCells;
+
   for (int i = threadIdx.x; i < E * kCells; i += kThreads) {
     const int e = i / kCells, c = i - e * kCells;
     cell_agents_s[i] = c < HW ? io.cell_agents[e * HW + c] : 0u;
   }
+  for (int i = threadIdx.x; i < A * E * NW; i += kThreads) {
+    const int row = i / NW, w = i - row * NW;
+    range_mask_s[i] = w < table_words ? io.range_mask[row * table_words + w] : 0u;
+  }
+  for (int c = threadIdx.x; c < kCells; c += kThreads) {
+    const int y = c / W, x = c - y * W;
+    const bool in_grid = c < HW;
+    cell_static_s[c] = uint32_t(y) | (uint32_t(x) << 8) | (uint32_t(in_grid && x > 0) << 16) |
+                       (uint32_t(in_grid && x < W - 1) << 17);
+    cell_ignition_s[c] = in_grid ? io.cell_ignition[c] : 0;
+    cell_reward_s[c] = in_grid ? io.cell_reward[c] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) attack_s[i * G + sub] = 0.f;
   __syncthreads();
 
-  FrzControl* control = io.control;
+  FrzControl* const control = io.control;
   const uint64_t step = control->step;
   const uint32_t alive_prev = control->alive;
   const uint32_t agents_with_tasks = control->agents_with_tasks;
@@ -109,27 +148,22 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   // (utils/env.py:212); the flags were published by the previous launch.
   const bool skip = (mode == kStep) && ((alive_prev & 3u) != 3u);
 
-  // per-lane constants: packed (y, x) and the "has a N/W/E/S neighbour" bits of the cells this lane owns
-  int yx[CPL];
-  uint32_t edge[CPL];
-#pragma unroll
-  for (int i = 0; i < CPL; ++i) {
-    const int c = i * G + sub, y = c / W, x = c - y * W;
-    yx[i] = (y << 16) | x;
-    edge[i] = c < HW ? (uint32_t(y > 0) | (uint32_t(x > 0) << 1) | (uint32_t(x < W - 1) << 2) | (uint32_t(y < H - 1) << 3)) : 0u;
-  }
   const bool is_agent = sub < A;
   const float base_power = is_agent ? p.agent_power[sub] : 0.f;
   const float agent_yf = is_agent ? float(p.agent_y[sub]) : 0.f;
   const float agent_xf = is_agent ? float(p.agent_x[sub]) : 0.f;
+  const int burned_state = p.num_fire_states - 1, almost_state = p.num_fire_states - 2;
+  const float p_grow = (flags & FRZ_WF_STOCH_FIRE_INCREASE) ? fminf(fmaxf(p.p_increase, 0.f), 1.f) : 1.f;
+  const float p_almost = fminf(fmaxf((flags & FRZ_WF_SPECIAL_BURNOUT) ? p.p_burnout : p.p_increase, 0.f), 1.f);
 
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
 
   if (!skip) {
-    for (int env0 = blockIdx.x * groups_per_cta; env0 < B; env0 += gridDim.x * groups_per_cta) {
-      const int env = env0 + group_in_cta;
-      const bool valid = env < B;
-      if (G == 32 && !valid) continue;  // the whole warp is past the end (sub-warp groups stay for the warp syncs)
+    const int groups_per_cta = (kThreads / 32) * kGroupsPerWarp;
+    for (int env0 = (blockIdx.x * (kThreads / 32) + warp_in_cta) * kGroupsPerWarp; env0 < B;
+         env0 += gridDim.x * groups_per_cta) {
+      const int env = env0 + lane / G;
+      const bool valid = (G == 32) || env < B;  // sub-warp groups past the end stay for the warp-wide votes
       const int e = valid ? env : B - 1;
       const size_t cell_row = size_t(e) * HW;
       const size_t agent_row = size_t(e) * A;
@@ -159,10 +193,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       int n_before = 0;  // tasks published by the previous launch: rows / mask bytes beyond are already padding
 #pragma unroll
       for (int i = 0; i < CPL; ++i) {
-        const uint32_t ballot = __ballot_sync(kFullMask, fires[i] > 0);
-        const uint32_t word = (G == 32) ? ballot : ((ballot >> group_base) & group_mask);
-        litw[(G == 32) ? i : 0] = word;
-        n_before += __popc(word);
+        litw[(G == 32) ? i : 0] = group_ballot<G>(fires[i] > 0, group_base, group_mask);
+        n_before += __popc(litw[(G == 32) ? i : 0]);
       }
       if (mode != kStep) n_before = HW;  // refresh / reset: (re)write every row
 
@@ -191,21 +223,31 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         // an agent without a single task in ANY environment is skipped by the reference's decode loop
         // (wildfire.py:434): no attack, no bad-action penalty -- only its refill flag is recorded
         if (is_agent && !refill && ((agents_with_tasks >> sub) & 1u)) {
-          const uint32_t* rm = io.range_mask + (size_t(sub) * E + equip) * table_words;
+          const uint32_t* rm = range_mask_s + (sub * E + equip) * NW;
           uint32_t availw[NW];
 #pragma unroll
-          for (int w = 0; w < NW; ++w) availw[w] = (supp > 0.f && w < table_words) ? (litw[w] & rm[w]) : 0u;
-          int k = act_k, found = -1;
+          for (int w = 0; w < NW; ++w) availw[w] = supp > 0.f ? (litw[w] & rm[w]) : 0u;
+          // the k-th set bit of the agent's choice words: pick the word by running popcounts, then one select
+          int k = act_k, found = -1, base_bit = 0;
+          uint32_t chosen = 0u;
+          bool hit = false;
           if (k >= 0) {
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
               const uint32_t choices = show_bad ? litw[w] : availw[w];
               const int count = __popc(choices);
-              if (found < 0) {
-                if (k < count) found = w * 32 + select_bit(choices, k); else k -= count;
+              if (!hit) {
+                if (k < count) {
+                  hit = true;
+                  chosen = choices;
+                  base_bit = 32 * w;
+                } else {
+                  k -= count;
+                }
               }
             }
           }
+          if (hit) found = base_bit + select_bit(chosen, k);
           if (found < 0) faults |= FRZ_FAULT_BAD_TASK_INDEX;
           else if (show_bad && !bit_at<NW>(availw, found)) bad = true;  // wildfire.py:464-477
           else target = found;
@@ -213,12 +255,20 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         const bool user = target >= 0;
         const float power = base_power + p.equipment_power_bonus[equip];  // wildfire.py:455-457
 
-        // attack power per cell, accumulated in agent order through shared memory (wildfire.py:470)
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) attack_s[i * G + sub] = 0.f;
-        __syncwarp();
-        for (int a = 0; a < A; ++a) {
-          if (sub == a && user) attack_s[target] = __fadd_rn(attack_s[target], power);
+        // attack power per cell (wildfire.py:470): agents aiming at the same cell find each other with match_any and
+        // sum their powers in agent order (the association of the reference's per-agent `+=`), then scatter the sum
+        {
+          const uint32_t key = user ? (uint32_t(group_base) << 16 | uint32_t(target)) : (0x80000000u | uint32_t(lane));
+          uint32_t peers = __match_any_sync(kFullMask, key);
+          if (!user) peers = 0u;
+          float total = 0.f;
+          while (__any_sync(kFullMask, peers != 0u)) {
+            const int source = (__ffs(peers) - 1) & 31;
+            const float theirs = __shfl_sync(kFullMask, power, source);
+            if (peers != 0u) total = __fadd_rn(total, theirs);
+            peers &= peers - 1u;
+          }
+          if (user) attack_s[target] = total;
           __syncwarp();
         }
 
@@ -296,7 +346,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         const bool increased = refill && (!(flags & FRZ_WF_STOCH_REFILL) || ua[2] < p.p_refill);
         if (increased) supp = __fadd_rn(cap, p.equipment_capacity_bonus[max(equip, 0)]);
         // capacity.py:39-66 -- bucketize(right=False): first i with r <= cum[i]
-        {
+        if (__any_sync(kFullMask, increased)) {
           int pick = p.num_capacities - 1;
           for (int i = p.num_capacities - 1; i >= 0; --i)
             if (ua[3] <= p.capacity_cum[i]) pick = i;
@@ -309,50 +359,43 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         }
 
         // ---------------------------------------------------------------- fire increase + decrease per cell
-        const int burned_state = p.num_fire_states - 1, almost_state = p.num_fire_states - 2;
-        const float p_grow = (flags & FRZ_WF_STOCH_FIRE_INCREASE) ? fminf(fmaxf(p.p_increase, 0.f), 1.f) : 1.f;
-        const float p_almost = fminf(fmaxf((flags & FRZ_WF_SPECIAL_BURNOUT) ? p.p_burnout : p.p_increase, 0.f), 1.f);
         uint32_t burned_bits = 0, putout_bits = 0;  // bit i = this lane's cell i
         uint32_t burnw[NW];
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
           const float attack = attack_s[i * G + sub];
-          int f = fires[i], it = inten[i], fu = fuel[i];
+          int f = fires[i], it = inten[i];
           // fire_increase.py:43-95
-          float diff = __fadd_rn(f >= 0 ? float(f) : 0.f, -attack);
-          bool burning = f > 0 && it > 0;
-          const bool unmet = diff > 0.f && burning;
+          const bool burning = f > 0 && it > 0;
+          const float diff = __fadd_rn(f > 0 ? float(f) : 0.f, -attack);
+          const bool unmet = burning && diff > 0.f;
           const float prob_up = unmet ? (it == almost_state ? p_almost : p_grow) : 0.f;
           const bool grow = uf[3 * i] < prob_up;
-          if (grow) it += 1;
+          it += grow ? 1 : 0;
           const bool burned = grow && it >= burned_state;
-          if (burned) {
-            f = -f;
-            fu = max(fu - 1, 0);
-            burned_bits |= 1u << i;
-          }
-          // fire_decrease.py:36-80 on the post-increase state; mul and add rounded separately like the reference
-          diff = __fadd_rn(f >= 0 ? float(f) : 0.f, -attack);
-          burning = f > 0 && it > 0;
-          const bool met = diff <= 0.f && burning;
+          // fire_decrease.py:36-80 sees the post-increase state: a cell that just burned out is no longer lit, any other
+          // burning cell kept its sign and a positive intensity, so `diff` is unchanged; the product and the sum are
+          // rounded separately like the reference's two aten ops
+          const bool met = burning && !burned && diff <= 0.f;
           float prob_down = 0.f;
           if (met)
-            prob_down = (flags & FRZ_WF_STOCH_FIRE_DECREASE) ? __fadd_rn(p.p_decrease, __fmul_rn(-diff, p.decrease_bonus)) : 1.f;
-          prob_down = fminf(fmaxf(prob_down, 0.f), 1.f);
+            prob_down = (flags & FRZ_WF_STOCH_FIRE_DECREASE)
+                            ? fminf(fmaxf(__fadd_rn(p.p_decrease, __fmul_rn(-diff, p.decrease_bonus)), 0.f), 1.f) : 1.f;
           const bool shrink = uf[3 * i + 1] < prob_down;
-          if (shrink) it -= 1;
+          it -= shrink ? 1 : 0;
           const bool put = shrink && it <= 0;
-          if (put) {
-            f = -f;
-            fu -= 1;
-            putout_bits |= 1u << i;
-          }
+          if (burned) fuel[i] = max(fuel[i] - 1, 0);  // burn-out clamps the fuel (fire_increase.py:90) ...
+          if (put) fuel[i] -= 1;                      // ... putting out does not (fire_decrease.py:75)
+          if (burned || put) f = -f;
+          burned_bits |= uint32_t(burned) << i;
+          putout_bits |= uint32_t(put) << i;
           fires[i] = f;
           inten[i] = it;
-          fuel[i] = fu;
-          const uint32_t ballot = __ballot_sync(kFullMask, f > 0 && it > 0);
-          burnw[(G == 32) ? i : 0] = (G == 32) ? ballot : ((ballot >> group_base) & group_mask);
+          burnw[(G == 32) ? i : 0] = group_ballot<G>(burning && !burned && !put, group_base, group_mask);
         }
+        // the agents that scattered an attack clear it again: the table is all zero between environments
+        __syncwarp();
+        if (user) attack_s[target] = 0.f;
 
         // ---------------------------------------------------------------- fire spread (fire_spreads.py:33-59)
         float my_put_reward = 0.f, my_burn_reward = 0.f;
@@ -364,41 +407,48 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           int f = fires[i], it = inten[i];
           const bool unlit = f < 0 && it == 0 && (!use_fuel || fuel[i] > 0);
           if (__any_sync(kFullMask, unlit)) {
-            // burning-neighbour pattern of cell c: bit0 N (c-W), bit1 W (c-1), bit2 E (c+1), bit3 S (c+W)
-            uint32_t pattern;
+            // burning neighbours of cell c as bit c of four words: N = cell c-W, W = c-1, E = c+1, S = c+W
             const uint32_t cur = burnw[(G == 32) ? i : 0];
             const uint32_t prev = (G == 32 && i > 0) ? burnw[(G == 32 && i > 0) ? i - 1 : 0] : 0u;
             const uint32_t next = (G == 32 && i + 1 < NW) ? burnw[(G == 32 && i + 1 < NW) ? i + 1 : 0] : 0u;
+            uint32_t north, south;
             if (W < 32) {
-              const uint32_t north = __funnelshift_l(prev, cur, W), south = __funnelshift_r(cur, next, W);
-              const uint32_t west = __funnelshift_l(prev, cur, 1), east = __funnelshift_r(cur, next, 1);
-              pattern = ((north >> sub) & 1u) | (((west >> sub) & 1u) << 1) | (((east >> sub) & 1u) << 2) |
-                        (((south >> sub) & 1u) << 3);
-            } else {
-              pattern = uint32_t(c >= W && bit_at<NW>(burnw, c - W)) | (uint32_t(c >= 1 && bit_at<NW>(burnw, c - 1)) << 1) |
-                        (uint32_t(c + 1 < kCells && bit_at<NW>(burnw, min(c + 1, kCells - 1))) << 2) |
-                        (uint32_t(c + W < kCells && bit_at<NW>(burnw, min(c + W, kCells - 1))) << 3);
+              north = __funnelshift_l(prev, cur, W);
+              south = __funnelshift_r(cur, next, W);
+            } else {  // a row is at least one word: the neighbour word is up to NW-1 words away
+              north = 0u;
+              south = 0u;
+              const int q = W >> 5, r = W & 31;
+#pragma unroll
+              for (int w = 0; w < NW; ++w) {
+                if (w == i - q) north |= r ? (burnw[w] << r) : burnw[w];
+                if (r && w == i - q - 1) north |= burnw[w] >> (32 - r);
+                if (w == i + q) south |= r ? (burnw[w] >> r) : burnw[w];
+                if (r && w == i + q + 1) south |= burnw[w] << (32 - r);
+              }
             }
-            pattern &= edge[i];
+            const uint32_t west = __funnelshift_l(prev, cur, 1), east = __funnelshift_r(cur, next, 1);
+            const uint32_t st = cell_static_s[c];
+            // the conv sum in the reference's accumulation order N, W, E, S (spread_lut is indexed by that pattern)
+            const uint32_t pattern = uint32_t((north & lane_bit) != 0u) | (uint32_t((west & lane_bit) != 0u && (st & 0x10000u)) << 1) |
+                                     (uint32_t((east & lane_bit) != 0u && (st & 0x20000u)) << 2) |
+                                     (uint32_t((south & lane_bit) != 0u) << 3);
             const float prob = unlit ? __fadd_rn(p.spread_lut[pattern], p.p_random_ignition) : 0.f;
             if (uf[3 * i + 2] < prob) {
               f = -f;
-              it = io.cell_ignition[c];
+              it = cell_ignition_s[c];
             }
           }
           fires[i] = f;
           inten[i] = it;
           const bool put = (putout_bits >> i) & 1u, burned = (burned_bits >> i) & 1u;
-          if (put) my_put_reward += io.cell_reward[c];
-          if (burned) my_burn_reward += io.cell_reward[c];
+          if (put) my_put_reward += cell_reward_s[c];
+          if (burned) my_burn_reward += cell_reward_s[c];
           my_fuel += fuel[i];
-          const uint32_t lit_ballot = __ballot_sync(kFullMask, f > 0);
-          const uint32_t put_ballot = (__ballot_sync(kFullMask, put) >> group_base) & group_mask;
-          const uint32_t burn_ballot = (__ballot_sync(kFullMask, burned) >> group_base) & group_mask;
-          litw[(G == 32) ? i : 0] = (G == 32) ? lit_ballot : ((lit_ballot >> group_base) & group_mask);
-          putw[(G == 32) ? i : 0] = put_ballot;
-          n_putout += __popc(put_ballot);
-          n_burned += __popc(burn_ballot);
+          litw[(G == 32) ? i : 0] = group_ballot<G>(f > 0, group_base, group_mask);
+          putw[(G == 32) ? i : 0] = group_ballot<G>(put, group_base, group_mask);
+          n_putout += __popc(putw[(G == 32) ? i : 0]);
+          n_burned += __popc(group_ballot<G>(burned, group_base, group_mask));
         }
 
         // ---------------------------------------------------------------- rewards + termination (wildfire.py:534-582)
@@ -426,7 +476,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         reward = bad ? p.bad_attack_penalty : 0.f;
         float gain = put_total;
         if (flags & FRZ_WF_LOCALIZE_PUTOUTS)
-          gain = (target >= 0 && bit_at<NW>(putw, target)) ? io.cell_reward[target] : 0.f;
+          gain = (target >= 0 && bit_at<NW>(putw, target)) ? cell_reward_s[target] : 0.f;
         reward = __fadd_rn(reward, __fadd_rn(gain, penalty_total));
         if (newly) {
           const float penalty = __fmul_rn(p.termination_kappa, logf(__fadd_rn(float(total_burnouts), 1.f)));
@@ -446,72 +496,64 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       for (int w = 0; w < NW; ++w) n_lit += __popc(litw[w]);
       const int n_rows = max(n_lit, n_before);  // rows / mask bytes that may differ from their padding value
 
+      int n_avail = 0;
+      if (is_agent && supp > 0.f) {
+        const uint32_t* rm = range_mask_s + (sub * E + max(equip, 0)) * NW;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) n_avail += __popc(litw[w] & rm[w]);
+      }
       // agents able to act right now, grouped by equipment state: a cell's fighters are the union over equipment
       // states of (agents that reach the cell in that state) & (agents in that state with suppressant left)
-      int n_avail = 0;
-      if (is_agent) {
-        const uint32_t* rm = io.range_mask + (size_t(sub) * E + max(equip, 0)) * table_words;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) n_avail += (supp > 0.f && w < table_words) ? __popc(litw[w] & rm[w]) : 0;
-      }
       uint32_t fighters[CPL];
 #pragma unroll
       for (int i = 0; i < CPL; ++i) fighters[i] = 0u;
       for (int q = 0; q < E; ++q) {
-        const uint32_t ready = (__ballot_sync(kFullMask, is_agent && supp > 0.f && equip == q) >> group_base) & group_mask;
+        const uint32_t ready = group_ballot<G>(is_agent && supp > 0.f && equip == q, group_base, group_mask);
 #pragma unroll
         for (int i = 0; i < CPL; ++i) fighters[i] |= cell_agents_s[q * kCells + i * G + sub] & ready;
       }
-      int4* task_row = reinterpret_cast<int4*>(io.task_obs) + cell_row;
+      int4* const task_row = reinterpret_cast<int4*>(io.task_obs) + cell_row;
       {
         int rank = 0;
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
           const uint32_t word = litw[(G == 32) ? i : 0];
-          if ((word >> sub) & 1u) {
+          if (word & lane_bit) {
             const int t = rank + __popc(word & lanes_below);  // env-local task index = rank in row-major lit order
+            const uint32_t st = cell_static_s[i * G + sub];
             task_agents_s[t] = fighters[i];
-            if (valid) task_row[t] = make_int4(yx[i] >> 16, yx[i] & 0xffff, fires[i], inten[i]);
+            if (valid) task_row[t] = make_int4(int(st & 0xffu), int((st >> 8) & 0xffu), fires[i], inten[i]);
           }
           rank += __popc(word);
         }
       }
+      // tasks of the previous launch that no longer exist: their rows go back to padding, their mask bytes to zero
+      const int quads = (n_rows + 3) >> 2;
+      for (int t = n_lit + sub; t < 4 * quads; t += G) {
+        task_agents_s[t] = 0u;
+        if (valid && t < n_before) task_row[t] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
+      }
       __syncwarp();
 
       if (valid) {
-        // padding rows only where the previous launch had real rows
-        for (int t = n_lit + sub; t < n_before; t += G) task_row[t] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
-
-        // action mask [A, mask_stride] bytes indexed by env-local task: a lane takes 4 tasks, transposes their agent
-        // bitmasks into byte planes (8 agents per plane) and emits one 4-byte word per agent -> coalesced row stores
-        uint32_t* mask_row = reinterpret_cast<uint32_t*>(io.action_mask + size_t(env) * A * mask_stride);
-        for (int q = sub; 4 * q < n_rows; q += G) {
-          uint4 m = *reinterpret_cast<const uint4*>(task_agents_s + 4 * q);
-          m.x = 4 * q < n_lit ? m.x : 0u;
-          m.y = 4 * q + 1 < n_lit ? m.y : 0u;
-          m.z = 4 * q + 2 < n_lit ? m.z : 0u;
-          m.w = 4 * q + 3 < n_lit ? m.w : 0u;
-          const uint32_t lo01 = __byte_perm(m.x, m.y, 0x5140), lo23 = __byte_perm(m.z, m.w, 0x5140);
-          const uint32_t hi01 = __byte_perm(m.x, m.y, 0x7362), hi23 = __byte_perm(m.z, m.w, 0x7362);
-          uint32_t plane[4];
-          plane[0] = __byte_perm(lo01, lo23, 0x5410);
-          plane[1] = __byte_perm(lo01, lo23, 0x7632);
-          plane[2] = __byte_perm(hi01, hi23, 0x5410);
-          plane[3] = __byte_perm(hi01, hi23, 0x7632);
-          uint32_t* out = mask_row + q;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (8 * k < A) {
-#pragma unroll
-              for (int b = 0; b < 8; ++b)
-                if (8 * k + b < A) out[(8 * k + b) * mask_words_row] = (plane[k] >> b) & 0x01010101u;
-            }
+        // action mask [A, mask_stride] bytes indexed by env-local task.  Work item = (agent, 4 consecutive tasks): the
+        // four tasks' agent bitmasks are shifted to the agent's bit and packed into one 4-byte store.  Items are laid
+        // out [agent][quad] with the quad count rounded up to a power of two, 32 (or G) items per pass.
+        uint32_t* const mask_row = reinterpret_cast<uint32_t*>(io.action_mask) + size_t(env) * A * mask_words_row;
+        const int shift = 32 - __clz(max(quads, 1) - 1);  // log2 of the rounded-up quad count
+        const int items = A << shift;
+        for (int item = sub; item < items; item += G) {
+          const int a = item >> shift, q = item & ((1 << shift) - 1);
+          if (q < quads) {
+            const uint4 m = *reinterpret_cast<const uint4*>(task_agents_s + 4 * q);
+            const uint32_t lo = __byte_perm(m.x >> a, m.y >> a, 0x0040), hi = __byte_perm(m.z >> a, m.w >> a, 0x0040);
+            mask_row[a * mask_words_row + q] = __byte_perm(lo, hi, 0x5410) & 0x01010101u;
           }
         }
 
         if (is_agent) {
           io.agent_task_count[agent_row + sub] = n_avail;
-          if (n_avail > 0) agent_bits |= 1u << sub;
+          if (n_avail > 0) agent_bits |= lane_bit;
           reinterpret_cast<float4*>(io.self_obs)[agent_row + sub] = make_float4(agent_yf, agent_xf, base_power, supp);
         }
         if (sub == 0) io.env_task_count[env] = n_lit;
@@ -624,8 +666,8 @@ int launch_step(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B,
   static int ctas_per_sm = 0, sm_count = 0;
   static size_t cached_smem = ~size_t(0);
   const int groups_per_cta = (kThreads / 32) * (32 / G);
-  const size_t smem =
-      (size_t(p.num_equipment_states) * G * CPL + size_t(groups_per_cta) * group_smem_words(G * CPL)) * sizeof(uint32_t);
+  const size_t smem = (size_t(static_smem_words(G * CPL, p.num_agents, p.num_equipment_states)) +
+                       size_t(groups_per_cta) * group_smem_words(G * CPL)) * sizeof(uint32_t);
   auto kernel = wildfire_step_kernel<G, CPL>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
