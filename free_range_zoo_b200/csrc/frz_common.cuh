@@ -64,6 +64,40 @@ __device__ __forceinline__ int select_bit(uint32_t w, int k) {
   return pos;
 }
 
+// ---------------------------------------------------------------------------------------------- shared memory
+
+// Shared memory is addressed through explicit 32-bit shared-window addresses (one base register + immediates) instead
+// of generic pointers: the compiler then emits plain LDS/STS [R + imm] and never re-derives the window base.
+__device__ __forceinline__ uint32_t shared_address(const void* pointer) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(pointer));
+}
+// read-only tables (written once before a __syncthreads): loads may be combined / moved freely
+__device__ __forceinline__ uint32_t lds_const(uint32_t address) {
+  uint32_t value;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(value) : "r"(address));
+  return value;
+}
+__device__ __forceinline__ uint4 lds_const_v4(uint32_t address) {
+  uint4 value;
+  asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(value.x), "=r"(value.y), "=r"(value.z), "=r"(value.w) : "r"(address));
+  return value;
+}
+// scratch that changes between warp-level synchronisation points: ordered with respect to each other
+__device__ __forceinline__ uint32_t lds(uint32_t address) {
+  uint32_t value;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(value) : "r"(address) : "memory");
+  return value;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t address) {
+  uint4 value;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(value.x), "=r"(value.y), "=r"(value.z), "=r"(value.w) : "r"(address) : "memory");
+  return value;
+}
+__device__ __forceinline__ void sts(uint32_t address, uint32_t value) {
+  asm volatile("st.shared.u32 [%0], %1;" : : "r"(address), "r"(value) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- launch epilogue
 
 // Called by every CTA once, after its last environment.

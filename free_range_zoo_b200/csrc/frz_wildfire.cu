@@ -59,28 +59,47 @@ __device__ __forceinline__ uint32_t group_ballot(bool pred, int group_base, uint
 
 // Shared memory of one CTA (32-bit words):
 //   static, filled once per CTA from the configuration tables
-//     cell_agents[E][kCells]   bit a = agent a reaches cell c when its equipment is in state e
-//     range_mask[A][E][NW]     bit c = cell c is within agent a's reach in equipment state e
 //     cell_static[kCells]      y | x << 8 | has-west-neighbour << 16 | has-east-neighbour << 17
 //     cell_ignition[kCells]    fire_config.ignition_temp
 //     cell_reward[kCells]      reward_config.fire_rewards (fp32)
-//   per group (= per environment in flight)
+//   per group (= per environment in flight), groups_per_cta times
 //     attack[kCells]           fp32 attack power per cell; all zero between environments
 //     task_agents[kCells]      env-local task t -> bitmask of the agents that may fight it
+//   static again (sizes depend on the configuration, so they come last: every offset above is a constant)
+//     cell_agents[E][kCells]   bit a = agent a reaches cell c when its equipment is in state e
+//     range_mask[A][E][NW]     bit c = cell c is within agent a's reach in equipment state e
 __host__ __device__ constexpr int group_smem_words(int cells) { return 2 * cells; }
 __host__ __device__ inline int static_smem_words(int cells, int agents, int states) {
   const int words = (cells + 31) / 32;
-  return states * cells + ((agents * states * words + 3) & ~3) + 3 * cells;
+  return 3 * cells + states * cells + agents * states * words;
+}
+
+// the NW range-mask words of one (agent, equipment state) row; one 16-byte load when the row is four words
+template <int NW>
+__device__ __forceinline__ void load_range_words(uint32_t address, uint32_t (&words)[NW]) {
+  if constexpr (NW == 4) {
+    const uint4 v = lds_const_v4(address);
+    words[0] = v.x;
+    words[1] = v.y;
+    words[2] = v.z;
+    words[3] = v.w;
+  } else {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) words[w] = lds_const(address + 4u * w);
+  }
 }
 
 #ifndef FRZ_WF_MIN_BLOCKS
 #define FRZ_WF_MIN_BLOCKS 3
 #endif
 
-template <int G, int CPL>
+// MODE: kStep or kRefresh.  INJECTED: the caller supplies uniforms (parity mode) for the field and / or the agents;
+// the production path (in-kernel Philox only) is compiled without those loads.
+template <int G, int CPL, int MODE, bool INJECTED>
 __global__ void __launch_bounds__(kThreads, (G * CPL > 128) ? 1 : FRZ_WF_MIN_BLOCKS)
 wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_constant__ FrzWildfireBuffers io,
-                     const int B, const int mode) {
+                     const int B) {
+  constexpr int mode = MODE;
   constexpr int kGroupsPerWarp = 32 / G;
   constexpr int kCells = G * CPL;
   constexpr int NW = (kCells + 31) / 32;
@@ -109,34 +128,38 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   const int mask_words_row = io.mask_stride >> 2;
   const int table_words = io.mask_words;
 
-  uint32_t* const cell_agents_s = smem;
-  uint32_t* const range_mask_s = cell_agents_s + E * kCells;
-  uint32_t* const cell_static_s = range_mask_s + ((A * E * NW + 3) & ~3);
-  int* const cell_ignition_s = reinterpret_cast<int*>(cell_static_s + kCells);
-  float* const cell_reward_s = reinterpret_cast<float*>(cell_static_s + 2 * kCells);
-  uint32_t* const region = cell_static_s + 3 * kCells +
-                           (warp_in_cta * kGroupsPerWarp + lane / G) * group_smem_words(kCells);
-  float* const attack_s = reinterpret_cast<float*>(region);
-  uint32_t* const task_agents_s = region + kCells;
+  // word offsets into smem[] (see the layout above): everything but the range-mask base is a compile-time constant
+  // plus, for the per-group region, one per-thread register -- shared memory is only ever addressed as smem[offset]
+  constexpr int kStaticOff = 0, kIgnitionOff = kCells, kRewardOff = 2 * kCells, kRegionOff = 3 * kCells;
+  constexpr int kCellAgentsOff = kRegionOff + (kThreads / 32) * kGroupsPerWarp * group_smem_words(kCells);
+  const int range_off = kCellAgentsOff + E * kCells;
+  const int attack_off = kRegionOff + (warp_in_cta * kGroupsPerWarp + lane / G) * group_smem_words(kCells);
+  const int tasks_off = attack_off + kCells;
+  // 32-bit shared-window byte addresses: static tables at this lane's cell column, this group's scratch region
+  const uint32_t s_base = shared_address(smem);
+  const uint32_t s_cell = s_base + 4u * uint32_t(sub);
+  const uint32_t s_attack = s_base + 4u * uint32_t(attack_off);
+  const uint32_t s_tasks = s_base + 4u * uint32_t(tasks_off);
+  const uint32_t s_range = s_base + 4u * uint32_t(range_off);
 
   for (int i = threadIdx.x; i < E * kCells; i += kThreads) {
     const int e = i / kCells, c = i - e * kCells;
-    cell_agents_s[i] = c < HW ? io.cell_agents[e * HW + c] : 0u;
+    smem[kCellAgentsOff + i] = c < HW ? io.cell_agents[e * HW + c] : 0u;
   }
   for (int i = threadIdx.x; i < A * E * NW; i += kThreads) {
     const int row = i / NW, w = i - row * NW;
-    range_mask_s[i] = w < table_words ? io.range_mask[row * table_words + w] : 0u;
+    smem[range_off + i] = w < table_words ? io.range_mask[row * table_words + w] : 0u;
   }
   for (int c = threadIdx.x; c < kCells; c += kThreads) {
     const int y = c / W, x = c - y * W;
     const bool in_grid = c < HW;
-    cell_static_s[c] = uint32_t(y) | (uint32_t(x) << 8) | (uint32_t(in_grid && x > 0) << 16) |
-                       (uint32_t(in_grid && x < W - 1) << 17);
-    cell_ignition_s[c] = in_grid ? io.cell_ignition[c] : 0;
-    cell_reward_s[c] = in_grid ? io.cell_reward[c] : 0.f;
+    smem[kStaticOff + c] = uint32_t(y) | (uint32_t(x) << 8) | (uint32_t(in_grid && x > 0) << 16) |
+                           (uint32_t(in_grid && x < W - 1) << 17);
+    smem[kIgnitionOff + c] = in_grid ? uint32_t(io.cell_ignition[c]) : 0u;
+    smem[kRewardOff + c] = in_grid ? __float_as_uint(io.cell_reward[c]) : 0u;
   }
 #pragma unroll
-  for (int i = 0; i < CPL; ++i) attack_s[i * G + sub] = 0.f;
+  for (int i = 0; i < CPL; ++i) smem[attack_off + i * G + sub] = 0u;
   __syncthreads();
 
   FrzControl* const control = io.control;
@@ -223,10 +246,10 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         // an agent without a single task in ANY environment is skipped by the reference's decode loop
         // (wildfire.py:434): no attack, no bad-action penalty -- only its refill flag is recorded
         if (is_agent && !refill && ((agents_with_tasks >> sub) & 1u)) {
-          const uint32_t* rm = range_mask_s + (sub * E + equip) * NW;
           uint32_t availw[NW];
+          load_range_words<NW>(s_range + 4u * uint32_t((sub * E + equip) * NW), availw);
 #pragma unroll
-          for (int w = 0; w < NW; ++w) availw[w] = supp > 0.f ? (litw[w] & rm[w]) : 0u;
+          for (int w = 0; w < NW; ++w) availw[w] = supp > 0.f ? (litw[w] & availw[w]) : 0u;
           // the k-th set bit of the agent's choice words: pick the word by running popcounts, then one select
           int k = act_k, found = -1, base_bit = 0;
           uint32_t chosen = 0u;
@@ -268,7 +291,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             if (peers != 0u) total = __fadd_rn(total, theirs);
             peers &= peers - 1u;
           }
-          if (user) attack_s[target] = total;
+          if (user) sts(s_attack + 4u * uint32_t(target), __float_as_uint(total));
           __syncwarp();
         }
 
@@ -278,12 +301,14 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         // Agent events: 0 suppressant decrease, 1 equipment, 2 refill, 3 capacity pick, 4 tank switch (wildfire.py:492-513).
         // "decrease" needs a fight action and "refill" a refill action, so in Philox mode events 0 and 2 share one draw.
         float ua[5], uf[3 * CPL];  // uf[3*i + event]: fire increase, fire decrease, fire spread of this lane's cell i
-        if (io.agent_uniforms != nullptr) {
+        const bool inject_agent = INJECTED && io.agent_uniforms != nullptr;
+        const bool inject_field = INJECTED && io.field_uniforms != nullptr;
+        if (inject_agent) {
 #pragma unroll
           for (int ev = 0; ev < 5; ++ev)
             ua[ev] = is_agent ? io.agent_uniforms[(size_t(ev) * B + e) * A + sub] : 1.f;
         }
-        if (io.field_uniforms != nullptr) {
+        if (inject_field) {
           const size_t plane = size_t(B) * HW;
 #pragma unroll
           for (int i = 0; i < CPL; ++i) {
@@ -292,7 +317,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             for (int ev = 0; ev < 3; ++ev) uf[3 * i + ev] = c < HW ? io.field_uniforms[ev * plane + cell_row + c] : 1.f;
           }
         }
-        if (io.field_uniforms == nullptr || io.agent_uniforms == nullptr) {
+        if (!inject_field || !inject_agent) {
           uint32_t bits[4 * kCalls];
 #pragma unroll
           for (int k = 0; k < kCalls; ++k) {
@@ -302,11 +327,11 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             bits[4 * k + 2] = r.z;
             bits[4 * k + 3] = r.w;
           }
-          if (io.field_uniforms == nullptr) {
+          if (!inject_field) {
 #pragma unroll
             for (int j = 0; j < 3 * CPL; ++j) uf[j] = u01(bits[j]);
           }
-          if (io.agent_uniforms == nullptr) {
+          if (!inject_agent) {
             uint32_t words[4];
             if (kAgentFromSpare) {
 #pragma unroll
@@ -363,7 +388,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         uint32_t burnw[NW];
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
-          const float attack = attack_s[i * G + sub];
+          const float attack = __uint_as_float(lds(s_attack + 4u * uint32_t(i * G + sub)));
           int f = fires[i], it = inten[i];
           // fire_increase.py:43-95
           const bool burning = f > 0 && it > 0;
@@ -395,7 +420,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         }
         // the agents that scattered an attack clear it again: the table is all zero between environments
         __syncwarp();
-        if (user) attack_s[target] = 0.f;
+        if (user) sts(s_attack + 4u * uint32_t(target), 0u);
 
         // ---------------------------------------------------------------- fire spread (fire_spreads.py:33-59)
         float my_put_reward = 0.f, my_burn_reward = 0.f;
@@ -428,7 +453,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
               }
             }
             const uint32_t west = __funnelshift_l(prev, cur, 1), east = __funnelshift_r(cur, next, 1);
-            const uint32_t st = cell_static_s[c];
+            const uint32_t st = lds_const(s_cell + 4u * (kStaticOff + i * G));
             // the conv sum in the reference's accumulation order N, W, E, S (spread_lut is indexed by that pattern)
             const uint32_t pattern = uint32_t((north & lane_bit) != 0u) | (uint32_t((west & lane_bit) != 0u && (st & 0x10000u)) << 1) |
                                      (uint32_t((east & lane_bit) != 0u && (st & 0x20000u)) << 2) |
@@ -436,14 +461,17 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             const float prob = unlit ? __fadd_rn(p.spread_lut[pattern], p.p_random_ignition) : 0.f;
             if (uf[3 * i + 2] < prob) {
               f = -f;
-              it = cell_ignition_s[c];
+              it = int(lds_const(s_cell + 4u * (kIgnitionOff + i * G)));
             }
           }
           fires[i] = f;
           inten[i] = it;
           const bool put = (putout_bits >> i) & 1u, burned = (burned_bits >> i) & 1u;
-          if (put) my_put_reward += cell_reward_s[c];
-          if (burned) my_burn_reward += cell_reward_s[c];
+          if (put || burned) {
+            const float cell_reward = __uint_as_float(lds_const(s_cell + 4u * (kRewardOff + i * G)));
+            if (put) my_put_reward += cell_reward;
+            if (burned) my_burn_reward += cell_reward;
+          }
           my_fuel += fuel[i];
           litw[(G == 32) ? i : 0] = group_ballot<G>(f > 0, group_base, group_mask);
           putw[(G == 32) ? i : 0] = group_ballot<G>(put, group_base, group_mask);
@@ -476,7 +504,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         reward = bad ? p.bad_attack_penalty : 0.f;
         float gain = put_total;
         if (flags & FRZ_WF_LOCALIZE_PUTOUTS)
-          gain = (target >= 0 && bit_at<NW>(putw, target)) ? cell_reward_s[target] : 0.f;
+          gain = (target >= 0 && bit_at<NW>(putw, target)) ? __uint_as_float(lds_const(s_base + 4u * uint32_t(kRewardOff + target))) : 0.f;
         reward = __fadd_rn(reward, __fadd_rn(gain, penalty_total));
         if (newly) {
           const float penalty = __fmul_rn(p.termination_kappa, logf(__fadd_rn(float(total_burnouts), 1.f)));
@@ -498,9 +526,10 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
 
       int n_avail = 0;
       if (is_agent && supp > 0.f) {
-        const uint32_t* rm = range_mask_s + (sub * E + max(equip, 0)) * NW;
+        uint32_t reach[NW];
+        load_range_words<NW>(s_range + 4u * uint32_t((sub * E + max(equip, 0)) * NW), reach);
 #pragma unroll
-        for (int w = 0; w < NW; ++w) n_avail += __popc(litw[w] & rm[w]);
+        for (int w = 0; w < NW; ++w) n_avail += __popc(litw[w] & reach[w]);
       }
       // agents able to act right now, grouped by equipment state: a cell's fighters are the union over equipment
       // states of (agents that reach the cell in that state) & (agents in that state with suppressant left)
@@ -510,7 +539,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       for (int q = 0; q < E; ++q) {
         const uint32_t ready = group_ballot<G>(is_agent && supp > 0.f && equip == q, group_base, group_mask);
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) fighters[i] |= cell_agents_s[q * kCells + i * G + sub] & ready;
+        for (int i = 0; i < CPL; ++i) fighters[i] |= lds_const(s_cell + 4u * uint32_t(kCellAgentsOff + q * kCells + i * G)) & ready;
       }
       int4* const task_row = reinterpret_cast<int4*>(io.task_obs) + cell_row;
       {
@@ -520,8 +549,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           const uint32_t word = litw[(G == 32) ? i : 0];
           if (word & lane_bit) {
             const int t = rank + __popc(word & lanes_below);  // env-local task index = rank in row-major lit order
-            const uint32_t st = cell_static_s[i * G + sub];
-            task_agents_s[t] = fighters[i];
+            const uint32_t st = lds_const(s_cell + 4u * (kStaticOff + i * G));
+            sts(s_tasks + 4u * uint32_t(t), fighters[i]);
             if (valid) task_row[t] = make_int4(int(st & 0xffu), int((st >> 8) & 0xffu), fires[i], inten[i]);
           }
           rank += __popc(word);
@@ -530,7 +559,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       // tasks of the previous launch that no longer exist: their rows go back to padding, their mask bytes to zero
       const int quads = (n_rows + 3) >> 2;
       for (int t = n_lit + sub; t < 4 * quads; t += G) {
-        task_agents_s[t] = 0u;
+        sts(s_tasks + 4u * uint32_t(t), 0u);
         if (valid && t < n_before) task_row[t] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
       }
       __syncwarp();
@@ -542,10 +571,12 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         uint32_t* const mask_row = reinterpret_cast<uint32_t*>(io.action_mask) + size_t(env) * A * mask_words_row;
         const int shift = 32 - __clz(max(quads, 1) - 1);  // log2 of the rounded-up quad count
         const int items = A << shift;
-        for (int item = sub; item < items; item += G) {
+        // (for one environment per warp the trip count is warp-uniform; the predicate inside does the rest)
+        for (int first = 0; first < items; first += G) {
+          const int item = first + sub;
           const int a = item >> shift, q = item & ((1 << shift) - 1);
-          if (q < quads) {
-            const uint4 m = *reinterpret_cast<const uint4*>(task_agents_s + 4 * q);
+          if (a < A && q < quads) {
+            const uint4 m = lds_v4(s_tasks + 16u * uint32_t(q));
             const uint32_t lo = __byte_perm(m.x >> a, m.y >> a, 0x0040), hi = __byte_perm(m.z >> a, m.w >> a, 0x0040);
             mask_row[a * mask_words_row + q] = __byte_perm(lo, hi, 0x5410) & 0x01010101u;
           }
@@ -661,14 +692,14 @@ bool pick_geometry(const FrzWildfireParams& p, Geometry* g) {
   return true;
 }
 
-template <int G, int CPL>
-int launch_step(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B, int mode, cudaStream_t stream) {
+template <int G, int CPL, int MODE, bool INJECTED>
+int launch_variant(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B, cudaStream_t stream) {
   static int ctas_per_sm = 0, sm_count = 0;
   static size_t cached_smem = ~size_t(0);
   const int groups_per_cta = (kThreads / 32) * (32 / G);
   const size_t smem = (size_t(static_smem_words(G * CPL, p.num_agents, p.num_equipment_states)) +
                        size_t(groups_per_cta) * group_smem_words(G * CPL)) * sizeof(uint32_t);
-  auto kernel = wildfire_step_kernel<G, CPL>;
+  auto kernel = wildfire_step_kernel<G, CPL, MODE, INJECTED>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
       return check_launch("wildfire smem attribute");
@@ -686,8 +717,15 @@ int launch_step(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B,
   const int work = (B + groups_per_cta - 1) / groups_per_cta;
   const int cap = sm_count * ctas_per_sm;
   const int grid = work < cap ? work : cap;
-  kernel<<<grid, kThreads, smem, stream>>>(p, io, B, mode);
+  kernel<<<grid, kThreads, smem, stream>>>(p, io, B);
   return check_launch("wildfire_step_kernel");
+}
+
+template <int G, int CPL>
+int launch_step(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B, int mode, cudaStream_t stream) {
+  if (mode != kStep) return launch_variant<G, CPL, kRefresh, false>(p, io, B, stream);
+  if (io.field_uniforms != nullptr || io.agent_uniforms != nullptr) return launch_variant<G, CPL, kStep, true>(p, io, B, stream);
+  return launch_variant<G, CPL, kStep, false>(p, io, B, stream);
 }
 
 int dispatch(const FrzWildfireParams* p, const FrzWildfireBuffers* io, int B, int mode, void* stream) {
