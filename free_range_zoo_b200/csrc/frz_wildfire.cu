@@ -59,7 +59,7 @@ __device__ __forceinline__ uint32_t group_ballot(bool pred, int group_base, uint
 
 // Shared memory of one CTA (32-bit words):
 //   static, filled once per CTA from the configuration tables
-//     cell_static[kCells]      y | x << 8 | has-west-neighbour << 16 | has-east-neighbour << 17
+//     cell_y[kCells], cell_x[kCells]   grid coordinates of cell c
 //     cell_ignition[kCells]    fire_config.ignition_temp
 //     cell_reward[kCells]      reward_config.fire_rewards (fp32)
 //   per group (= per environment in flight), groups_per_cta times
@@ -71,7 +71,7 @@ __device__ __forceinline__ uint32_t group_ballot(bool pred, int group_base, uint
 __host__ __device__ constexpr int group_smem_words(int cells) { return 2 * cells; }
 __host__ __device__ inline int static_smem_words(int cells, int agents, int states) {
   const int words = (cells + 31) / 32;
-  return 3 * cells + states * cells + agents * states * words;
+  return 4 * cells + states * cells + agents * states * words;
 }
 
 // the NW range-mask words of one (agent, equipment state) row; one 16-byte load when the row is four words
@@ -95,18 +95,24 @@ __device__ __forceinline__ void load_range_words(uint32_t address, uint32_t (&wo
 
 // MODE: kStep or kRefresh.  INJECTED: the caller supplies uniforms (parity mode) for the field and / or the agents;
 // the production path (in-kernel Philox only) is compiled without those loads.
+// Launch-time constants derived from the configuration on the host (fold_configuration below).
+struct Derived {
+  uint32_t west_ok[FRZ_MAX_CELLS / 32];  // bit c: cell c has a western neighbour (x > 0)
+  uint32_t east_ok[FRZ_MAX_CELLS / 32];  // bit c: cell c has an eastern neighbour (x < W - 1)
+  int32_t spare_lanes_feed_agents;       // Philox: the agents' four words come from lanes whose last cell is off-grid
+};
+
 template <int G, int CPL, int MODE, bool INJECTED>
 __global__ void __launch_bounds__(kThreads, (G * CPL > 128) ? 1 : FRZ_WF_MIN_BLOCKS)
 wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_constant__ FrzWildfireBuffers io,
-                     const int B) {
+                     const __grid_constant__ Derived derived, const int B) {
   constexpr int mode = MODE;
   constexpr int kGroupsPerWarp = 32 / G;
   constexpr int kCells = G * CPL;
   constexpr int NW = (kCells + 31) / 32;
-  // Philox calls per lane: 3 x 24-bit uniforms per cell; with >= 4 cells per lane the 12 spare low bytes of the first
-  // twelve words also yield the agent's four 24-bit uniforms, otherwise the agent needs a call of its own
-  constexpr int kCalls = (3 * CPL + 3) / 4;
-  constexpr bool kAgentFromSpare = CPL >= 4;
+  // Philox words per lane: two per cell (a cell consumes either its fire-increase or its fire-decrease draw, never
+  // both, so the two events share a word; the other word is the spread draw) and four per agent
+  constexpr int kCalls = (2 * CPL + 3) / 4;
   static_assert(G == 32 || CPL == 1, "sub-warp groups hold one cell per lane");
   extern __shared__ __align__(16) uint32_t smem[];
 
@@ -130,7 +136,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
 
   // word offsets into smem[] (see the layout above): everything but the range-mask base is a compile-time constant
   // plus, for the per-group region, one per-thread register -- shared memory is only ever addressed as smem[offset]
-  constexpr int kStaticOff = 0, kIgnitionOff = kCells, kRewardOff = 2 * kCells, kRegionOff = 3 * kCells;
+  constexpr int kYOff = 0, kXOff = kCells, kIgnitionOff = 2 * kCells, kRewardOff = 3 * kCells, kRegionOff = 4 * kCells;
   constexpr int kCellAgentsOff = kRegionOff + (kThreads / 32) * kGroupsPerWarp * group_smem_words(kCells);
   const int range_off = kCellAgentsOff + E * kCells;
   const int attack_off = kRegionOff + (warp_in_cta * kGroupsPerWarp + lane / G) * group_smem_words(kCells);
@@ -153,8 +159,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   for (int c = threadIdx.x; c < kCells; c += kThreads) {
     const int y = c / W, x = c - y * W;
     const bool in_grid = c < HW;
-    smem[kStaticOff + c] = uint32_t(y) | (uint32_t(x) << 8) | (uint32_t(in_grid && x > 0) << 16) |
-                           (uint32_t(in_grid && x < W - 1) << 17);
+    smem[kYOff + c] = uint32_t(y);
+    smem[kXOff + c] = uint32_t(x);
     smem[kIgnitionOff + c] = in_grid ? uint32_t(io.cell_ignition[c]) : 0u;
     smem[kRewardOff + c] = in_grid ? __float_as_uint(io.cell_reward[c]) : 0u;
   }
@@ -176,8 +182,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   const float agent_yf = is_agent ? float(p.agent_y[sub]) : 0.f;
   const float agent_xf = is_agent ? float(p.agent_x[sub]) : 0.f;
   const int burned_state = p.num_fire_states - 1, almost_state = p.num_fire_states - 2;
-  const float p_grow = (flags & FRZ_WF_STOCH_FIRE_INCREASE) ? fminf(fmaxf(p.p_increase, 0.f), 1.f) : 1.f;
-  const float p_almost = fminf(fmaxf((flags & FRZ_WF_SPECIAL_BURNOUT) ? p.p_burnout : p.p_increase, 0.f), 1.f);
+  const int mask_agent = sub % A, mask_slot = sub / A, mask_slots = G / A;  // action-mask builder: lane -> (slot, agent)
 
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
 
@@ -296,8 +301,6 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         }
 
         // ---------------------------------------------------------------- randomness
-        const uint32_t env_lo = uint32_t(p.env_offset + e), env_hi = uint32_t(uint64_t(p.env_offset + e) >> 32);
-        const uint32_t step_lo = uint32_t(step), step_hi = uint32_t(step >> 32) ^ env_hi;
         // Agent events: 0 suppressant decrease, 1 equipment, 2 refill, 3 capacity pick, 4 tank switch (wildfire.py:492-513).
         // "decrease" needs a fight action and "refill" a refill action, so in Philox mode events 0 and 2 share one draw.
         float ua[5], uf[3 * CPL];  // uf[3*i + event]: fire increase, fire decrease, fire spread of this lane's cell i
@@ -318,6 +321,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           }
         }
         if (!inject_field || !inject_agent) {
+          const uint32_t env_lo = uint32_t(p.env_offset + e), env_hi = uint32_t(uint64_t(p.env_offset + e) >> 32);
+          const uint32_t step_lo = uint32_t(step), step_hi = uint32_t(step >> 32) ^ env_hi;
           uint32_t bits[4 * kCalls];
 #pragma unroll
           for (int k = 0; k < kCalls; ++k) {
@@ -329,16 +334,27 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           }
           if (!inject_field) {
 #pragma unroll
-            for (int j = 0; j < 3 * CPL; ++j) uf[j] = u01(bits[j]);
+            for (int i = 0; i < CPL; ++i) {
+              uf[3 * i] = uf[3 * i + 1] = u01(bits[2 * i]);
+              uf[3 * i + 2] = u01(bits[2 * i + 1]);
+            }
           }
           if (!inject_agent) {
             uint32_t words[4];
-            if (kAgentFromSpare) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                words[j] = ((bits[(3 * j) % (4 * kCalls)] & 0xffu) << 24) | ((bits[(3 * j + 1) % (4 * kCalls)] & 0xffu) << 16) |
-                           ((bits[(3 * j + 2) % (4 * kCalls)] & 0xffu) << 8);
-            } else {
+            bool have_words = false;
+            if constexpr (G == 32 && CPL == 4) {
+              // lanes whose fourth cell lies outside the grid never use their last two words: agent a takes the pairs
+              // of lanes 31 - a and 31 - A - a (the host checked that those lanes exist for this grid)
+              if (derived.spare_lanes_feed_agents) {
+                const int first = (31 - sub) & 31, second = (31 - A - sub) & 31;
+                words[0] = __shfl_sync(kFullMask, bits[6], first);
+                words[1] = __shfl_sync(kFullMask, bits[7], first);
+                words[2] = __shfl_sync(kFullMask, bits[6], second);
+                words[3] = __shfl_sync(kFullMask, bits[7], second);
+                have_words = true;
+              }
+            }
+            if (!have_words) {
               const uint4 r = philox(env_lo, step_lo, 0x80000000u | uint32_t(sub), step_hi);
               words[0] = r.x;
               words[1] = r.y;
@@ -353,29 +369,30 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         }
 
         // ---------------------------------------------------------------- agent transitions
+        // (the host folded the StochasticConfiguration switches into the thresholds: 2 = always, -1 = never)
         // suppressant_decrease.py:34-63
-        const bool decrease = user && (!(flags & FRZ_WF_STOCH_SUPPRESSANT_DECREASE) || ua[0] < p.p_suppressant_decrease);
+        const bool decrease = user && ua[0] < p.p_suppressant_decrease;
         supp = fmaxf(decrease ? __fadd_rn(supp, -1.f) : supp, 0.f);
         // equipment.py:42-77 -- masks from the pre-update state, one uniform for all three tests
         {
           const bool pristine = equip == E - 1, damaged = equip == 0;
           const bool wearable = pristine || !damaged;  // pristine | intermediate
-          const bool repairs = damaged && (!(flags & FRZ_WF_STOCH_REPAIR) || ua[1] < p.p_repair);
-          const bool critical = (flags & FRZ_WF_CRITICAL_ERROR) && pristine && ua[1] < p.p_critical;
-          const bool degrades = wearable && (!(flags & FRZ_WF_STOCH_DEGRADE) || ua[1] < p.p_degrade) && !critical;
+          const bool repairs = damaged && ua[1] < p.p_repair;
+          const bool critical = pristine && ua[1] < p.p_critical;
+          const bool degrades = wearable && ua[1] < p.p_degrade && !critical;
           if (repairs) equip = E - 1;
           if (critical) equip = 0;
           if (degrades) equip -= 1;
         }
         // suppressant_refill.py:43-74 -- bonus of the equipment state AFTER its transition
-        const bool increased = refill && (!(flags & FRZ_WF_STOCH_REFILL) || ua[2] < p.p_refill);
+        const bool increased = refill && ua[2] < p.p_refill;
         if (increased) supp = __fadd_rn(cap, p.equipment_capacity_bonus[max(equip, 0)]);
         // capacity.py:39-66 -- bucketize(right=False): first i with r <= cum[i]
         if (__any_sync(kFullMask, increased)) {
           int pick = p.num_capacities - 1;
           for (int i = p.num_capacities - 1; i >= 0; --i)
             if (ua[3] <= p.capacity_cum[i]) pick = i;
-          const bool switches = increased && (!(flags & FRZ_WF_STOCH_TANK_SWITCH) || ua[4] < p.p_tank_switch);
+          const bool switches = increased && ua[4] < p.p_tank_switch;
           const float extra = __fadd_rn(supp, -cap);
           if (switches) {
             cap = p.capacity_value[pick];
@@ -384,6 +401,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         }
 
         // ---------------------------------------------------------------- fire increase + decrease per cell
+        // p.p_increase / p.p_burnout arrive clamped (and 1 when the increase is deterministic); a deterministic
+        // decrease arrives as p_decrease = 2, bonus = 0, which the clamp turns into probability 1
         uint32_t burned_bits = 0, putout_bits = 0;  // bit i = this lane's cell i
         uint32_t burnw[NW];
 #pragma unroll
@@ -394,19 +413,15 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           const bool burning = f > 0 && it > 0;
           const float diff = __fadd_rn(f > 0 ? float(f) : 0.f, -attack);
           const bool unmet = burning && diff > 0.f;
-          const float prob_up = unmet ? (it == almost_state ? p_almost : p_grow) : 0.f;
-          const bool grow = uf[3 * i] < prob_up;
+          const bool grow = unmet && uf[3 * i] < (it == almost_state ? p.p_burnout : p.p_increase);
           it += grow ? 1 : 0;
           const bool burned = grow && it >= burned_state;
           // fire_decrease.py:36-80 sees the post-increase state: a cell that just burned out is no longer lit, any other
           // burning cell kept its sign and a positive intensity, so `diff` is unchanged; the product and the sum are
           // rounded separately like the reference's two aten ops
           const bool met = burning && !burned && diff <= 0.f;
-          float prob_down = 0.f;
-          if (met)
-            prob_down = (flags & FRZ_WF_STOCH_FIRE_DECREASE)
-                            ? fminf(fmaxf(__fadd_rn(p.p_decrease, __fmul_rn(-diff, p.decrease_bonus)), 0.f), 1.f) : 1.f;
-          const bool shrink = uf[3 * i + 1] < prob_down;
+          const float prob_down = fminf(fmaxf(__fadd_rn(p.p_decrease, __fmul_rn(-diff, p.decrease_bonus)), 0.f), 1.f);
+          const bool shrink = met && uf[3 * i + 1] < prob_down;
           it -= shrink ? 1 : 0;
           const bool put = shrink && it <= 0;
           if (burned) fuel[i] = max(fuel[i] - 1, 0);  // burn-out clamps the fuel (fire_increase.py:90) ...
@@ -423,12 +438,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         if (user) sts(s_attack + 4u * uint32_t(target), 0u);
 
         // ---------------------------------------------------------------- fire spread (fire_spreads.py:33-59)
-        float my_put_reward = 0.f, my_burn_reward = 0.f;
-        int my_fuel = 0;
-        uint32_t putw[NW];
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
-          const int c = i * G + sub;
           int f = fires[i], it = inten[i];
           const bool unlit = f < 0 && it == 0 && (!use_fuel || fuel[i] > 0);
           if (__any_sync(kFullMask, unlit)) {
@@ -452,47 +463,66 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
                 if (r && w == i + q + 1) south |= burnw[w] << (32 - r);
               }
             }
-            const uint32_t west = __funnelshift_l(prev, cur, 1), east = __funnelshift_r(cur, next, 1);
-            const uint32_t st = lds_const(s_cell + 4u * (kStaticOff + i * G));
-            // the conv sum in the reference's accumulation order N, W, E, S (spread_lut is indexed by that pattern)
-            const uint32_t pattern = uint32_t((north & lane_bit) != 0u) | (uint32_t((west & lane_bit) != 0u && (st & 0x10000u)) << 1) |
-                                     (uint32_t((east & lane_bit) != 0u && (st & 0x20000u)) << 2) |
-                                     (uint32_t((south & lane_bit) != 0u) << 3);
-            const float prob = unlit ? __fadd_rn(p.spread_lut[pattern], p.p_random_ignition) : 0.f;
-            if (uf[3 * i + 2] < prob) {
+            const uint32_t west = __funnelshift_l(prev, cur, 1) & derived.west_ok[(G == 32) ? i : 0];
+            const uint32_t east = __funnelshift_r(cur, next, 1) & derived.east_ok[(G == 32) ? i : 0];
+            // the conv sum in the reference's accumulation order N, W, E, S, starting from zero (spread_lut[1 << k] is
+            // the weight of direction k; see spread_lut() on the host for the order)
+            float prob = 0.f;
+            if (north & lane_bit) prob = p.spread_lut[1];
+            if (west & lane_bit) prob = __fadd_rn(prob, p.spread_lut[2]);
+            if (east & lane_bit) prob = __fadd_rn(prob, p.spread_lut[4]);
+            if (south & lane_bit) prob = __fadd_rn(prob, p.spread_lut[8]);
+            prob = __fadd_rn(prob, p.p_random_ignition);
+            if (unlit && uf[3 * i + 2] < prob) {
               f = -f;
               it = int(lds_const(s_cell + 4u * (kIgnitionOff + i * G)));
             }
           }
           fires[i] = f;
           inten[i] = it;
-          const bool put = (putout_bits >> i) & 1u, burned = (burned_bits >> i) & 1u;
-          if (put || burned) {
-            const float cell_reward = __uint_as_float(lds_const(s_cell + 4u * (kRewardOff + i * G)));
-            if (put) my_put_reward += cell_reward;
-            if (burned) my_burn_reward += cell_reward;
-          }
-          my_fuel += fuel[i];
           litw[(G == 32) ? i : 0] = group_ballot<G>(f > 0, group_base, group_mask);
-          putw[(G == 32) ? i : 0] = group_ballot<G>(put, group_base, group_mask);
-          n_putout += __popc(putw[(G == 32) ? i : 0]);
-          n_burned += __popc(group_ballot<G>(burned, group_base, group_mask));
         }
 
         // ---------------------------------------------------------------- rewards + termination (wildfire.py:534-582)
-        // (the reductions are skipped when no group of the warp needs them; the test must be warp-uniform)
+        // burn-outs and put-outs are rare: count them with one reduction each and only then look at which cells
+        if constexpr (G == 32) {
+          n_burned = __reduce_add_sync(kFullMask, __popc(burned_bits));
+          n_putout = __reduce_add_sync(kFullMask, __popc(putout_bits));
+        } else {
+          n_burned = group_sum<G>(__popc(burned_bits));
+          n_putout = group_sum<G>(__popc(putout_bits));
+        }
         float put_total = 0.f, burn_total = 0.f;
-        if (__any_sync(kFullMask, n_putout > 0) && !(flags & FRZ_WF_LOCALIZE_PUTOUTS))
-          put_total = group_sum<G>(my_put_reward);
-        if (__any_sync(kFullMask, n_burned > 0) && (flags & FRZ_WF_BURNOUT_SCALED))
-          burn_total = group_sum<G>(my_burn_reward);
+        uint32_t putw[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) putw[w] = 0u;
+        if (__any_sync(kFullMask, (n_putout | n_burned) != 0)) {  // warp-uniform test
+          float my_put_reward = 0.f, my_burn_reward = 0.f;
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) {
+            const bool put = (putout_bits >> i) & 1u, burned = (burned_bits >> i) & 1u;
+            if (put || burned) {
+              const float cell_reward = __uint_as_float(lds_const(s_cell + 4u * (kRewardOff + i * G)));
+              if (put) my_put_reward += cell_reward;
+              if (burned) my_burn_reward += cell_reward;
+            }
+            if (flags & FRZ_WF_LOCALIZE_PUTOUTS) putw[(G == 32) ? i : 0] = group_ballot<G>(put, group_base, group_mask);
+          }
+          if (!(flags & FRZ_WF_LOCALIZE_PUTOUTS)) put_total = group_sum<G>(my_put_reward);
+          if (flags & FRZ_WF_BURNOUT_SCALED) burn_total = group_sum<G>(my_burn_reward);
+        }
         const float penalty_total =
             (flags & FRZ_WF_BURNOUT_SCALED) ? -burn_total : __fmul_rn(p.burnout_penalty, float(n_burned));
         uint32_t any_lit = 0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) any_lit |= litw[w];
         bool dead = any_lit == 0;
-        if (use_fuel && __any_sync(kFullMask, dead)) dead = dead && group_sum<G>(my_fuel) <= 0;
+        if (use_fuel && __any_sync(kFullMask, dead)) {
+          int my_fuel = 0;
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) my_fuel += fuel[i];
+          dead = dead && group_sum<G>(my_fuel) <= 0;
+        }
         if (dead) {  // wildfire.py:570
 #pragma unroll
           for (int i = 0; i < CPL; ++i) fires[i] = 0;
@@ -549,36 +579,36 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           const uint32_t word = litw[(G == 32) ? i : 0];
           if (word & lane_bit) {
             const int t = rank + __popc(word & lanes_below);  // env-local task index = rank in row-major lit order
-            const uint32_t st = lds_const(s_cell + 4u * (kStaticOff + i * G));
             sts(s_tasks + 4u * uint32_t(t), fighters[i]);
-            if (valid) task_row[t] = make_int4(int(st & 0xffu), int((st >> 8) & 0xffu), fires[i], inten[i]);
+            if (valid)
+              task_row[t] = make_int4(int(lds_const(s_cell + 4u * (kYOff + i * G))), int(lds_const(s_cell + 4u * (kXOff + i * G))),
+                                      fires[i], inten[i]);
           }
           rank += __popc(word);
         }
       }
       // tasks of the previous launch that no longer exist: their rows go back to padding, their mask bytes to zero
       const int quads = (n_rows + 3) >> 2;
-      for (int t = n_lit + sub; t < 4 * quads; t += G) {
-        sts(s_tasks + 4u * uint32_t(t), 0u);
-        if (valid && t < n_before) task_row[t] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
+      for (int first = n_lit; first < 4 * quads; first += G) {
+        const int t = first + sub;
+        if (t < 4 * quads) {
+          sts(s_tasks + 4u * uint32_t(t), 0u);
+          if (valid && t < n_before) task_row[t] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
+        }
       }
       __syncwarp();
 
       if (valid) {
-        // action mask [A, mask_stride] bytes indexed by env-local task.  Work item = (agent, 4 consecutive tasks): the
-        // four tasks' agent bitmasks are shifted to the agent's bit and packed into one 4-byte store.  Items are laid
-        // out [agent][quad] with the quad count rounded up to a power of two, 32 (or G) items per pass.
-        uint32_t* const mask_row = reinterpret_cast<uint32_t*>(io.action_mask) + size_t(env) * A * mask_words_row;
-        const int shift = 32 - __clz(max(quads, 1) - 1);  // log2 of the rounded-up quad count
-        const int items = A << shift;
-        // (for one environment per warp the trip count is warp-uniform; the predicate inside does the rest)
-        for (int first = 0; first < items; first += G) {
-          const int item = first + sub;
-          const int a = item >> shift, q = item & ((1 << shift) - 1);
-          if (a < A && q < quads) {
+        // action mask [A, mask_stride] bytes indexed by env-local task.  Lane (slot, agent) = (sub / A, sub % A) packs
+        // the agent's bit of four consecutive tasks into one 4-byte store; G / A such quads are done per pass.
+        uint32_t* const mask_out = reinterpret_cast<uint32_t*>(io.action_mask) + (size_t(env) * A + mask_agent) * mask_words_row;
+        for (int first = 0; first < quads; first += mask_slots) {
+          const int q = first + mask_slot;
+          if (mask_slot < mask_slots && q < quads) {
             const uint4 m = lds_v4(s_tasks + 16u * uint32_t(q));
-            const uint32_t lo = __byte_perm(m.x >> a, m.y >> a, 0x0040), hi = __byte_perm(m.z >> a, m.w >> a, 0x0040);
-            mask_row[a * mask_words_row + q] = __byte_perm(lo, hi, 0x5410) & 0x01010101u;
+            const uint32_t lo = __byte_perm(m.x >> mask_agent, m.y >> mask_agent, 0x0040);
+            const uint32_t hi = __byte_perm(m.z >> mask_agent, m.w >> mask_agent, 0x0040);
+            mask_out[q] = __byte_perm(lo, hi, 0x5410) & 0x01010101u;
           }
         }
 
@@ -692,8 +722,45 @@ bool pick_geometry(const FrzWildfireParams& p, Geometry* g) {
   return true;
 }
 
+// What the kernel receives instead of the caller's FrzWildfireParams: the StochasticConfiguration switches
+// (structures/configuration.py:271-322) are folded into the thresholds the uniforms are compared with -- every draw is
+// in [0, 1), so a threshold of 2 makes the event certain and -1 impossible, exactly what the reference's
+// "if not stochastic: skip the randomness test" branches do -- and the per-word neighbour masks are tabulated.
+void fold_configuration(const FrzWildfireParams& in, int group, int cells_per_lane, FrzWildfireParams* out, Derived* derived) {
+  *out = in;
+  const uint32_t flags = in.flags;
+  const auto clamp01 = [](float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); };
+  if (!(flags & FRZ_WF_STOCH_SUPPRESSANT_DECREASE)) out->p_suppressant_decrease = 2.f;  // suppressant_decrease.py:49-53
+  if (!(flags & FRZ_WF_STOCH_REFILL)) out->p_refill = 2.f;                                // suppressant_refill.py:58-62
+  if (!(flags & FRZ_WF_STOCH_TANK_SWITCH)) out->p_tank_switch = 2.f;                      // capacity.py:54-58
+  if (!(flags & FRZ_WF_CRITICAL_ERROR)) out->p_critical = -1.f;                           // equipment.py:60-63
+  if (!(flags & FRZ_WF_STOCH_DEGRADE)) out->p_degrade = 2.f;                              // equipment.py:65-69
+  if (!(flags & FRZ_WF_STOCH_REPAIR)) out->p_repair = 2.f;                                // equipment.py:54-58
+  // fire_increase.py:62-78: probability 1 when deterministic; "almost burned out" cells use the burnout probability
+  out->p_increase = (flags & FRZ_WF_STOCH_FIRE_INCREASE) ? clamp01(in.p_increase) : 1.f;
+  out->p_burnout = clamp01((flags & FRZ_WF_SPECIAL_BURNOUT) ? in.p_burnout : in.p_increase);
+  if (!(flags & FRZ_WF_STOCH_FIRE_DECREASE)) {  // fire_decrease.py:60-66: clamp(2 + x * 0) = 1
+    out->p_decrease = 2.f;
+    out->decrease_bonus = 0.f;
+  }
+  const int H = in.height, W = in.width, HW = H * W;
+  for (int w = 0; w < FRZ_MAX_CELLS / 32; ++w) derived->west_ok[w] = derived->east_ok[w] = 0u;
+  for (int c = 0; c < HW; ++c) {
+    const int x = c % W;
+    if (x > 0) derived->west_ok[c >> 5] |= 1u << (c & 31);
+    if (x < W - 1) derived->east_ok[c >> 5] |= 1u << (c & 31);
+  }
+  // Philox layout of the 4-cells-per-lane geometry: lanes whose fourth cell (96 + lane) is off-grid have two unused
+  // words each; two such lanes per agent replace a third Philox call
+  const int first_spare = HW - 96 > 0 ? HW - 96 : 0;
+  derived->spare_lanes_feed_agents = (group == 32 && cells_per_lane == 4 && 2 * in.num_agents <= 32 - first_spare) ? 1 : 0;
+}
+
 template <int G, int CPL, int MODE, bool INJECTED>
-int launch_variant(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B, cudaStream_t stream) {
+int launch_variant(const FrzWildfireParams& caller_params, const FrzWildfireBuffers& io, int B, cudaStream_t stream) {
+  FrzWildfireParams p;
+  Derived derived;
+  fold_configuration(caller_params, G, CPL, &p, &derived);
   static int ctas_per_sm = 0, sm_count = 0;
   static size_t cached_smem = ~size_t(0);
   const int groups_per_cta = (kThreads / 32) * (32 / G);
@@ -717,7 +784,7 @@ int launch_variant(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int
   const int work = (B + groups_per_cta - 1) / groups_per_cta;
   const int cap = sm_count * ctas_per_sm;
   const int grid = work < cap ? work : cap;
-  kernel<<<grid, kThreads, smem, stream>>>(p, io, B);
+  kernel<<<grid, kThreads, smem, stream>>>(p, io, derived, B);
   return check_launch("wildfire_step_kernel");
 }
 
