@@ -193,8 +193,9 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       const int env = env0 + lane / G;
       const bool valid = (G == 32) || env < B;  // sub-warp groups past the end stay for the warp-wide votes
       const int e = valid ? env : B - 1;
-      const size_t cell_row = size_t(e) * HW;
-      const size_t agent_row = size_t(e) * A;
+      // 32-bit element indices (the host rejects batches whose arrays exceed 2^32 elements): one IMAD.WIDE per access
+      const uint32_t cell_row = uint32_t(e) * uint32_t(HW);
+      const uint32_t agent_at = uint32_t(e) * uint32_t(A) + uint32_t(sub);
       int* const fires_row = io.fires + cell_row;
       int* const inten_row = io.intensity + cell_row;
       int* const fuel_row = io.fuel + cell_row;
@@ -212,9 +213,9 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       float supp = 0.f, cap = 0.f;
       int equip = 0;
       if (is_agent) {
-        supp = io.suppressants[agent_row + sub];
-        cap = io.capacity[agent_row + sub];
-        equip = min(max(io.equipment[agent_row + sub], 0), E - 1);
+        supp = io.suppressants[agent_at];
+        cap = io.capacity[agent_at];
+        equip = min(max(io.equipment[agent_at], 0), E - 1);
       }
 
       uint32_t litw[NW];
@@ -234,10 +235,10 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         // ---------------------------------------------------------------- action decode (wildfire.py:412-486)
         int act_k = 0, act_id = -1;
         if (is_agent) {
-          const int2 act = reinterpret_cast<const int2*>(io.actions)[agent_row + sub];
+          const int2 act = reinterpret_cast<const int2*>(io.actions)[agent_at];
           act_k = act.x;
           act_id = act.y;
-          cumulative = io.cumulative_rewards[agent_row + sub];
+          cumulative = io.cumulative_rewards[agent_at];
         }
         moves = io.num_moves[e];
         total_burnouts = io.num_burnouts[e];
@@ -571,7 +572,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
 #pragma unroll
         for (int i = 0; i < CPL; ++i) fighters[i] |= lds_const(s_cell + 4u * uint32_t(kCellAgentsOff + q * kCells + i * G)) & ready;
       }
-      int4* const task_row = reinterpret_cast<int4*>(io.task_obs) + cell_row;
+      int4* const task_rows = reinterpret_cast<int4*>(io.task_obs);
       {
         int rank = 0;
 #pragma unroll
@@ -581,7 +582,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             const int t = rank + __popc(word & lanes_below);  // env-local task index = rank in row-major lit order
             sts(s_tasks + 4u * uint32_t(t), fighters[i]);
             if (valid)
-              task_row[t] = make_int4(int(lds_const(s_cell + 4u * (kYOff + i * G))), int(lds_const(s_cell + 4u * (kXOff + i * G))),
+              task_rows[cell_row + uint32_t(t)] = make_int4(int(lds_const(s_cell + 4u * (kYOff + i * G))), int(lds_const(s_cell + 4u * (kXOff + i * G))),
                                       fires[i], inten[i]);
           }
           rank += __popc(word);
@@ -593,7 +594,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         const int t = first + sub;
         if (t < 4 * quads) {
           sts(s_tasks + 4u * uint32_t(t), 0u);
-          if (valid && t < n_before) task_row[t] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
+          if (valid && t < n_before) task_rows[cell_row + uint32_t(t)] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
         }
       }
       __syncwarp();
@@ -601,21 +602,22 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       if (valid) {
         // action mask [A, mask_stride] bytes indexed by env-local task.  Lane (slot, agent) = (sub / A, sub % A) packs
         // the agent's bit of four consecutive tasks into one 4-byte store; G / A such quads are done per pass.
-        uint32_t* const mask_out = reinterpret_cast<uint32_t*>(io.action_mask) + (size_t(env) * A + mask_agent) * mask_words_row;
+        const uint32_t mask_at = (uint32_t(env) * uint32_t(A) + uint32_t(mask_agent)) * uint32_t(mask_words_row);
+        uint32_t* const mask_words = reinterpret_cast<uint32_t*>(io.action_mask);
         for (int first = 0; first < quads; first += mask_slots) {
           const int q = first + mask_slot;
           if (mask_slot < mask_slots && q < quads) {
             const uint4 m = lds_v4(s_tasks + 16u * uint32_t(q));
             const uint32_t lo = __byte_perm(m.x >> mask_agent, m.y >> mask_agent, 0x0040);
             const uint32_t hi = __byte_perm(m.z >> mask_agent, m.w >> mask_agent, 0x0040);
-            mask_out[q] = __byte_perm(lo, hi, 0x5410) & 0x01010101u;
+            mask_words[mask_at + uint32_t(q)] = __byte_perm(lo, hi, 0x5410) & 0x01010101u;
           }
         }
 
         if (is_agent) {
-          io.agent_task_count[agent_row + sub] = n_avail;
+          io.agent_task_count[agent_at] = n_avail;
           if (n_avail > 0) agent_bits |= lane_bit;
-          reinterpret_cast<float4*>(io.self_obs)[agent_row + sub] = make_float4(agent_yf, agent_xf, base_power, supp);
+          reinterpret_cast<float4*>(io.self_obs)[agent_at] = make_float4(agent_yf, agent_xf, base_power, supp);
         }
         if (sub == 0) io.env_task_count[env] = n_lit;
 
@@ -630,11 +632,11 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             }
           }
           if (is_agent) {
-            io.suppressants[agent_row + sub] = supp;
-            io.capacity[agent_row + sub] = cap;
-            io.equipment[agent_row + sub] = equip;
-            io.rewards[agent_row + sub] = reward;
-            io.cumulative_rewards[agent_row + sub] = cumulative;
+            io.suppressants[agent_at] = supp;
+            io.capacity[agent_at] = cap;
+            io.equipment[agent_at] = equip;
+            io.rewards[agent_at] = reward;
+            io.cumulative_rewards[agent_at] = cumulative;
           }
           if (sub == 0) {
             io.terminated[env] = terminated;
@@ -808,6 +810,14 @@ int dispatch(const FrzWildfireParams* p, const FrzWildfireBuffers* io, int B, in
     set_error("frz_wildfire: unsupported shape B=%d H=%d W=%d A=%d E=%d", B, p->height, p->width, p->num_agents,
               p->num_equipment_states);
     return FRZ_ERR_SHAPE;
+  }
+  {  // the kernels index every array with 32-bit element indices
+    const uint64_t cells = uint64_t(B) * uint64_t(p->height * p->width);
+    const uint64_t mask_words = uint64_t(B) * uint64_t(p->num_agents) * uint64_t(io->mask_stride / 4);
+    if (cells >= (1ull << 32) || mask_words >= (1ull << 32)) {
+      set_error("frz_wildfire: B=%d is too large for one launch (arrays exceed 2^32 elements); shard the batch", B);
+      return FRZ_ERR_SHAPE;
+    }
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (g.group == 8) return launch_step<8, 1>(*p, *io, B, mode, s);
