@@ -98,6 +98,42 @@ __device__ __forceinline__ void sts(uint32_t address, uint32_t value) {
   asm volatile("st.shared.u32 [%0], %1;" : : "r"(address), "r"(value) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------- bulk async copies
+
+// 1-D bulk copies of the async proxy (the TMA unit; SASS UBLKCP): one elected thread moves a whole tile between global
+// and shared memory, completion of loads is signalled on an mbarrier, stores are tracked as bulk groups.  Addresses and
+// sizes must be multiples of 16 bytes.
+__device__ __forceinline__ void mbarrier_init(uint32_t barrier, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" : : "r"(barrier), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" : : : "memory");
+}
+__device__ __forceinline__ void mbarrier_expect_bytes(uint32_t barrier, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" : : "r"(barrier), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarrier_wait(uint32_t barrier, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred done;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n"
+      "@!done bra WAIT_LOOP;\n"
+      "}\n"
+      : : "r"(barrier), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t shared_dst, const void* global_src, uint32_t bytes, uint32_t barrier) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               : : "r"(shared_dst), "l"(global_src), "r"(bytes), "r"(barrier) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* global_dst, uint32_t shared_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               : : "l"(global_dst), "r"(shared_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" : : : "memory"); }
+// wait until the committed bulk stores have finished READING shared memory (it may then be reused / the CTA may exit)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" : : : "memory"); }
+// make generic-proxy writes to shared memory visible to the async proxy before a bulk store reads them
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" : : : "memory"); }
+
 // ---------------------------------------------------------------------------------------------- launch epilogue
 
 // Called by every CTA once, after its last environment.

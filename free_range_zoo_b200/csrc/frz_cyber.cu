@@ -21,165 +21,374 @@ namespace {
 constexpr int kCyThreads = 128;
 enum CyMode { kCyStep = 0, kCyRefresh = 1 };
 
+// The rows of one environment in every array the step touches.  They point into global memory (direct kernel) or into
+// the CTA's staged tile in shared memory (tiled kernel); the step itself is the same code.
+struct CyberRows {
+  int32_t* state;           // [N]
+  int32_t* location;        // [D]
+  uint8_t* presence;        // [n]
+  const int2* actions;      // [n]
+  float* rewards;           // [n]
+  float* cumulative;        // [n]
+  int32_t* num_moves;       // [1]
+  uint8_t* truncated;       // [1]
+  int32_t* env_task_count;  // [1]
+  int32_t* agent_task_count;// [n]
+  float2* attacker_self;    // [Att]
+  float* defender_self;     // [D * 3]
+  int2* task_obs;           // [N]
+  uint8_t* monitored;       // [D]
+  const float* network_uniforms;  // [N] or nullptr
+  const float* agent_uniforms;    // [n] or nullptr
+};
+
+// One environment, one thread.  Returns the launch-epilogue bits through alive_bits / faults.
+template <int MODE>
+__device__ __forceinline__ void cyber_env_step(const FrzCyberParams& p, const CyberRows& r, const float* score_lut,
+                                               const Philox& philox, const uint64_t step, const int64_t global_env,
+                                               unsigned& alive_bits, unsigned& faults) {
+  const int N = p.num_nodes, n_att = p.num_attackers, n_def = p.num_defenders, n_agents = n_att + n_def;
+  const bool show_bad = p.flags & FRZ_CY_SHOW_BAD_ACTIONS;
+  const bool stochastic = p.flags & FRZ_CY_STOCHASTIC_STATE;
+
+  uint32_t present = 0;  // bit a = agent a is present (attackers first)
+  for (int a = 0; a < n_agents; ++a) present |= uint32_t(r.presence[a] != 0) << a;
+
+  if (MODE == kCyStep) {
+    const uint32_t env_lo = uint32_t(global_env), env_hi = uint32_t(uint64_t(global_env) >> 32);
+
+    // ---------------------------------------------------------------- decode (cybersecurity.py:317-384)
+    // Only bit sets are kept; who acts on which node is re-read from the action rows below (they sit in shared memory
+    // on the step path).  The subnetwork transition only depends on the attacks / patches decided here -- patches use
+    // the defender's location BEFORE this step's move -- so it runs before movement / presence overwrite the rows.
+    uint32_t patching = 0, monitoring = 0;
+#pragma unroll 1
+    for (int a = 0; a < n_agents; ++a) {
+      const int2 act = r.actions[a];
+      if (!show_bad && !((present >> a) & 1u) && act.y != -1) faults |= FRZ_FAULT_ABSENT_ACTED;  // :345,362
+      if (act.y == 0 && (act.x < 0 || act.x >= N)) faults |= FRZ_FAULT_BAD_NODE;                 // :341,357
+      if (a >= n_att) {
+        if (act.y == -2 && r.location[a - n_att] != -1) patching |= 1u << a;  // :354
+        if (act.y == -3) monitoring |= 1u << a;
+      }
+    }
+
+    // ---------------------------------------------------------------- subnetwork.py:40-72 + rewards :395-409
+    float network_reward = 0.f;
+    uint4 bits = make_uint4(0u, 0u, 0u, 0u);  // one Philox call serves four consecutive nodes / agents
+#pragma unroll 1
+    for (int node = 0; node < N; ++node) {
+      uint32_t actors = 0;
+      float attacks = 0.f, patches = 0.f;
+      for (int a = 0; a < n_att; ++a) {
+        const int2 act = r.actions[a];
+        if (act.y == 0 && act.x == node) {  // attack node act.x
+          actors |= 1u << a;
+          attacks = __fadd_rn(attacks, p.power[a]);
+        }
+      }
+      for (int a = n_att; a < n_agents; ++a) {
+        if (((patching >> a) & 1u) && r.location[a - n_att] == node) {  // patch the node the defender stands on
+          actors |= 1u << a;
+          patches = __fadd_rn(patches, p.power[a]);
+        }
+      }
+      float score;
+      if (p.lut_bits > 0) score = score_lut[actors];
+      else score = tanhf(__fdiv_rn(__fadd_rn(patches, -attacks), p.temperature));
+      bool better = score > 0.f, worse = score < 0.f;
+      if (stochastic) {
+        float u;
+        if (r.network_uniforms != nullptr) {
+          u = r.network_uniforms[node];
+        } else {
+          if ((node & 3) == 0) bits = philox(env_lo, uint32_t(step), uint32_t(node >> 2), uint32_t(step >> 32) ^ env_hi);
+          const uint32_t word = (node & 3) == 0 ? bits.x : (node & 3) == 1 ? bits.y : (node & 3) == 2 ? bits.z : bits.w;
+          u = u01(word);
+        }
+        const bool within = fabsf(score) <= u;  // larger |score| => LESS likely, as in the reference
+        better = better && within;
+        worse = worse && within;
+      }
+      int s = r.state[node] - int(better) + int(worse);
+      s = min(max(s, 0), p.num_states - 1);
+      r.state[node] = s;
+      network_reward = __fadd_rn(network_reward, __fmul_rn(p.state_rewards[s], p.criticality[node]));
+      r.task_obs[node] = make_int2(s, int(p.criticality[node]));
+    }
+
+    // ---------------------------------------------------------------- movement.py:17-32 + presence.py:35-60
+    uint32_t now_present = 0;
+#pragma unroll 1
+    for (int a = 0; a < n_agents; ++a) {
+      float u;
+      if (r.agent_uniforms != nullptr) {
+        u = r.agent_uniforms[a];
+      } else {
+        if ((a & 3) == 0) bits = philox(env_lo, uint32_t(step), 0x80000000u | uint32_t(a >> 2), uint32_t(step >> 32) ^ env_hi);
+        const uint32_t word = (a & 3) == 0 ? bits.x : (a & 3) == 1 ? bits.y : (a & 3) == 2 ? bits.z : bits.w;
+        u = u01(word);
+      }
+      const bool was = (present >> a) & 1u;
+      const bool returning = !was && u < p.returns[a];
+      const bool leaving = was && u >= p.persist[a];
+      const bool is = (was || returning) && !leaving;
+      now_present |= uint32_t(is) << a;
+      r.presence[a] = is;
+      if (a >= n_att) {
+        const int d = a - n_att;
+        const int2 act = r.actions[a];
+        int loc = r.location[d];
+        if (act.y == 0) loc = act.x;  // move to node act.x (no adjacency check, movement.py:17-32)
+        if (returning) loc = -1;      // returning defenders start at the home node
+        r.location[d] = loc;
+      }
+    }
+
+    const int moves = r.num_moves[0] + 1;
+    const bool truncated = moves >= p.max_steps;
+    r.num_moves[0] = moves;
+    r.truncated[0] = truncated;
+    alive_bits |= 1u | (truncated ? 0u : 2u);  // cybersecurity never terminates (:299)
+#pragma unroll 1
+    for (int a = 0; a < n_agents; ++a) {
+      float reward = ((patching >> a) & 1u) ? p.patch_reward : 0.f;  // :376 (the bad-action branch :379-381 is dead)
+      reward = __fadd_rn(reward, a < n_att ? -network_reward : network_reward);
+      r.rewards[a] = reward;
+      r.cumulative[a] = __fadd_rn(r.cumulative[a], reward);
+      if (a >= n_att) r.monitored[a - n_att] = (monitoring >> a) & 1u;
+    }
+    present = now_present;
+  } else {
+    for (int node = 0; node < N; ++node) r.task_obs[node] = make_int2(r.state[node], int(p.criticality[node]));
+  }
+
+  // ------------------------------------------------------------------ update_actions / update_observations
+  r.env_task_count[0] = N;
+  for (int a = 0; a < n_agents; ++a) {
+    const bool is = (present >> a) & 1u;
+    r.agent_task_count[a] = is ? N : 0;
+    if (a < n_att) {
+      r.attacker_self[a] = make_float2(p.power[a], is ? 1.f : 0.f);
+    } else {
+      const int d = a - n_att;
+      float* out = r.defender_self + d * 3;
+      out[0] = p.power[a];
+      out[1] = is ? 1.f : 0.f;
+      out[2] = float(r.location[d]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- direct kernel
+// One thread per environment straight on global memory: refresh / reset, and steps whose tile would not fit in shared
+// memory.
+template <int MODE>
 __global__ void __launch_bounds__(kCyThreads)
-cyber_step_kernel(const __grid_constant__ FrzCyberParams p, const __grid_constant__ FrzCyberBuffers io, const int B,
-                  const int mode) {
+cyber_step_kernel(const __grid_constant__ FrzCyberParams p, const __grid_constant__ FrzCyberBuffers io, const int B) {
   const int N = p.num_nodes, n_att = p.num_attackers, n_def = p.num_defenders, n_agents = n_att + n_def;
   FrzControl* control = io.control;
   const uint64_t step = control->step;
   const uint32_t alive_prev = control->alive;
   const Philox philox(control->seed);
-  const bool skip = (mode == kCyStep) && ((alive_prev & 3u) != 3u);  // utils/env.py:212
-  const bool show_bad = p.flags & FRZ_CY_SHOW_BAD_ACTIONS;
-  const bool stochastic = p.flags & FRZ_CY_STOCHASTIC_STATE;
+  const bool skip = (MODE == kCyStep) && ((alive_prev & 3u) != 3u);  // utils/env.py:212
   unsigned alive_bits = 0, faults = 0;
 
   if (!skip) {
     for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < B; env += gridDim.x * blockDim.x) {
-      int32_t* state = io.network_state + size_t(env) * N;
-      int32_t* location = io.location + size_t(env) * n_def;
-      uint8_t* presence = io.presence + size_t(env) * n_agents;
-      const size_t agent_row = size_t(env) * n_agents;
-
-      uint32_t present = 0;  // bit a = agent a is present (attackers first)
-      for (int a = 0; a < n_agents; ++a) present |= uint32_t(presence[a] != 0) << a;
-
-      if (mode == kCyStep) {
-        const int2* actions = reinterpret_cast<const int2*>(io.actions) + agent_row;
-        const uint32_t env_lo = uint32_t(p.env_offset + env), env_hi = uint32_t(uint64_t(p.env_offset + env) >> 32);
-
-        // ---------------------------------------------------------------- decode (cybersecurity.py:317-384)
-        // acting[a] = node the agent attacks / patches this step, or -1
-        uint32_t patching = 0, monitoring = 0, moving = 0;
-        int8_t acting[FRZ_MAX_AGENTS];
-        int32_t move_to[FRZ_MAX_AGENTS];
-#pragma unroll 1
-        for (int a = 0; a < n_agents; ++a) {
-          const int2 act = actions[a];
-          acting[a] = -1;
-          move_to[a] = 0;
-          if (!show_bad && !((present >> a) & 1u) && act.y != -1) faults |= FRZ_FAULT_ABSENT_ACTED;  // :345,362
-          if (a < n_att) {
-            if (act.y == 0) {  // attack node act.x
-              if (act.x < 0 || act.x >= N) faults |= FRZ_FAULT_BAD_NODE;  // :341
-              else acting[a] = int8_t(act.x);
-            }
-          } else {
-            const int d = a - n_att;
-            const int loc = location[d];
-            if (act.y == 0) {  // move to node act.x
-              if (act.x < 0 || act.x >= N) faults |= FRZ_FAULT_BAD_NODE;  // :357
-              moving |= 1u << a;
-              move_to[a] = act.x;
-            } else if (act.y == -2 && loc != -1) {  // patch the node the defender stands on (pre-move) :354
-              patching |= 1u << a;
-              if (loc >= 0 && loc < N) acting[a] = int8_t(loc);
-            }
-            if (act.y == -3) monitoring |= 1u << a;
-          }
-        }
-
-        // ---------------------------------------------------------------- movement.py:17-32 + presence.py:35-60
-        uint32_t now_present = 0;
-#pragma unroll 1
-        for (int a = 0; a < n_agents; ++a) {
-          float r;
-          if (io.agent_uniforms != nullptr) {
-            r = io.agent_uniforms[agent_row + a];
-          } else {
-            const uint4 bits = philox(env_lo, uint32_t(step), 0x80000000u | uint32_t(a >> 2), uint32_t(step >> 32) ^ env_hi);
-            const uint32_t word = (a & 3) == 0 ? bits.x : (a & 3) == 1 ? bits.y : (a & 3) == 2 ? bits.z : bits.w;
-            r = u01(word);
-          }
-          const bool was = (present >> a) & 1u;
-          const bool returning = !was && r < p.returns[a];
-          const bool leaving = was && r >= p.persist[a];
-          const bool is = (was || returning) && !leaving;
-          now_present |= uint32_t(is) << a;
-          presence[a] = is;
-          if (a >= n_att) {
-            const int d = a - n_att;
-            int loc = location[d];
-            if ((moving >> a) & 1u) loc = move_to[a];
-            if (returning) loc = -1;  // returning defenders start at the home node
-            location[d] = loc;
-          }
-        }
-
-        // ---------------------------------------------------------------- subnetwork.py:40-72 + rewards :395-409
-        float network_reward = 0.f;
-#pragma unroll 1
-        for (int node = 0; node < N; ++node) {
-          uint32_t actors = 0;
-          float attacks = 0.f, patches = 0.f;
-          for (int a = 0; a < n_agents; ++a) {
-            if (acting[a] == node) {
-              actors |= 1u << a;
-              if (a < n_att) attacks = __fadd_rn(attacks, p.power[a]); else patches = __fadd_rn(patches, p.power[a]);
-            }
-          }
-          float score;
-          if (p.lut_bits > 0) score = io.score_lut[actors];
-          else score = tanhf(__fdiv_rn(__fadd_rn(patches, -attacks), p.temperature));
-          bool better = score > 0.f, worse = score < 0.f;
-          if (stochastic) {
-            float r;
-            if (io.network_uniforms != nullptr) {
-              r = io.network_uniforms[size_t(env) * N + node];
-            } else {
-              const uint4 bits = philox(env_lo, uint32_t(step), uint32_t(node >> 2), uint32_t(step >> 32) ^ env_hi);
-              const uint32_t word = (node & 3) == 0 ? bits.x : (node & 3) == 1 ? bits.y : (node & 3) == 2 ? bits.z : bits.w;
-              r = u01(word);
-            }
-            const bool within = fabsf(score) <= r;  // larger |score| => LESS likely, as in the reference
-            better = better && within;
-            worse = worse && within;
-          }
-          int s = state[node] - int(better) + int(worse);
-          s = min(max(s, 0), p.num_states - 1);
-          state[node] = s;
-          network_reward = __fadd_rn(network_reward, __fmul_rn(p.state_rewards[s], p.criticality[node]));
-          reinterpret_cast<int2*>(io.task_obs)[size_t(env) * N + node] = make_int2(s, int(p.criticality[node]));
-        }
-
-        const int moves = io.num_moves[env] + 1;
-        const bool truncated = moves >= p.max_steps;
-        io.num_moves[env] = moves;
-        io.truncated[env] = truncated;
-        alive_bits |= 1u | (truncated ? 0u : 2u);  // cybersecurity never terminates (:299)
-#pragma unroll 1
-        for (int a = 0; a < n_agents; ++a) {
-          float reward = ((patching >> a) & 1u) ? p.patch_reward : 0.f;  // :376 (the bad-action branch :379-381 is dead)
-          reward = __fadd_rn(reward, a < n_att ? -network_reward : network_reward);
-          io.rewards[agent_row + a] = reward;
-          io.cumulative_rewards[agent_row + a] = __fadd_rn(io.cumulative_rewards[agent_row + a], reward);
-          if (a >= n_att) io.monitored[size_t(env) * n_def + (a - n_att)] = (monitoring >> a) & 1u;
-        }
-        present = now_present;
-      } else {
-        for (int node = 0; node < N; ++node)
-          reinterpret_cast<int2*>(io.task_obs)[size_t(env) * N + node] = make_int2(state[node], int(p.criticality[node]));
-      }
-
-      // ------------------------------------------------------------------ update_actions / update_observations
-      io.env_task_count[env] = N;
-      for (int a = 0; a < n_agents; ++a) {
-        const bool is = (present >> a) & 1u;
-        io.agent_task_count[agent_row + a] = is ? N : 0;
-        if (a < n_att) {
-          reinterpret_cast<float2*>(io.attacker_self)[size_t(env) * n_att + a] = make_float2(p.power[a], is ? 1.f : 0.f);
-        } else {
-          const int d = a - n_att;
-          float* out = io.defender_self + (size_t(env) * n_def + d) * 3;
-          out[0] = p.power[a];
-          out[1] = is ? 1.f : 0.f;
-          out[2] = float(location[d]);
-        }
-      }
+      const size_t e = size_t(env);
+      CyberRows r;
+      r.state = io.network_state + e * N;
+      r.location = io.location + e * n_def;
+      r.presence = io.presence + e * n_agents;
+      r.actions = reinterpret_cast<const int2*>(io.actions) + e * n_agents;
+      r.rewards = io.rewards + e * n_agents;
+      r.cumulative = io.cumulative_rewards + e * n_agents;
+      r.num_moves = io.num_moves + e;
+      r.truncated = io.truncated + e;
+      r.env_task_count = io.env_task_count + e;
+      r.agent_task_count = io.agent_task_count + e * n_agents;
+      r.attacker_self = reinterpret_cast<float2*>(io.attacker_self) + e * n_att;
+      r.defender_self = io.defender_self + e * n_def * 3;
+      r.task_obs = reinterpret_cast<int2*>(io.task_obs) + e * N;
+      r.monitored = io.monitored + e * n_def;
+      r.network_uniforms = io.network_uniforms != nullptr ? io.network_uniforms + e * N : nullptr;
+      r.agent_uniforms = io.agent_uniforms != nullptr ? io.agent_uniforms + e * n_agents : nullptr;
+      cyber_env_step<MODE>(p, r, io.score_lut, philox, step, p.env_offset + env, alive_bits, faults);
     }
   }
   finish_launch(control, alive_bits, faults, 0u,
-                skip ? kPublishNothing : (mode == kCyStep ? kPublishStep : kPublishRefresh));
+                skip ? kPublishNothing : (MODE == kCyStep ? kPublishStep : kPublishRefresh));
+}
+
+// ---------------------------------------------------------------------------------------------- tiled kernel
+// The step path.  A CTA owns a tile of kCyThreads consecutive environments.  Every [B, *] array is environment-major,
+// so the tile of each array is ONE contiguous byte range: a single elected thread streams all of them into shared
+// memory with bulk async copies (the TMA unit, completion on an mbarrier), every thread then steps its environment
+// entirely in shared memory, and the elected thread streams the results back with bulk stores.  HBM sees only full,
+// aligned bursts; the per-thread row accesses (stride = row size) never leave the SM.
+struct CyberTileLayout {  // byte offsets of the staged arrays inside the tile (each a multiple of 16)
+  int state, location, presence, cumulative, num_moves;                     // read and written
+  int actions, network_uniforms, agent_uniforms;                            // read only
+  int rewards, truncated, env_task_count, agent_task_count, attacker_self,  // written only
+      defender_self, task_obs, monitored;
+  int total;
+};
+
+__host__ __device__ inline CyberTileLayout cyber_tile_layout(int N, int n_att, int n_def, bool injected) {
+  const int n = n_att + n_def, T = kCyThreads;
+  CyberTileLayout L;
+  int at = 0;
+  auto take = [&at](int bytes) {
+    const int offset = at;
+    at += (bytes + 15) & ~15;
+    return offset;
+  };
+  L.state = take(T * N * 4);
+  L.location = take(T * n_def * 4);
+  L.presence = take(T * n);
+  L.cumulative = take(T * n * 4);
+  L.num_moves = take(T * 4);
+  L.actions = take(T * n * 8);
+  L.network_uniforms = take(injected ? T * N * 4 : 0);
+  L.agent_uniforms = take(injected ? T * n * 4 : 0);
+  L.rewards = take(T * n * 4);
+  L.truncated = take(T);
+  L.env_task_count = take(T * 4);
+  L.agent_task_count = take(T * n * 4);
+  L.attacker_self = take(T * n_att * 8);
+  L.defender_self = take(T * n_def * 12);
+  L.task_obs = take(T * N * 8);
+  L.monitored = take(T * n_def);
+  L.total = at;
+  return L;
+}
+
+// cooperative copy for the (at most one) partial tile at the end of the batch: sizes need not be multiples of 16
+__device__ __forceinline__ void tile_copy(uint8_t* dst, const uint8_t* src, int bytes) {
+  for (int i = threadIdx.x; i < bytes; i += kCyThreads) dst[i] = src[i];
+}
+
+template <bool INJECTED>
+__global__ void __launch_bounds__(kCyThreads)
+cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_constant__ FrzCyberBuffers io, const int B) {
+  extern __shared__ __align__(128) uint8_t tile[];
+  __shared__ __align__(8) uint64_t barrier_storage;
+  const int N = p.num_nodes, n_att = p.num_attackers, n_def = p.num_defenders, n = n_att + n_def;
+  FrzControl* control = io.control;
+  const uint64_t step = control->step;
+  const uint32_t alive_prev = control->alive;
+  const Philox philox(control->seed);
+  const bool skip = (alive_prev & 3u) != 3u;  // utils/env.py:212
+  unsigned alive_bits = 0, faults = 0;
+
+  if (!skip) {
+    const CyberTileLayout L = cyber_tile_layout(N, n_att, n_def, INJECTED);
+    const int first = blockIdx.x * kCyThreads;
+    const int count = min(kCyThreads, B - first);
+    const size_t e = size_t(first);
+    const bool inject_network = INJECTED && io.network_uniforms != nullptr;
+    const bool inject_agent = INJECTED && io.agent_uniforms != nullptr;
+    const bool full = count == kCyThreads;
+    const uint32_t tile_s = shared_address(tile), barrier = shared_address(&barrier_storage);
+
+    // ------------------------------------------------------------------ stage in
+    if (full) {
+      if (threadIdx.x == 0) mbarrier_init(barrier, 1);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const uint32_t T = kCyThreads;
+        uint32_t bytes = T * (N * 4 + n_def * 4 + n + n * 4 + 4 + n * 8);
+        if (inject_network) bytes += T * N * 4;
+        if (inject_agent) bytes += T * n * 4;
+        mbarrier_expect_bytes(barrier, bytes);
+        bulk_load(tile_s + L.state, io.network_state + e * N, T * N * 4, barrier);
+        bulk_load(tile_s + L.location, io.location + e * n_def, T * n_def * 4, barrier);
+        bulk_load(tile_s + L.presence, io.presence + e * n, T * n, barrier);
+        bulk_load(tile_s + L.cumulative, io.cumulative_rewards + e * n, T * n * 4, barrier);
+        bulk_load(tile_s + L.num_moves, io.num_moves + e, T * 4, barrier);
+        bulk_load(tile_s + L.actions, io.actions + e * n * 2, T * n * 8, barrier);
+        if (inject_network) bulk_load(tile_s + L.network_uniforms, io.network_uniforms + e * N, T * N * 4, barrier);
+        if (inject_agent) bulk_load(tile_s + L.agent_uniforms, io.agent_uniforms + e * n, T * n * 4, barrier);
+      }
+      mbarrier_wait(barrier, 0);
+    } else {
+      tile_copy(tile + L.state, reinterpret_cast<const uint8_t*>(io.network_state + e * N), count * N * 4);
+      tile_copy(tile + L.location, reinterpret_cast<const uint8_t*>(io.location + e * n_def), count * n_def * 4);
+      tile_copy(tile + L.presence, io.presence + e * n, count * n);
+      tile_copy(tile + L.cumulative, reinterpret_cast<const uint8_t*>(io.cumulative_rewards + e * n), count * n * 4);
+      tile_copy(tile + L.num_moves, reinterpret_cast<const uint8_t*>(io.num_moves + e), count * 4);
+      tile_copy(tile + L.actions, reinterpret_cast<const uint8_t*>(io.actions + e * n * 2), count * n * 8);
+      if (inject_network)
+        tile_copy(tile + L.network_uniforms, reinterpret_cast<const uint8_t*>(io.network_uniforms + e * N), count * N * 4);
+      if (inject_agent)
+        tile_copy(tile + L.agent_uniforms, reinterpret_cast<const uint8_t*>(io.agent_uniforms + e * n), count * n * 4);
+      __syncthreads();
+    }
+
+    // ------------------------------------------------------------------ step, entirely in shared memory
+    const int t = threadIdx.x;
+    if (t < count) {
+      CyberRows r;
+      r.state = reinterpret_cast<int32_t*>(tile + L.state) + t * N;
+      r.location = reinterpret_cast<int32_t*>(tile + L.location) + t * n_def;
+      r.presence = tile + L.presence + t * n;
+      r.actions = reinterpret_cast<const int2*>(tile + L.actions) + t * n;
+      r.rewards = reinterpret_cast<float*>(tile + L.rewards) + t * n;
+      r.cumulative = reinterpret_cast<float*>(tile + L.cumulative) + t * n;
+      r.num_moves = reinterpret_cast<int32_t*>(tile + L.num_moves) + t;
+      r.truncated = tile + L.truncated + t;
+      r.env_task_count = reinterpret_cast<int32_t*>(tile + L.env_task_count) + t;
+      r.agent_task_count = reinterpret_cast<int32_t*>(tile + L.agent_task_count) + t * n;
+      r.attacker_self = reinterpret_cast<float2*>(tile + L.attacker_self) + t * n_att;
+      r.defender_self = reinterpret_cast<float*>(tile + L.defender_self) + t * n_def * 3;
+      r.task_obs = reinterpret_cast<int2*>(tile + L.task_obs) + t * N;
+      r.monitored = tile + L.monitored + t * n_def;
+      r.network_uniforms = inject_network ? reinterpret_cast<const float*>(tile + L.network_uniforms) + t * N : nullptr;
+      r.agent_uniforms = inject_agent ? reinterpret_cast<const float*>(tile + L.agent_uniforms) + t * n : nullptr;
+      cyber_env_step<kCyStep>(p, r, io.score_lut, philox, step, p.env_offset + first + t, alive_bits, faults);
+    }
+
+    // ------------------------------------------------------------------ stage out
+    if (full) {
+      fence_async_shared();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const uint32_t T = kCyThreads;
+        bulk_store(io.network_state + e * N, tile_s + L.state, T * N * 4);
+        bulk_store(io.location + e * n_def, tile_s + L.location, T * n_def * 4);
+        bulk_store(io.presence + e * n, tile_s + L.presence, T * n);
+        bulk_store(io.cumulative_rewards + e * n, tile_s + L.cumulative, T * n * 4);
+        bulk_store(io.num_moves + e, tile_s + L.num_moves, T * 4);
+        bulk_store(io.rewards + e * n, tile_s + L.rewards, T * n * 4);
+        bulk_store(io.truncated + e, tile_s + L.truncated, T);
+        bulk_store(io.env_task_count + e, tile_s + L.env_task_count, T * 4);
+        bulk_store(io.agent_task_count + e * n, tile_s + L.agent_task_count, T * n * 4);
+        bulk_store(io.attacker_self + e * n_att * 2, tile_s + L.attacker_self, T * n_att * 8);
+        bulk_store(io.defender_self + e * n_def * 3, tile_s + L.defender_self, T * n_def * 12);
+        bulk_store(io.task_obs + e * N * 2, tile_s + L.task_obs, T * N * 8);
+        bulk_store(io.monitored + e * n_def, tile_s + L.monitored, T * n_def);
+        bulk_commit();
+        bulk_wait_read();
+      }
+    } else {
+      __syncthreads();
+      tile_copy(reinterpret_cast<uint8_t*>(io.network_state + e * N), tile + L.state, count * N * 4);
+      tile_copy(reinterpret_cast<uint8_t*>(io.location + e * n_def), tile + L.location, count * n_def * 4);
+      tile_copy(io.presence + e * n, tile + L.presence, count * n);
+      tile_copy(reinterpret_cast<uint8_t*>(io.cumulative_rewards + e * n), tile + L.cumulative, count * n * 4);
+      tile_copy(reinterpret_cast<uint8_t*>(io.num_moves + e), tile + L.num_moves, count * 4);
+      tile_copy(reinterpret_cast<uint8_t*>(io.rewards + e * n), tile + L.rewards, count * n * 4);
+      tile_copy(io.truncated + e, tile + L.truncated, count);
+      tile_copy(reinterpret_cast<uint8_t*>(io.env_task_count + e), tile + L.env_task_count, count * 4);
+      tile_copy(reinterpret_cast<uint8_t*>(io.agent_task_count + e * n), tile + L.agent_task_count, count * n * 4);
+      tile_copy(reinterpret_cast<uint8_t*>(io.attacker_self + e * n_att * 2), tile + L.attacker_self, count * n_att * 8);
+      tile_copy(reinterpret_cast<uint8_t*>(io.defender_self + e * n_def * 3), tile + L.defender_self, count * n_def * 12);
+      tile_copy(reinterpret_cast<uint8_t*>(io.task_obs + e * N * 2), tile + L.task_obs, count * N * 8);
+      tile_copy(io.monitored + e * n_def, tile + L.monitored, count * n_def);
+    }
+  }
+  finish_launch(control, alive_bits, faults, 0u, skip ? kPublishNothing : kPublishStep);
 }
 
 __global__ void cyber_restore_kernel(const FrzCyberParams p, const FrzCyberBuffers io, const int B,
@@ -252,10 +461,26 @@ int cyber_validate(const FrzCyberParams* p, const FrzCyberBuffers* io, int B, co
   return FRZ_OK;
 }
 
+constexpr int kCyMaxTileBytes = 72 * 1024;  // keeps >= 3 tiles resident per SM
+
 int cyber_launch(const FrzCyberParams* p, const FrzCyberBuffers* io, int B, int mode, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (mode == kCyStep) {
+    const bool injected = io->network_uniforms != nullptr || io->agent_uniforms != nullptr;
+    const CyberTileLayout layout = cyber_tile_layout(p->num_nodes, p->num_attackers, p->num_defenders, injected);
+    if (layout.total <= kCyMaxTileBytes) {
+      auto kernel = injected ? cyber_step_tiled_kernel<true> : cyber_step_tiled_kernel<false>;
+      if (layout.total > 48 * 1024 &&
+          cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, layout.total) != cudaSuccess)
+        return check_launch("cyber tile shared memory");
+      kernel<<<(B + kCyThreads - 1) / kCyThreads, kCyThreads, layout.total, s>>>(*p, *io, B);
+      return check_launch("cyber_step_tiled_kernel");
+    }
+  }
   const int work = (B + kCyThreads - 1) / kCyThreads;
   const int grid = persistent_grid(work, 8);
-  cyber_step_kernel<<<grid, kCyThreads, 0, static_cast<cudaStream_t>(stream)>>>(*p, *io, B, mode);
+  if (mode == kCyStep) cyber_step_kernel<kCyStep><<<grid, kCyThreads, 0, s>>>(*p, *io, B);
+  else cyber_step_kernel<kCyRefresh><<<grid, kCyThreads, 0, s>>>(*p, *io, B);
   return check_launch("cyber_step_kernel");
 }
 

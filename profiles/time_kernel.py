@@ -44,12 +44,33 @@ def child(args):
     torch.cuda.synchronize()
     times = [b.elapsed_time(a) for b, a in pairs]
     raw.check_errors()
+
+    # launch-overhead-free estimate for small batches: K x [sample, step] in one CUDA graph minus K x [sample]
+    def graph_time(with_step: bool, repeats: int = 20) -> float:
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(repeats):
+                raw.sample_actions(2026)
+                if with_step:
+                    raw.step_environment()
+        graph.replay()
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(5):
+            graph.replay()
+        stop.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(stop) / (5 * repeats)
+
+    graph_us = 1e3 * (graph_time(True) - graph_time(False))
     bytes_per_env = bench.algorithmic_bytes(spec['domain'], raw)
     peak, _ = bench.measured_peak_gbs()
     mean = sum(times) / len(times)
     checksum = float(raw._cumulative.double().sum().item())
     print(json.dumps({'library': os.environ.get('FRZ_LIBRARY', 'default'), 'workload': args.workload, 'B': B,
-                      'kernel_us_mean': 1e3 * mean, 'kernel_us_min': 1e3 * min(times),
+                      'kernel_us_mean': 1e3 * mean, 'kernel_us_min': 1e3 * min(times), 'kernel_us_in_graph': graph_us,
                       'frac': bytes_per_env * B / (mean * 1e-3) / 1e9 / peak, 'reward_checksum': checksum}))
 
 
