@@ -43,89 +43,131 @@ struct CyberRows {
 };
 
 // One environment, one thread.  Returns the launch-epilogue bits through alive_bits / faults.
-template <int MODE>
+//
+// MAXN / MAXATT / MAXDEF are compile-time upper bounds of the node / attacker / defender counts (0 = no bound: runtime
+// loops).  With bounds every loop is fully unrolled and the environment's actions, locations and presence live in
+// registers for the whole step; the runtime counts only predicate the unrolled iterations.
+template <int MODE, int MAXN, int MAXATT, int MAXDEF>
 __device__ __forceinline__ void cyber_env_step(const FrzCyberParams& p, const CyberRows& r, const float* score_lut,
                                                const Philox& philox, const uint64_t step, const int64_t global_env,
                                                unsigned& alive_bits, unsigned& faults) {
-  const int N = p.num_nodes, n_att = p.num_attackers, n_def = p.num_defenders, n_agents = n_att + n_def;
+  constexpr bool kBounded = MAXN > 0;
+  const int N = p.num_nodes, n_att = p.num_attackers, n_def = p.num_defenders;
+  // loop bounds: the compile-time bound when there is one (the body is then predicated by the runtime count)
+  const int kNodes = kBounded ? MAXN : N, kAtt = kBounded ? MAXATT : n_att, kDef = kBounded ? MAXDEF : n_def;
   const bool show_bad = p.flags & FRZ_CY_SHOW_BAD_ACTIONS;
   const bool stochastic = p.flags & FRZ_CY_STOCHASTIC_STATE;
 
+  // register copies of the rows (bounded variant); the unbounded variant re-reads the rows instead
+  int2 att_act[kBounded ? MAXATT : 1] = {}, def_act[kBounded ? MAXDEF : 1] = {};
+  int def_loc[kBounded ? MAXDEF : 1] = {};
+  const auto attacker_action = [&](int i) { return kBounded ? att_act[kBounded ? i : 0] : r.actions[i]; };
+  const auto defender_action = [&](int d) { return kBounded ? def_act[kBounded ? d : 0] : r.actions[n_att + d]; };
+  const auto defender_location = [&](int d) { return kBounded ? def_loc[kBounded ? d : 0] : r.location[d]; };
+
   uint32_t present = 0;  // bit a = agent a is present (attackers first)
-  for (int a = 0; a < n_agents; ++a) present |= uint32_t(r.presence[a] != 0) << a;
+#pragma unroll
+  for (int i = 0; i < kAtt; ++i) {
+    if (i < n_att) {
+      present |= uint32_t(r.presence[i] != 0) << i;
+      if (kBounded && MODE == kCyStep) att_act[kBounded ? i : 0] = r.actions[i];
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < kDef; ++d) {
+    if (d < n_def) {
+      present |= uint32_t(r.presence[n_att + d] != 0) << (n_att + d);
+      if (kBounded) def_loc[kBounded ? d : 0] = r.location[d];
+      if (kBounded && MODE == kCyStep) def_act[kBounded ? d : 0] = r.actions[n_att + d];
+    }
+  }
 
   if (MODE == kCyStep) {
     const uint32_t env_lo = uint32_t(global_env), env_hi = uint32_t(uint64_t(global_env) >> 32);
+    const uint32_t step_lo = uint32_t(step), step_hi = uint32_t(step >> 32) ^ env_hi;
 
     // ---------------------------------------------------------------- decode (cybersecurity.py:317-384)
-    // Only bit sets are kept; who acts on which node is re-read from the action rows below (they sit in shared memory
-    // on the step path).  The subnetwork transition only depends on the attacks / patches decided here -- patches use
-    // the defender's location BEFORE this step's move -- so it runs before movement / presence overwrite the rows.
-    uint32_t patching = 0, monitoring = 0;
-#pragma unroll 1
-    for (int a = 0; a < n_agents; ++a) {
-      const int2 act = r.actions[a];
-      if (!show_bad && !((present >> a) & 1u) && act.y != -1) faults |= FRZ_FAULT_ABSENT_ACTED;  // :345,362
-      if (act.y == 0 && (act.x < 0 || act.x >= N)) faults |= FRZ_FAULT_BAD_NODE;                 // :341,357
-      if (a >= n_att) {
-        if (act.y == -2 && r.location[a - n_att] != -1) patching |= 1u << a;  // :354
-        if (act.y == -3) monitoring |= 1u << a;
+    // The subnetwork transition only depends on the attacks / patches decided here -- patches use the defender's
+    // location BEFORE this step's move -- so it runs before movement / presence change the rows.
+    uint32_t patching = 0, monitoring = 0;  // bit d = defender d
+#pragma unroll
+    for (int i = 0; i < kAtt; ++i) {
+      if (i < n_att) {
+        const int2 act = attacker_action(i);
+        if (!show_bad && !((present >> i) & 1u) && act.y != -1) faults |= FRZ_FAULT_ABSENT_ACTED;  // :345
+        if (act.y == 0 && (act.x < 0 || act.x >= N)) faults |= FRZ_FAULT_BAD_NODE;                 // :341
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < kDef; ++d) {
+      if (d < n_def) {
+        const int2 act = defender_action(d);
+        if (!show_bad && !((present >> (n_att + d)) & 1u) && act.y != -1) faults |= FRZ_FAULT_ABSENT_ACTED;  // :362
+        if (act.y == 0 && (act.x < 0 || act.x >= N)) faults |= FRZ_FAULT_BAD_NODE;                           // :357
+        if (act.y == -2 && defender_location(d) != -1) patching |= 1u << d;                                  // :354
+        if (act.y == -3) monitoring |= 1u << d;
       }
     }
 
     // ---------------------------------------------------------------- subnetwork.py:40-72 + rewards :395-409
     float network_reward = 0.f;
     uint4 bits = make_uint4(0u, 0u, 0u, 0u);  // one Philox call serves four consecutive nodes / agents
-#pragma unroll 1
-    for (int node = 0; node < N; ++node) {
-      uint32_t actors = 0;
-      float attacks = 0.f, patches = 0.f;
-      for (int a = 0; a < n_att; ++a) {
-        const int2 act = r.actions[a];
-        if (act.y == 0 && act.x == node) {  // attack node act.x
-          actors |= 1u << a;
-          attacks = __fadd_rn(attacks, p.power[a]);
+#pragma unroll
+    for (int node = 0; node < kNodes; ++node) {
+      if (node < N) {
+        uint32_t actors = 0;
+        float attacks = 0.f, patches = 0.f;
+#pragma unroll
+        for (int i = 0; i < kAtt; ++i) {
+          if (i < n_att) {
+            const int2 act = attacker_action(i);
+            if (act.y == 0 && act.x == node) {  // attack node act.x
+              actors |= 1u << i;
+              attacks = __fadd_rn(attacks, p.power[i]);
+            }
+          }
         }
-      }
-      for (int a = n_att; a < n_agents; ++a) {
-        if (((patching >> a) & 1u) && r.location[a - n_att] == node) {  // patch the node the defender stands on
-          actors |= 1u << a;
-          patches = __fadd_rn(patches, p.power[a]);
+#pragma unroll
+        for (int d = 0; d < kDef; ++d) {
+          if (d < n_def && ((patching >> d) & 1u) && defender_location(d) == node) {  // patch the node stood on
+            actors |= 1u << (n_att + d);
+            patches = __fadd_rn(patches, p.power[n_att + d]);
+          }
         }
-      }
-      float score;
-      if (p.lut_bits > 0) score = score_lut[actors];
-      else score = tanhf(__fdiv_rn(__fadd_rn(patches, -attacks), p.temperature));
-      bool better = score > 0.f, worse = score < 0.f;
-      if (stochastic) {
-        float u;
-        if (r.network_uniforms != nullptr) {
-          u = r.network_uniforms[node];
-        } else {
-          if ((node & 3) == 0) bits = philox(env_lo, uint32_t(step), uint32_t(node >> 2), uint32_t(step >> 32) ^ env_hi);
-          const uint32_t word = (node & 3) == 0 ? bits.x : (node & 3) == 1 ? bits.y : (node & 3) == 2 ? bits.z : bits.w;
-          u = u01(word);
+        float score;
+        if (p.lut_bits > 0) score = score_lut[actors];
+        else score = tanhf(__fdiv_rn(__fadd_rn(patches, -attacks), p.temperature));
+        bool better = score > 0.f, worse = score < 0.f;
+        if (stochastic) {
+          float u;
+          if (r.network_uniforms != nullptr) {
+            u = r.network_uniforms[node];
+          } else {
+            if ((node & 3) == 0) bits = philox(env_lo, step_lo, uint32_t(node >> 2), step_hi);
+            const uint32_t word = (node & 3) == 0 ? bits.x : (node & 3) == 1 ? bits.y : (node & 3) == 2 ? bits.z : bits.w;
+            u = u01(word);
+          }
+          const bool within = fabsf(score) <= u;  // larger |score| => LESS likely, as in the reference
+          better = better && within;
+          worse = worse && within;
         }
-        const bool within = fabsf(score) <= u;  // larger |score| => LESS likely, as in the reference
-        better = better && within;
-        worse = worse && within;
+        int s = r.state[node] - int(better) + int(worse);
+        s = min(max(s, 0), p.num_states - 1);
+        r.state[node] = s;
+        network_reward = __fadd_rn(network_reward, __fmul_rn(p.state_rewards[s], p.criticality[node]));
+        r.task_obs[node] = make_int2(s, int(p.criticality[node]));
       }
-      int s = r.state[node] - int(better) + int(worse);
-      s = min(max(s, 0), p.num_states - 1);
-      r.state[node] = s;
-      network_reward = __fadd_rn(network_reward, __fmul_rn(p.state_rewards[s], p.criticality[node]));
-      r.task_obs[node] = make_int2(s, int(p.criticality[node]));
     }
 
     // ---------------------------------------------------------------- movement.py:17-32 + presence.py:35-60
+    // one uniform per agent, agent a uses word a of the agent stream (attackers first)
     uint32_t now_present = 0;
-#pragma unroll 1
-    for (int a = 0; a < n_agents; ++a) {
+    const auto presence_step = [&](int a) {
       float u;
       if (r.agent_uniforms != nullptr) {
         u = r.agent_uniforms[a];
       } else {
-        if ((a & 3) == 0) bits = philox(env_lo, uint32_t(step), 0x80000000u | uint32_t(a >> 2), uint32_t(step >> 32) ^ env_hi);
+        if ((a & 3) == 0 || a == n_att) bits = philox(env_lo, step_lo, 0x80000000u | uint32_t(a >> 2), step_hi);
         const uint32_t word = (a & 3) == 0 ? bits.x : (a & 3) == 1 ? bits.y : (a & 3) == 2 ? bits.z : bits.w;
         u = u01(word);
       }
@@ -135,13 +177,21 @@ __device__ __forceinline__ void cyber_env_step(const FrzCyberParams& p, const Cy
       const bool is = (was || returning) && !leaving;
       now_present |= uint32_t(is) << a;
       r.presence[a] = is;
-      if (a >= n_att) {
-        const int d = a - n_att;
-        const int2 act = r.actions[a];
-        int loc = r.location[d];
+      return returning;
+    };
+#pragma unroll
+    for (int i = 0; i < kAtt; ++i)
+      if (i < n_att) presence_step(i);
+#pragma unroll
+    for (int d = 0; d < kDef; ++d) {
+      if (d < n_def) {
+        const bool returning = presence_step(n_att + d);
+        const int2 act = defender_action(d);
+        int loc = defender_location(d);
         if (act.y == 0) loc = act.x;  // move to node act.x (no adjacency check, movement.py:17-32)
         if (returning) loc = -1;      // returning defenders start at the home node
         r.location[d] = loc;
+        if (kBounded) def_loc[kBounded ? d : 0] = loc;
       }
     }
 
@@ -150,32 +200,52 @@ __device__ __forceinline__ void cyber_env_step(const FrzCyberParams& p, const Cy
     r.num_moves[0] = moves;
     r.truncated[0] = truncated;
     alive_bits |= 1u | (truncated ? 0u : 2u);  // cybersecurity never terminates (:299)
-#pragma unroll 1
-    for (int a = 0; a < n_agents; ++a) {
-      float reward = ((patching >> a) & 1u) ? p.patch_reward : 0.f;  // :376 (the bad-action branch :379-381 is dead)
-      reward = __fadd_rn(reward, a < n_att ? -network_reward : network_reward);
-      r.rewards[a] = reward;
-      r.cumulative[a] = __fadd_rn(r.cumulative[a], reward);
-      if (a >= n_att) r.monitored[a - n_att] = (monitoring >> a) & 1u;
+#pragma unroll
+    for (int i = 0; i < kAtt; ++i) {
+      if (i < n_att) {
+        const float reward = __fadd_rn(0.f, -network_reward);
+        r.rewards[i] = reward;
+        r.cumulative[i] = __fadd_rn(r.cumulative[i], reward);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < kDef; ++d) {
+      if (d < n_def) {
+        const int a = n_att + d;
+        // :376 (the bad-action branch :379-381 is dead)
+        const float reward = __fadd_rn(((patching >> d) & 1u) ? p.patch_reward : 0.f, network_reward);
+        r.rewards[a] = reward;
+        r.cumulative[a] = __fadd_rn(r.cumulative[a], reward);
+        r.monitored[d] = (monitoring >> d) & 1u;
+      }
     }
     present = now_present;
   } else {
-    for (int node = 0; node < N; ++node) r.task_obs[node] = make_int2(r.state[node], int(p.criticality[node]));
+#pragma unroll
+    for (int node = 0; node < kNodes; ++node)
+      if (node < N) r.task_obs[node] = make_int2(r.state[node], int(p.criticality[node]));
   }
 
   // ------------------------------------------------------------------ update_actions / update_observations
   r.env_task_count[0] = N;
-  for (int a = 0; a < n_agents; ++a) {
-    const bool is = (present >> a) & 1u;
-    r.agent_task_count[a] = is ? N : 0;
-    if (a < n_att) {
-      r.attacker_self[a] = make_float2(p.power[a], is ? 1.f : 0.f);
-    } else {
-      const int d = a - n_att;
+#pragma unroll
+  for (int i = 0; i < kAtt; ++i) {
+    if (i < n_att) {
+      const bool is = (present >> i) & 1u;
+      r.agent_task_count[i] = is ? N : 0;
+      r.attacker_self[i] = make_float2(p.power[i], is ? 1.f : 0.f);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < kDef; ++d) {
+    if (d < n_def) {
+      const int a = n_att + d;
+      const bool is = (present >> a) & 1u;
+      r.agent_task_count[a] = is ? N : 0;
       float* out = r.defender_self + d * 3;
       out[0] = p.power[a];
       out[1] = is ? 1.f : 0.f;
-      out[2] = float(r.location[d]);
+      out[2] = float(defender_location(d));
     }
   }
 }
@@ -214,7 +284,7 @@ cyber_step_kernel(const __grid_constant__ FrzCyberParams p, const __grid_constan
       r.monitored = io.monitored + e * n_def;
       r.network_uniforms = io.network_uniforms != nullptr ? io.network_uniforms + e * N : nullptr;
       r.agent_uniforms = io.agent_uniforms != nullptr ? io.agent_uniforms + e * n_agents : nullptr;
-      cyber_env_step<MODE>(p, r, io.score_lut, philox, step, p.env_offset + env, alive_bits, faults);
+      cyber_env_step<MODE, 0, 0, 0>(p, r, io.score_lut, philox, step, p.env_offset + env, alive_bits, faults);
     }
   }
   finish_launch(control, alive_bits, faults, 0u,
@@ -269,7 +339,7 @@ __device__ __forceinline__ void tile_copy(uint8_t* dst, const uint8_t* src, int 
   for (int i = threadIdx.x; i < bytes; i += kCyThreads) dst[i] = src[i];
 }
 
-template <bool INJECTED>
+template <bool INJECTED, int MAXN, int MAXATT, int MAXDEF>
 __global__ void __launch_bounds__(kCyThreads)
 cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_constant__ FrzCyberBuffers io, const int B) {
   extern __shared__ __align__(128) uint8_t tile[];
@@ -346,7 +416,7 @@ cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_c
       r.monitored = tile + L.monitored + t * n_def;
       r.network_uniforms = inject_network ? reinterpret_cast<const float*>(tile + L.network_uniforms) + t * N : nullptr;
       r.agent_uniforms = inject_agent ? reinterpret_cast<const float*>(tile + L.agent_uniforms) + t * n : nullptr;
-      cyber_env_step<kCyStep>(p, r, io.score_lut, philox, step, p.env_offset + first + t, alive_bits, faults);
+      cyber_env_step<kCyStep, MAXN, MAXATT, MAXDEF>(p, r, io.score_lut, philox, step, p.env_offset + first + t, alive_bits, faults);
     }
 
     // ------------------------------------------------------------------ stage out
@@ -469,7 +539,14 @@ int cyber_launch(const FrzCyberParams* p, const FrzCyberBuffers* io, int B, int 
     const bool injected = io->network_uniforms != nullptr || io->agent_uniforms != nullptr;
     const CyberTileLayout layout = cyber_tile_layout(p->num_nodes, p->num_attackers, p->num_defenders, injected);
     if (layout.total <= kCyMaxTileBytes) {
-      auto kernel = injected ? cyber_step_tiled_kernel<true> : cyber_step_tiled_kernel<false>;
+      // size classes: loops over nodes / attackers / defenders are unrolled to the class bound (0 = runtime loops)
+      void (*kernel)(FrzCyberParams, FrzCyberBuffers, int);
+      const int N = p->num_nodes, att = p->num_attackers, def = p->num_defenders;
+      if (injected) kernel = cyber_step_tiled_kernel<true, 0, 0, 0>;
+      else if (N <= 4 && att <= 2 && def <= 2) kernel = cyber_step_tiled_kernel<false, 4, 2, 2>;
+      else if (N <= 8 && att <= 4 && def <= 4) kernel = cyber_step_tiled_kernel<false, 8, 4, 4>;
+      else if (N <= 16 && att <= 8 && def <= 8) kernel = cyber_step_tiled_kernel<false, 16, 8, 8>;
+      else kernel = cyber_step_tiled_kernel<false, 0, 0, 0>;
       if (layout.total > 48 * 1024 &&
           cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, layout.total) != cudaSuccess)
         return check_launch("cyber tile shared memory");
