@@ -109,7 +109,8 @@ RS_TASK_COLUMNS = 8
 
 class RideshareParams(C.Structure):
     _fields_ = [
-        ('num_agents', C.c_int32), ('capacity', C.c_int32), ('schedule_rows', C.c_int32), ('pool_limit', C.c_int32),
+        ('num_agents', C.c_int32), ('capacity', C.c_int32), ('schedule_rows', C.c_int32), ('schedule_horizon', C.c_int32),
+        ('pool_limit', C.c_int32),
         ('max_steps', C.c_int32), ('flags', C.c_uint32), ('env_offset', C.c_int64), ('wait_limit', C.c_int32 * 3),
         ('long_wait_time', C.c_int32), ('move_cost', C.c_float), ('drop_cost', C.c_float), ('noop_cost', C.c_float),
         ('accept_cost', C.c_float), ('pool_limit_cost', C.c_float), ('general_wait_cost', C.c_float),
@@ -117,7 +118,7 @@ class RideshareParams(C.Structure):
     ]
 
 
-_RS_POINTERS = ('agents', 'passengers', 'init_agents', 'init_passengers', 'init_count', 'schedule', 'actions',
+_RS_POINTERS = ('agents', 'passengers', 'init_agents', 'init_passengers', 'init_count', 'schedule', 'schedule_index', 'actions',
                 'rewards', 'cumulative_rewards', 'terminated', 'truncated', 'num_moves', 'env_task_count',
                 'agent_task_count', 'task_mask', 'self_obs', 'task_obs', 'control')
 

@@ -11,6 +11,7 @@
 // shared memory with coalesced loads, lane p owns table row p (and p+32 when K > 32), lane a owns agent a.  Task
 // lists, conflict detection, compaction and the per-class "last row" reward quirk are ballots, match_any and
 // popcounts; agent -> passenger effects travel through shuffles.
+#include <climits>
 #include <math_constants.h>
 
 #include "frz_common.cuh"
@@ -40,38 +41,49 @@ __device__ __forceinline__ int select_bit64(uint64_t mask, int k) {
   return k < in_lo ? select_bit(lo, k) : 32 + select_bit(uint32_t(mask >> 32), k - in_lo);
 }
 
-__device__ __forceinline__ float l2(int dy, int dx) { return __fsqrt_rn(float(dy * dy + dx * dx)); }
+// Squared Euclidean length.  The reference compares fp32 L2 norms of small integer vectors (movement.py:57-116,
+// passenger_state.py:48-74); sqrt is strictly increasing on these exactly representable integers (neighbouring values are
+// > 1e-3 apart, far above an fp32 ulp), so argmin, ties, "== 0" and "< 1e-6" give the same answers on the squares.
+__device__ __forceinline__ int squared(int dy, int dx) { return dy * dy + dx * dx; }
 
-template <int PPL>
+// MODE is a template parameter so that the refresh / reset variants carry none of the step's code.
+template <int PPL, int MODE>
 __global__ void __launch_bounds__(kRsThreads)
 rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid_constant__ FrzRideshareBuffers io,
-                      const int B, const int mode, const uint8_t* __restrict__ entry_mask) {
+                      const int B, const uint8_t* __restrict__ entry_mask) {
   extern __shared__ int smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // broadcast from lane 0: makes the warp index, hence the environment loop and every ballot, provably warp-uniform
+  const int warp = __shfl_sync(kFullMask, int(threadIdx.x >> 5), 0);
+  constexpr int warps = kRsThreads / 32;
   const int K = p.capacity, A = p.num_agents, S = p.schedule_rows;
-  int* table = smem + warp * (K * kCols);
+  // this warp's passenger table as a 32-bit shared-window address: rows are read / written as [table + 4 * index]
+  const uint32_t table = shared_address(smem) + uint32_t(warp * (K * kCols)) * 4u;
   const uint32_t lanes_below = (1u << lane) - 1u;
 
   FrzControl* control = io.control;
   const uint32_t alive_prev = control->alive;
   const uint32_t agents_with_tasks = control->agents_with_tasks;
-  const bool skip = (mode == kRsStep) && ((alive_prev & 3u) != 3u);  // utils/env.py:212
+  const bool skip = (MODE == kRsStep) && ((alive_prev & 3u) != 3u);  // utils/env.py:212
   const bool is_agent = lane < A;
   const bool fast = p.flags & FRZ_RS_FAST_TRAVEL, diagonal = p.flags & FRZ_RS_DIAGONAL_TRAVEL;
   const int directions = diagonal ? 9 : 5;
+  // task-mask stores: lane -> (agent, four consecutive table rows)
+  const int quads = (K + 3) >> 2;
+  const uint32_t inverse_quads = (65536u + uint32_t(quads) - 1u) / uint32_t(quads);  // item / quads for item < 512
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
 
   if (!skip) {
     for (int env = blockIdx.x * warps + warp; env < B; env += gridDim.x * warps) {
+      const uint32_t agent_at = uint32_t(env) * uint32_t(A) + uint32_t(lane);
+      const uint32_t table_at = uint32_t(env) * uint32_t(K * kCols);
       const int n_before = min(io.env_task_count[env], K);
-      int* global_rows = io.passengers + size_t(env) * K * kCols;
-      for (int i = lane; i < n_before * kCols; i += 32) table[i] = global_rows[i];
-      __syncwarp();
+      int* const global_rows = io.passengers + table_at;
+      for (int i = lane; i < n_before * kCols; i += 32) sts(table + 4u * i, uint32_t(global_rows[i]));
 
-      const size_t agent_row = size_t(env) * A;
       int agent_y = 0, agent_x = 0;
       if (is_agent) {
-        const int2 at = reinterpret_cast<const int2*>(io.agents)[agent_row + lane];
+        const int2 at = reinterpret_cast<const int2*>(io.agents)[agent_at];
         agent_y = at.x;
         agent_x = at.y;
       }
@@ -79,8 +91,9 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
       int n_kept = n_before, fare_won = 0;
       float move_cost = 0.f;
       bool noop = false, accept = false;
+      __syncwarp();
 
-      if (mode == kRsStep) {
+      if (MODE == kRsStep) {
         // rows owned by this lane
         int row[PPL][kCols];
         bool valid[PPL];
@@ -89,7 +102,7 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
           const int r = lane + 32 * i;
           valid[i] = r < n_before;
 #pragma unroll
-          for (int c = 0; c < kCols; ++c) row[i][c] = valid[i] ? table[r * kCols + c] : -1;
+          for (int c = 0; c < kCols; ++c) row[i][c] = valid[i] ? int(lds(table + 4u * (r * kCols + c))) : -1;
         }
 
         // ---------------------------------------------------------------- task lists (rideshare.py:374-386)
@@ -107,7 +120,7 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
 
         // ---------------------------------------------------------------- decode (rideshare.py:255-300)
         int2 act = make_int2(0, -100);
-        if (is_agent) act = reinterpret_cast<const int2*>(io.actions)[agent_row + lane];
+        if (is_agent) act = reinterpret_cast<const int2*>(io.actions)[agent_at];
         noop = act.y == -1;
         accept = act.y == 0;
         const bool pick = act.y == 1, drop = act.y == 2;
@@ -120,24 +133,24 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         const bool has_vector = target >= 0 && (accept || pick || drop);
         int goal_y = 0, goal_x = 0, fare_target = 0;
         if (has_vector) {
-          const int* t = table + target * kCols;
-          goal_y = drop ? t[cDestY] : t[cY];
-          goal_x = drop ? t[cDestX] : t[cX];
-          fare_target = t[cFare];
+          const uint32_t t = table + 4u * uint32_t(target * kCols);
+          goal_y = int(lds(t + 4u * (drop ? cDestY : cY)));
+          goal_x = int(lds(t + 4u * (drop ? cDestX : cX)));
+          fare_target = int(lds(t + 4u * cFare));
         }
 
         // ---------------------------------------------------------------- movement (transitions/movement.py:57-116)
         int move_y = 0, move_x = 0;
-        float distance = CUDART_INF_F;  // agent -> goal before moving (passenger_state.py:48-49)
+        int distance2 = INT_MAX;  // squared distance agent -> goal before moving (passenger_state.py:48-49)
         if (has_vector) {
-          distance = l2(agent_y - goal_y, agent_x - goal_x);
+          distance2 = squared(agent_y - goal_y, agent_x - goal_x);
           if (fast) {
             move_y = goal_y - agent_y;
             move_x = goal_x - agent_x;
           } else {
-            float best = CUDART_INF_F;
+            int best = INT_MAX;
             for (int d = 0; d < directions; ++d) {  // first argmin: strict <
-              const float candidate = l2(agent_y + kDirY[d] - goal_y, agent_x + kDirX[d] - goal_x);
+              const int candidate = squared(agent_y + kDirY[d] - goal_y, agent_x + kDirX[d] - goal_x);
               if (candidate < best) {
                 best = candidate;
                 move_y = kDirY[d];
@@ -145,7 +158,7 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
               }
             }
           }
-          move_cost = diagonal ? l2(move_y, move_x) : float(abs(move_y) + abs(move_x));
+          move_cost = diagonal ? __fsqrt_rn(float(squared(move_y, move_x))) : float(abs(move_y) + abs(move_x));
         }
         agent_y += move_y;
         agent_x += move_x;
@@ -166,18 +179,16 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         {
           const unsigned key = claim >= 0 ? unsigned(claim) : (0x80000000u | unsigned(lane));
           const bool duplicated = __popc(__match_any_sync(kFullMask, key)) > 1;
-          if (__ballot_sync(kFullMask, duplicated)) {
+          if (__any_sync(kFullMask, duplicated)) {
             // among ALL duplicated claims of the environment only the closest claimant (first on ties) survives
-            float contest = duplicated ? distance : CUDART_INF_F, closest = contest;
-#pragma unroll
-            for (int offset = 16; offset >= 1; offset >>= 1)
-              closest = fminf(closest, __shfl_xor_sync(kFullMask, closest, offset));
+            const int contest = duplicated ? distance2 : INT_MAX;
+            const int closest = __reduce_min_sync(kFullMask, contest);
             const int keeper = __ffs(__ballot_sync(kFullMask, duplicated && contest == closest)) - 1;
             if (duplicated && lane != keeper) claim = -1;
           }
         }
-        const int picked = (pick && target >= 0 && distance < 1e-6f) ? target : -1;  // passenger_state.py:89-92
-        const int dropped = (drop && target >= 0 && distance == 0.f) ? target : -1;   // passenger_exit.py:40-45
+        const int picked = (pick && target >= 0 && distance2 == 0) ? target : -1;   // passenger_state.py:89-92 (< 1e-6)
+        const int dropped = (drop && target >= 0 && distance2 == 0) ? target : -1;  // passenger_exit.py:40-45 (== 0)
         fare_won = dropped >= 0 ? fare_target : 0;
 
         // ---------------------------------------------------------------- apply to the rows (accept, then pick, exit)
@@ -195,11 +206,11 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
             }
           }
         }
-        for (int a = 0; a < A; ++a) {
-          const int c = __shfl_sync(kFullMask, picked, a), d = __shfl_sync(kFullMask, dropped, a);
+        for (int a = 0; a < A; ++a) {  // all accepts land before any pick, like the reference's transition
+          const int k = __shfl_sync(kFullMask, picked, a), d = __shfl_sync(kFullMask, dropped, a);
 #pragma unroll
           for (int i = 0; i < PPL; ++i) {
-            if (valid[i] && c == lane + 32 * i) {
+            if (valid[i] && k == lane + 32 * i) {
               row[i][cState] = 2;
               row[i][cPicked] = t_now;
             }
@@ -215,52 +226,54 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         for (int i = 0; i < PPL; ++i) {
           if (keep[i]) {
             const uint64_t below = (i == 0) ? uint64_t(lanes_below) : ((uint64_t(lanes_below) << 32) | 0xffffffffull);
-            int* out = table + __popcll(kept & below) * kCols;
+            const uint32_t out = table + 4u * uint32_t(__popcll(kept & below) * kCols);
 #pragma unroll
-            for (int c = 0; c < kCols; ++c) out[c] = row[i][c];
+            for (int c = 0; c < kCols; ++c) sts(out + 4u * c, uint32_t(row[i][c]));
           }
         }
       }
 
       // ------------------------------------------------------------------ entry (passenger_entry.py:25-72)
       int n_rows = n_kept;
-      const bool admits = mode == kRsStep || (mode == kRsEntryRefresh && (entry_mask == nullptr || entry_mask[env]));
+      const bool admits = MODE == kRsStep || (MODE == kRsEntryRefresh && (entry_mask == nullptr || entry_mask[env]));
       if (admits) {
-        const int t_entry = (mode == kRsStep) ? t_now + 1 : t_now;  // rideshare.py:307 vs :212
-        const int64_t global_env = p.env_offset + env;
-        int lo = 0, hi = S;  // first schedule row with time >= t_entry (rows are sorted by time)
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (io.schedule[mid * 7] < t_entry) lo = mid + 1; else hi = mid;
+        const int t_entry = (MODE == kRsStep) ? t_now + 1 : t_now;  // rideshare.py:307 vs :212
+        // rows of the time-sorted schedule that enter at t_entry: [schedule_index[t], schedule_index[t + 1])
+        int lo = S, hi = S;
+        if (t_entry >= 0 && t_entry <= p.schedule_horizon) {
+          lo = io.schedule_index[t_entry];
+          hi = io.schedule_index[t_entry + 1];
         }
-        for (int base = lo; base < S; base += 32) {
-          const int r = base + lane;
-          const bool now = r < S && io.schedule[r * 7] == t_entry;
-          const int batch = now ? io.schedule[r * 7 + 1] : 0;
-          const bool enters = now && (batch == -1 || batch == global_env);
-          const unsigned entering = __ballot_sync(kFullMask, enters);
-          const int slot = n_rows + __popc(entering & lanes_below);
-          if (enters) {
-            if (slot < K) {
-              int* out = table + slot * kCols;
-              const int* s = io.schedule + r * 7;
-              out[cBatch] = env;
-              out[cY] = s[2];
-              out[cX] = s[3];
-              out[cDestY] = s[4];
-              out[cDestX] = s[5];
-              out[cFare] = s[6];
-              out[cState] = 0;
-              out[cAssoc] = -1;
-              out[cEntered] = t_entry;
-              out[cAccepted] = -1;
-              out[cPicked] = -1;
-            } else {
-              faults |= FRZ_FAULT_TABLE_FULL;
+        if (lo < hi) {
+          const int64_t global_env = p.env_offset + env;
+          for (int base = lo; base < hi; base += 32) {
+            const int r = base + lane;
+            const bool now = r < hi;
+            const int* s = io.schedule + r * 7;
+            const int batch = now ? s[1] : 0;
+            const bool enters = now && (batch == -1 || batch == global_env);
+            const unsigned entering = __ballot_sync(kFullMask, enters);
+            const int slot = n_rows + __popc(entering & lanes_below);
+            if (enters) {
+              if (slot < K) {
+                const uint32_t out = table + 4u * uint32_t(slot * kCols);
+                sts(out + 4u * cBatch, uint32_t(env));
+                sts(out + 4u * cY, uint32_t(s[2]));
+                sts(out + 4u * cX, uint32_t(s[3]));
+                sts(out + 4u * cDestY, uint32_t(s[4]));
+                sts(out + 4u * cDestX, uint32_t(s[5]));
+                sts(out + 4u * cFare, uint32_t(s[6]));
+                sts(out + 4u * cState, 0u);
+                sts(out + 4u * cAssoc, uint32_t(-1));
+                sts(out + 4u * cEntered, uint32_t(t_entry));
+                sts(out + 4u * cAccepted, uint32_t(-1));
+                sts(out + 4u * cPicked, uint32_t(-1));
+              } else {
+                faults |= FRZ_FAULT_TABLE_FULL;
+              }
             }
+            n_rows = min(n_rows + __popc(entering), K);
           }
-          n_rows = min(n_rows + __popc(entering), K);
-          if (__ballot_sync(kFullMask, now) != kFullMask) break;
         }
       }
       __syncwarp();
@@ -272,18 +285,19 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
       for (int i = 0; i < PPL; ++i) {
         const int r = lane + 32 * i;
         present[i] = r < n_rows;
-        const int* t = table + r * kCols;
-        state[i] = present[i] ? t[cState] : -1;
-        assoc[i] = present[i] ? t[cAssoc] : -1;
-        stamp[i] = present[i] ? t[state[i] == 0 ? cEntered : (state[i] == 1 ? cAccepted : cPicked)] : 0;
+        const uint32_t t = table + 4u * uint32_t(r * kCols);
+        state[i] = present[i] ? int(lds(t + 4u * cState)) : -1;
+        assoc[i] = present[i] ? int(lds(t + 4u * cAssoc)) : -1;
+        stamp[i] = present[i] ? int(lds(t + 4u * (state[i] == 0 ? cEntered : (state[i] == 1 ? cAccepted : cPicked)))) : 0;
         // task observation row (rideshare.py:398-416) + padding of rows that just became free
-        if (r < K && (present[i] || r < n_before || mode != kRsStep)) {
+        if (r < K && (present[i] || r < n_before || MODE != kRsStep)) {
           int4 head = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD), tail = head;
           if (present[i]) {
-            head = make_int4(t[cY], t[cX], t[cDestY], t[cDestX]);
-            tail = make_int4(state[i] == 1 ? assoc[i] : FRZ_PAD, state[i] == 2 ? assoc[i] : FRZ_PAD, t[cFare], t[cEntered]);
+            head = make_int4(int(lds(t + 4u * cY)), int(lds(t + 4u * cX)), int(lds(t + 4u * cDestY)), int(lds(t + 4u * cDestX)));
+            tail = make_int4(state[i] == 1 ? assoc[i] : FRZ_PAD, state[i] == 2 ? assoc[i] : FRZ_PAD, int(lds(t + 4u * cFare)),
+                             int(lds(t + 4u * cEntered)));
           }
-          int4* out = reinterpret_cast<int4*>(io.task_obs) + (size_t(env) * K + r) * 2;
+          int4* out = reinterpret_cast<int4*>(io.task_obs) + (uint32_t(env) * uint32_t(K) + uint32_t(r)) * 2u;
           out[0] = head;
           out[1] = tail;
         }
@@ -291,6 +305,7 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
 
       // per-agent counts; lane a keeps agent a's
       int associated = 0, n_accepted = 0, n_riding = 0, n_tasks = 0;
+      uint64_t members_mine = 0;
       bool pred[PPL];
 #pragma unroll
       for (int i = 0; i < PPL; ++i) pred[i] = present[i] && state[i] == 0;
@@ -305,22 +320,44 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
 #pragma unroll
         for (int i = 0; i < PPL; ++i) pred[i] = present[i] && assoc[i] == a && state[i] == 2;
         const uint64_t own_riding = ballot_rows<PPL>(pred);
-        const uint64_t members = unaccepted | own;
         if (lane == a) {
           associated = __popcll(own);
           n_accepted = __popcll(own_accepted);
           n_riding = __popcll(own_riding);
-          n_tasks = __popcll(members);
+          members_mine = unaccepted | own;
+          n_tasks = __popcll(members_mine);
         }
-        uint8_t* mask_row = io.task_mask + (agent_row + a) * K;
+      }
+      // task mask [A, K] bytes: work item (agent, four consecutive rows) -> one 4-byte store; K is a multiple of 4 or
+      // the last quad of a row spills into bytes that the next agent's first quad rewrites (rows are written in order)
+      {
+        uint32_t* const mask_words = reinterpret_cast<uint32_t*>(io.task_mask);
+        const bool aligned = (K & 3) == 0;
+        if (aligned) {
+          const uint32_t mask_at = uint32_t(env) * uint32_t(A * quads);
+          for (int first = 0; first < A * quads; first += 32) {
+            const int item = first + lane;
+            const int a = int((uint32_t(item) * inverse_quads) >> 16), q = item - a * quads;
+            const uint32_t lo = __shfl_sync(kFullMask, uint32_t(members_mine), a & 31);
+            const uint32_t hi = __shfl_sync(kFullMask, uint32_t(members_mine >> 32), a & 31);
+            const uint32_t nibble = ((q < 8 ? lo : hi) >> (4 * (q & 7))) & 0xfu;
+            if (item < A * quads) mask_words[mask_at + item] = (nibble * 0x00204081u) & 0x01010101u;
+          }
+        } else {
+          for (int a = 0; a < A; ++a) {
+            const uint64_t members = (uint64_t(__shfl_sync(kFullMask, uint32_t(members_mine >> 32), a)) << 32) |
+                                     __shfl_sync(kFullMask, uint32_t(members_mine), a);
+            uint8_t* mask_row = io.task_mask + (uint32_t(env) * uint32_t(A) + uint32_t(a)) * uint32_t(K);
 #pragma unroll
-        for (int i = 0; i < PPL; ++i) {
-          const int r = lane + 32 * i;
-          if (r < K) mask_row[r] = (members >> r) & 1u;
+            for (int i = 0; i < PPL; ++i) {
+              const int r = lane + 32 * i;
+              if (r < K) mask_row[r] = (members >> r) & 1u;
+            }
+          }
         }
       }
 
-      if (mode == kRsStep) {
+      if (MODE == kRsStep) {
         // ---------------------------------------------------------------- rewards (rideshare.py:309-363)
         float shared = 0.f;
         if (p.flags & FRZ_RS_WAITING_COSTS) {
@@ -363,9 +400,9 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
           if (p.flags & FRZ_RS_VARIABLE_MOVE_COST) move_reward = __fdiv_rn(move_reward, float(associated + 1));
           reward = __fadd_rn(reward, move_reward);
           reward = __fadd_rn(reward, shared);
-          io.rewards[agent_row + lane] = reward;
-          io.cumulative_rewards[agent_row + lane] = __fadd_rn(io.cumulative_rewards[agent_row + lane], reward);
-          reinterpret_cast<int2*>(io.agents)[agent_row + lane] = make_int2(agent_y, agent_x);
+          io.rewards[agent_at] = reward;
+          io.cumulative_rewards[agent_at] = __fadd_rn(io.cumulative_rewards[agent_at], reward);
+          reinterpret_cast<int2*>(io.agents)[agent_at] = make_int2(agent_y, agent_x);
         }
         if (lane == 0) {
           io.num_moves[env] = moves;
@@ -376,18 +413,18 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
 
       // ------------------------------------------------------------------ publish
       if (is_agent) {
-        io.agent_task_count[agent_row + lane] = n_tasks;
+        io.agent_task_count[agent_at] = n_tasks;
         if (n_tasks > 0) agent_bits |= 1u << lane;
-        reinterpret_cast<int4*>(io.self_obs)[agent_row + lane] = make_int4(agent_y, agent_x, n_accepted, n_riding);
+        reinterpret_cast<int4*>(io.self_obs)[agent_at] = make_int4(agent_y, agent_x, n_accepted, n_riding);
       }
       if (lane == 0) io.env_task_count[env] = n_rows;
       if (admits)
-        for (int i = lane; i < n_rows * kCols; i += 32) global_rows[i] = table[i];
+        for (int i = lane; i < n_rows * kCols; i += 32) global_rows[i] = int(lds(table + 4u * i));
       __syncwarp();
     }
   }
   finish_launch(control, alive_bits, faults, agent_bits,
-                skip ? kPublishNothing : (mode == kRsStep ? kPublishStep : kPublishRefresh));
+                skip ? kPublishNothing : (MODE == kRsStep ? kPublishStep : kPublishRefresh));
 }
 
 __global__ void rideshare_restore_kernel(const FrzRideshareParams p, const FrzRideshareBuffers io, const int B,
@@ -449,12 +486,13 @@ __global__ void rideshare_sample_kernel(const FrzRideshareParams p, const FrzRid
 
 int rideshare_validate(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, const char* what) {
   if (p == nullptr || io == nullptr || io->control == nullptr || io->passengers == nullptr || io->agents == nullptr ||
-      (p->schedule_rows > 0 && io->schedule == nullptr)) {
+      (p->schedule_rows > 0 && (io->schedule == nullptr || io->schedule_index == nullptr))) {
     set_error("%s: NULL params / buffers", what);
     return FRZ_ERR_NULL;
   }
   if (B <= 0 || p->num_agents < 1 || p->num_agents > FRZ_MAX_AGENTS || p->capacity < 1 ||
-      p->capacity > FRZ_MAX_PASSENGERS || p->schedule_rows < 0) {
+      p->capacity > FRZ_MAX_PASSENGERS || p->schedule_rows < 0 ||
+      uint64_t(B) * uint64_t(p->capacity) * FRZ_RS_PASSENGER_COLUMNS >= (1ull << 32)) {  // 32-bit element indices
     set_error("%s: unsupported shape B=%d agents=%d capacity=%d schedule=%d", what, B, p->num_agents, p->capacity,
               p->schedule_rows);
     return FRZ_ERR_SHAPE;
@@ -462,15 +500,23 @@ int rideshare_validate(const FrzRideshareParams* p, const FrzRideshareBuffers* i
   return FRZ_OK;
 }
 
-int rideshare_launch(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, int mode, void* stream,
-                     const uint8_t* entry_mask = nullptr) {
+template <int MODE>
+int rideshare_launch_mode(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, cudaStream_t s,
+                          const uint8_t* entry_mask) {
   const int warps = kRsThreads / 32;
   const size_t smem = size_t(warps) * p->capacity * kCols * sizeof(int);
   const int grid = persistent_grid((B + warps - 1) / warps, 12);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (p->capacity <= 32) rideshare_step_kernel<1><<<grid, kRsThreads, smem, s>>>(*p, *io, B, mode, entry_mask);
-  else rideshare_step_kernel<2><<<grid, kRsThreads, smem, s>>>(*p, *io, B, mode, entry_mask);
+  if (p->capacity <= 32) rideshare_step_kernel<1, MODE><<<grid, kRsThreads, smem, s>>>(*p, *io, B, entry_mask);
+  else rideshare_step_kernel<2, MODE><<<grid, kRsThreads, smem, s>>>(*p, *io, B, entry_mask);
   return check_launch("rideshare_step_kernel");
+}
+
+int rideshare_launch(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, int mode, void* stream,
+                     const uint8_t* entry_mask = nullptr) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (mode == kRsStep) return rideshare_launch_mode<kRsStep>(p, io, B, s, entry_mask);
+  if (mode == kRsRefresh) return rideshare_launch_mode<kRsRefresh>(p, io, B, s, entry_mask);
+  return rideshare_launch_mode<kRsEntryRefresh>(p, io, B, s, entry_mask);
 }
 
 }  // namespace

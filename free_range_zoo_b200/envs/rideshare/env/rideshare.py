@@ -58,6 +58,7 @@ def flatten_configuration(config, max_steps, parallel_envs: int, env_offset: int
     capacity = max(1, min(wildcard + addressed, _lib.MAX_PASSENGERS))
     p = _lib.RideshareParams()
     p.num_agents, p.capacity, p.schedule_rows, p.pool_limit = A, capacity, len(schedule), int(ac.pool_limit)
+    p.schedule_horizon = int(schedule[:, 0].max()) if len(schedule) else -1
     p.max_steps = 2**31 - 1 if max_steps is None else int(max_steps)
     p.flags = ((_lib.RS_FAST_TRAVEL if ac.use_fast_travel else 0) | (_lib.RS_DIAGONAL_TRAVEL if ac.use_diagonal_travel else 0) |
                (_lib.RS_VARIABLE_MOVE_COST if rc.use_variable_move_cost else 0) |
@@ -70,6 +71,11 @@ def flatten_configuration(config, max_steps, parallel_envs: int, env_offset: int
                  'long_wait_cost'):
         setattr(p, name, float(getattr(rc, name)))
     return p, schedule
+
+
+def schedule_index(schedule: np.ndarray, horizon: int) -> np.ndarray:
+    """index[t] = first row of the time-sorted schedule whose entry step is >= t, for t in [0, horizon + 1]."""
+    return np.searchsorted(schedule[:, 0], np.arange(horizon + 2), side='left').astype(np.int32)
 
 
 class raw_env(BatchedAECEnv):
@@ -102,6 +108,8 @@ class raw_env(BatchedAECEnv):
         self._init_passengers = torch.zeros((B, K, 11), dtype=i32, device=dev)
         self._init_count = torch.zeros(B, dtype=i32, device=dev)
         self._schedule = torch.from_numpy(schedule).to(dev) if len(schedule) else torch.zeros((1, 7), dtype=i32, device=dev)
+        index = schedule_index(schedule, self._params.schedule_horizon) if len(schedule) else np.zeros(1, np.int32)
+        self._schedule_index = torch.from_numpy(index).to(dev)
         self._task_mask = torch.zeros((B, A, K), dtype=torch.uint8, device=dev)
         self._self_obs = torch.zeros((B, A, 4), dtype=i32, device=dev)
         self._task_obs = torch.full((B, K, 8), _lib.PAD, dtype=i32, device=dev)
@@ -115,6 +123,7 @@ class raw_env(BatchedAECEnv):
         io = _lib.RideshareBuffers()
         tensors = dict(agents=self._state.agents, passengers=self._state.passenger_table, init_agents=self._init_agents,
                        init_passengers=self._init_passengers, init_count=self._init_count, schedule=self._schedule,
+                       schedule_index=self._schedule_index,
                        actions=self._actions, rewards=self._rewards, cumulative_rewards=self._cumulative,
                        terminated=self._terminated, truncated=self._truncated, num_moves=self.num_moves,
                        env_task_count=self.environment_task_count, agent_task_count=self._agent_task_count,

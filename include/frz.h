@@ -257,6 +257,7 @@ typedef struct {
   int32_t num_agents;
   int32_t capacity;        /* K: rows of the per-environment passenger table (<= FRZ_MAX_PASSENGERS) */
   int32_t schedule_rows;   /* S */
+  int32_t schedule_horizon;/* latest entry step named by the schedule (-1 when it is empty) */
   int32_t pool_limit;
   int32_t max_steps;
   uint32_t flags;
@@ -276,6 +277,8 @@ typedef struct {
   const int32_t* init_passengers;    /* [B, K, 11] table before the t = 0 entry (normally empty) */
   const int32_t* init_count;         /* [B] */
   const int32_t* schedule;   /* [S, 7] (t, batch | -1, y, x, dest_y, dest_x, fare), stably sorted by t */
+  const int32_t* schedule_index; /* [schedule_horizon + 2]: index[t] = first schedule row with entry step >= t, so the
+                                    rows entering at step t are [index[t], index[t + 1]); index[horizon + 1] = S */
   /* AEC runtime */
   const int32_t* actions;    /* [B, A, 2] (agent-local task index, action id: 0 accept, 1 pick, 2 drop, -1 noop) */
   float* rewards;            /* [B, A] */
