@@ -98,6 +98,13 @@ __device__ __forceinline__ void sts(uint32_t address, uint32_t value) {
   asm volatile("st.shared.u32 [%0], %1;" : : "r"(address), "r"(value) : "memory");
 }
 
+// Ampere-style asynchronous copies (LDGSTS) for pieces that are not 16-byte multiples
+__device__ __forceinline__ void cp_async_4(uint32_t shared_dst, const void* global_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" : : "r"(shared_dst), "l"(global_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" : : : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" : : : "memory"); }
+
 // ---------------------------------------------------------------------------------------------- bulk async copies
 
 // 1-D bulk copies of the async proxy (the TMA unit; SASS UBLKCP): one elected thread moves a whole tile between global

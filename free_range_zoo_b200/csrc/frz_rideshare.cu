@@ -57,8 +57,10 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
   const int warp = __shfl_sync(kFullMask, int(threadIdx.x >> 5), 0);
   constexpr int warps = kRsThreads / 32;
   const int K = p.capacity, A = p.num_agents, S = p.schedule_rows;
-  // this warp's passenger table as a 32-bit shared-window address: rows are read / written as [table + 4 * index]
-  const uint32_t table = shared_address(smem) + uint32_t(warp * (K * kCols)) * 4u;
+  // this warp's two passenger-table buffers as 32-bit shared-window addresses: the rows of the environment being
+  // stepped are read / written as [table + 4 * index] while cp.async fills the other buffer with the next one's
+  const uint32_t table_bytes = uint32_t(K * kCols) * 4u;
+  const uint32_t tables = shared_address(smem) + uint32_t(warp) * 2u * table_bytes;
   const uint32_t lanes_below = (1u << lane) - 1u;
 
   FrzControl* control = io.control;
@@ -74,12 +76,27 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
 
   if (!skip) {
-    for (int env = blockIdx.x * warps + warp; env < B; env += gridDim.x * warps) {
+    // software pipeline: while environment e is stepped, the rows of this warp's next environment stream into the
+    // other buffer (cp.async, 4 bytes per lane per instruction: rows are 44 bytes, so nothing wider stays aligned)
+    const int stride = gridDim.x * warps;
+    const auto prefetch_rows = [&](int env, int rows, uint32_t buffer) {
+      const int* source = io.passengers + uint32_t(env) * uint32_t(K * kCols);
+      for (int i = lane; i < rows * kCols; i += 32) cp_async_4(buffer + 4u * i, source + i);
+      cp_async_commit();
+    };
+    int env = blockIdx.x * warps + warp;
+    int n_next = env < B ? min(io.env_task_count[env], K) : 0;
+    uint32_t parity = 0;
+    if (env < B) prefetch_rows(env, n_next, tables);
+    for (; env < B; env += stride) {
+      const uint32_t table = tables + parity * table_bytes;
       const uint32_t agent_at = uint32_t(env) * uint32_t(A) + uint32_t(lane);
       const uint32_t table_at = uint32_t(env) * uint32_t(K * kCols);
-      const int n_before = min(io.env_task_count[env], K);
+      const int n_before = n_next;
       int* const global_rows = io.passengers + table_at;
-      for (int i = lane; i < n_before * kCols; i += 32) sts(table + 4u * i, uint32_t(global_rows[i]));
+      const int env_after = env + stride;
+      n_next = env_after < B ? min(io.env_task_count[env_after], K) : 0;  // needed by the prefetch issued below
+      cp_async_wait_all();
 
       int agent_y = 0, agent_x = 0;
       if (is_agent) {
@@ -277,6 +294,9 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         }
       }
       __syncwarp();
+
+      if (env_after < B) prefetch_rows(env_after, n_next, tables + (parity ^ 1u) * table_bytes);
+      parity ^= 1u;
 
       // ------------------------------------------------------------------ the new table, one row per lane again
       int state[PPL], assoc[PPL], stamp[PPL];
@@ -504,7 +524,7 @@ template <int MODE>
 int rideshare_launch_mode(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, cudaStream_t s,
                           const uint8_t* entry_mask) {
   const int warps = kRsThreads / 32;
-  const size_t smem = size_t(warps) * p->capacity * kCols * sizeof(int);
+  const size_t smem = size_t(warps) * 2 * p->capacity * kCols * sizeof(int);  // two table buffers per warp
   const int grid = persistent_grid((B + warps - 1) / warps, 12);
   if (p->capacity <= 32) rideshare_step_kernel<1, MODE><<<grid, kRsThreads, smem, s>>>(*p, *io, B, entry_mask);
   else rideshare_step_kernel<2, MODE><<<grid, kRsThreads, smem, s>>>(*p, *io, B, entry_mask);
