@@ -542,11 +542,14 @@ int cyber_launch(const FrzCyberParams* p, const FrzCyberBuffers* io, int B, int 
       // size classes: loops over nodes / attackers / defenders are unrolled to the class bound (0 = runtime loops)
       void (*kernel)(FrzCyberParams, FrzCyberBuffers, int);
       const int N = p->num_nodes, att = p->num_attackers, def = p->num_defenders;
-      if (injected) kernel = cyber_step_tiled_kernel<true, 0, 0, 0>;
-      else if (N <= 4 && att <= 2 && def <= 2) kernel = cyber_step_tiled_kernel<false, 4, 2, 2>;
-      else if (N <= 8 && att <= 4 && def <= 4) kernel = cyber_step_tiled_kernel<false, 8, 4, 4>;
-      else if (N <= 16 && att <= 8 && def <= 8) kernel = cyber_step_tiled_kernel<false, 16, 8, 8>;
-      else kernel = cyber_step_tiled_kernel<false, 0, 0, 0>;
+      if (N <= 4 && att <= 2 && def <= 2)
+        kernel = injected ? cyber_step_tiled_kernel<true, 4, 2, 2> : cyber_step_tiled_kernel<false, 4, 2, 2>;
+      else if (N <= 8 && att <= 4 && def <= 4)
+        kernel = injected ? cyber_step_tiled_kernel<true, 8, 4, 4> : cyber_step_tiled_kernel<false, 8, 4, 4>;
+      else if (N <= 16 && att <= 8 && def <= 8)
+        kernel = injected ? cyber_step_tiled_kernel<true, 16, 8, 8> : cyber_step_tiled_kernel<false, 16, 8, 8>;
+      else
+        kernel = injected ? cyber_step_tiled_kernel<true, 0, 0, 0> : cyber_step_tiled_kernel<false, 0, 0, 0>;
       if (layout.total > 48 * 1024 &&
           cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, layout.total) != cudaSuccess)
         return check_launch("cyber tile shared memory");

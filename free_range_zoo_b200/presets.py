@@ -301,6 +301,23 @@ def cyber_quirks(ns=None):
                   bad_action_penalty=-9.0)
 
 
+def cyber_synthetic(ns=None, nodes: int = 10, attackers: int = 5, defenders: int = 4, seed: int = 77):
+    """Parity-only: random graph / powers / presence dynamics of a given size (exercises the kernel's size classes)."""
+    gen = torch.Generator().manual_seed(seed)
+    rand = lambda n, lo, hi: (lo + (hi - lo) * torch.rand(n, generator=gen)).tolist()
+    adjacency = (torch.rand((nodes, nodes), generator=gen) < 0.4).int()
+    adjacency.fill_diagonal_(0)
+    adjacency[torch.arange(nodes), (torch.arange(nodes) + 1) % nodes] = 1  # every node has a neighbour
+    return _cyber(ns, threat=rand(attackers, 0.5, 2.5), mitigation=rand(defenders, 0.5, 2.5),
+                  att_presence=(torch.rand(attackers, generator=gen) < 0.7).tolist(),
+                  def_presence=(torch.rand(defenders, generator=gen) < 0.7).tolist(),
+                  def_location=torch.randint(-1, nodes, (defenders, ), generator=gen).tolist(),
+                  att_probs=(rand(attackers, 0.6, 0.95), rand(attackers, 0.3, 0.7)),
+                  def_probs=(rand(defenders, 0.6, 0.95), rand(defenders, 0.3, 0.7)), states=(2, 1, 2), temperature=1.75,
+                  initial_state=torch.randint(0, 5, (nodes, ), generator=gen).tolist(), adjacency=adjacency.tolist(),
+                  state_rewards=[2.0, 1.0, 0.0, -1.5, -3.0], stochastic=True, patch_reward=-0.25)
+
+
 PRESETS = SimpleNamespace(
     wildfire=dict(profile=wildfire_profile, c1=wildfire_3x3, c4=wildfire_large, quirks=wildfire_quirks),
     rideshare=dict(profile=rideshare_profile, c2=rideshare_c2, quirks=rideshare_quirks),

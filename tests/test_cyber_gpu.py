@@ -52,10 +52,14 @@ def legal_actions(oracle, rng):
     ('cyber_c3', 16384, 40, dict(show_bad_actions=False, partially_observable=True)),
     ('cyber_quirks', 5000, 30, dict(show_bad_actions=True, observe_other_location=True)),
     ('cyber_profile', 777, 12, {}),
+    # the kernel's other size classes: (16, 8, 8) tiled; runtime-loop tiled; too large for a tile -> direct kernel
+    (('cyber_synthetic', dict(nodes=10, attackers=5, defenders=4)), 1500, 20, dict(show_bad_actions=True)),
+    (('cyber_synthetic', dict(nodes=17, attackers=1, defenders=1)), 700, 20, dict(show_bad_actions=True)),
+    (('cyber_synthetic', dict(nodes=20, attackers=9, defenders=9)), 300, 15, dict(show_bad_actions=True)),
 ])
 def test_matches_oracle_on_random_rollouts(preset, B, steps, kwargs):
     from oracle.cybersecurity import CybersecurityOracle
-    config = getattr(presets, preset)()
+    config = getattr(presets, preset)() if isinstance(preset, str) else getattr(presets, preset[0])(**preset[1])
     oracle = CybersecurityOracle(config, B, steps, **kwargs)
     oracle.reset()
     env = make_env(config, B, steps, **kwargs)

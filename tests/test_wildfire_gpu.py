@@ -43,10 +43,16 @@ def test_matches_reference_trajectory(name):
     ('wildfire_quirks', 2048, 30, dict(show_bad_actions=True, observe_other_power=True)),
     ('wildfire_3x3', 4099, 40, {}),
     ('wildfire_profile', 1000, 15, {}),
+    # the kernel's other geometries: 2 and 8 cells per lane, rows of >= 32 cells (word-crossing neighbours), 20 agents
+    (('wildfire_large', dict(height=7, width=8, num_agents=5, seed=5)), 700, 20, {}),
+    (('wildfire_large', dict(height=12, width=16, num_agents=12, seed=6)), 300, 20, {}),
+    (('wildfire_large', dict(height=4, width=40, num_agents=6, seed=7)), 300, 20, {}),
+    (('wildfire_large', dict(height=3, width=33, num_agents=20, seed=8)), 300, 20, dict(show_bad_actions=True)),
+    (('wildfire_large', dict(height=2, width=100, num_agents=7, seed=9)), 200, 15, {}),
 ])
 def test_matches_oracle_on_random_rollouts(preset, B, steps, kwargs):
     from oracle.wildfire import WildfireOracle
-    config = getattr(presets, preset)()
+    config = getattr(presets, preset)() if isinstance(preset, str) else getattr(presets, preset[0])(**preset[1])
     oracle = WildfireOracle(config, B, steps, **kwargs)
     oracle.reset()
     env = make_env(config, B, steps, **kwargs)
