@@ -41,10 +41,11 @@ WORKLOADS = {
     'cyber_c3': dict(domain='cybersecurity', preset='cyber_c3', envs=16384,
                      kwargs=dict(show_bad_actions=False, partially_observable=True)),
 }
-KERNELS = {'wildfire': 'wildfire_step_kernel', 'rideshare': 'rideshare_step_kernel', 'cybersecurity': 'cyber_step_kernel'}
+KERNELS = {'wildfire': 'wildfire_step_kernel', 'rideshare': 'rideshare_step_kernel',
+           'cybersecurity': 'cyber_step_tiled_kernel'}
 
 
-def algorithmic_bytes(domain: str, raw) -> float:
+def algorithmic_bytes(domain: str, raw, present: float = 0.0) -> float:
     """ALGORITHMIC bytes per env-step (restated in DESIGN.md section 4): every live tensor read
     once and written once in the reference's dtypes, outputs written once, padded int32 observations, u8 masks."""
     if domain == 'wildfire':
@@ -56,8 +57,7 @@ def algorithmic_bytes(domain: str, raw) -> float:
         n = att + dfd
         state = 4 * N + 4 * dfd + n
         return 2 * state + 8 * n + 4 * n + 2 * n + 4 + (8 * att + 12 * dfd) + 8 * N + dfd + n
-    A, K = len(raw.agents), raw._capacity
-    present = float(raw.environment_task_count.float().mean().item())  # measured mean passengers per environment
+    A, K = len(raw.agents), raw._capacity  # `present` = measured mean passengers per environment over the timed steps
     return 2 * (8 * A + 44 * present) + 8 * A + 4 * A + 2 + 4 + 16 * A + 32 * present + A * K + 4 * (A + 1)
 
 
@@ -66,6 +66,16 @@ def measured_peak_gbs():
     if os.path.exists(path):
         return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(workload: str, parallel_envs: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one step-kernel launch, from the committed `ncu --set full`
+    capture of this workload (profiles/traffic.json, written by profiles/summarize.py); None when there is none."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(path):
+        return None
+    entry = json.load(open(path)).get(f'{workload}@{parallel_envs}')
+    return None if entry is None else entry['dram_bytes_per_launch']
 
 
 class ClockSampler:
@@ -276,20 +286,52 @@ def run_engine(args):
     graph_ms = max_over_ranks(start.elapsed_time(stop))
     value = world * B * K / (graph_ms * 1e-3)
 
-    # ---- (2) the step kernel alone: CUDA events around each launch on the launching stream
+    # ---- (2) the step kernel alone, CUDA events on the launching stream.  Two measurements:
+    #   eager:    an event pair around each frz_<domain>_step launch (includes the host's launch latency when the kernel
+    #             is shorter than a launch, i.e. for the small named batches)
+    #   in graph: R x [sample, step] captured in one CUDA graph minus R x [sample] -- back-to-back kernels, no host in
+    #             between; this is the duration the roofline fraction uses
     pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for _ in range(W):
         raw.sample_actions(SAMPLER)
         raw.step_environment()
     barrier()
+    tasks_seen = torch.zeros((), dtype=torch.float64, device=device)  # rideshare: passengers present, summed over steps
     for before, after in pairs:
         raw.sample_actions(SAMPLER)
         before.record()
         raw.step_environment()
         after.record()
+        tasks_seen += raw.environment_task_count.sum()
     barrier()
-    kernel_ms = sum(b.elapsed_time(a) for b, a in pairs) / K
-    bytes_per_env = algorithmic_bytes(domain, raw)
+    eager_ms = sum(b.elapsed_time(a) for b, a in pairs) / K
+    mean_tasks = float(tasks_seen.item()) / (K * B)
+    raw.check_errors()
+
+    def in_graph_ms(with_step: bool, repeats: int = 10) -> float:
+        env.reset(seed=SEED)
+        for _ in range(W):
+            raw.sample_actions(SAMPLER)
+            raw.step_environment()
+        torch.cuda.synchronize(device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(repeats):
+                raw.sample_actions(SAMPLER)
+                if with_step:
+                    raw.step_environment()
+        graph.replay()
+        torch.cuda.synchronize(device)
+        rounds = max(1, K // repeats)
+        start.record()
+        for _ in range(rounds):
+            graph.replay()
+        stop.record()
+        torch.cuda.synchronize(device)
+        return start.elapsed_time(stop) / (rounds * repeats)
+
+    kernel_ms = max(in_graph_ms(True) - in_graph_ms(False), 1e-6)
+    bytes_per_env = algorithmic_bytes(domain, raw, mean_tasks)
     peak, peak_kind = measured_peak_gbs()
     achieved = bytes_per_env * B / (kernel_ms * 1e-3) / 1e9
     raw.check_errors()
@@ -348,8 +390,10 @@ def run_engine(args):
             },
             'roofline': {
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_kind': peak_kind, 'kernel': KERNELS[domain], 'kernel_ms': kernel_ms,
-                'algorithmic_bytes_per_env_step': bytes_per_env,
+                'traffic': ncu_traffic(args.workload, B), 'peak_kind': peak_kind, 'kernel': KERNELS[domain],
+                'kernel_ms': kernel_ms, 'kernel_ms_eager_launch': eager_ms,
+                'algorithmic_bytes_per_launch': bytes_per_env * B, 'algorithmic_bytes_per_env_step': bytes_per_env,
+                'mean_tasks_per_env': mean_tasks,
             },
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_ms / K},

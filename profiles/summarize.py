@@ -94,8 +94,28 @@ def kernel(path: str, top: int) -> None:
         print(f'  {100 * inst / instructions:5.1f}% inst {100 * smp / samples:5.1f}% smp  {name}:{line:<4d} {text[:100]}')
 
 
+def traffic(path: str, key: str) -> None:
+    """Record the DRAM bytes of the first profiled launch under profiles/traffic.json[key] (key = workload@envs)."""
+    import json
+    import os
+    raw = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    header, units, row = rows[0], rows[1], rows[2]
+    scale = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}
+    total = sum(float(row[header.index(m)].replace(',', '')) * scale[units[header.index(m)]]
+                for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+    store = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'traffic.json')
+    data = json.load(open(store)) if os.path.exists(store) else {}
+    data[key] = {'dram_bytes_per_launch': total, 'report': os.path.basename(path),
+                 'kernel': row[header.index('Kernel Name')][:80]}
+    json.dump(data, open(store, 'w'), indent=1, sort_keys=True)
+    print(key, total)
+
+
 if __name__ == '__main__':
     if sys.argv[1] == 'launches':
         launches(sys.argv[2])
+    elif sys.argv[1] == 'traffic':
+        traffic(sys.argv[2], sys.argv[3])
     else:
         kernel(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 30)

@@ -65,7 +65,7 @@ def child(args):
         return start.elapsed_time(stop) / (5 * repeats)
 
     graph_us = 1e3 * (graph_time(True) - graph_time(False))
-    bytes_per_env = bench.algorithmic_bytes(spec['domain'], raw)
+    bytes_per_env = bench.algorithmic_bytes(spec['domain'], raw, float(raw.environment_task_count.float().mean().item()))
     peak, _ = bench.measured_peak_gbs()
     mean = sum(times) / len(times)
     checksum = float(raw._cumulative.double().sum().item())
