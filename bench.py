@@ -291,12 +291,18 @@ def run_engine(args):
     #             is shorter than a launch, i.e. for the small named batches)
     #   in graph: R x [sample, step] captured in one CUDA graph minus R x [sample] -- back-to-back kernels, no host in
     #             between; this is the duration the roofline fraction uses
+    # Every measurement covers the same window of the same seeded rollout: reset, W warm-up steps, K timed steps (the
+    # cost of a step follows the number of live tasks, which changes along a rollout).
+    def restart():
+        env.reset(seed=SEED)
+        for _ in range(W):
+            raw.sample_actions(SAMPLER)
+            raw.step_environment()
+        barrier()
+
     pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for _ in range(W):
-        raw.sample_actions(SAMPLER)
-        raw.step_environment()
-    barrier()
-    tasks_seen = torch.zeros((), dtype=torch.float64, device=device)  # rideshare: passengers present, summed over steps
+    restart()
+    tasks_seen = torch.zeros((), dtype=torch.float64, device=device)  # live tasks per environment, summed over steps
     for before, after in pairs:
         raw.sample_actions(SAMPLER)
         before.record()
@@ -308,11 +314,8 @@ def run_engine(args):
     mean_tasks = float(tasks_seen.item()) / (K * B)
     raw.check_errors()
 
-    def in_graph_ms(with_step: bool, repeats: int = 10) -> float:
-        env.reset(seed=SEED)
-        for _ in range(W):
-            raw.sample_actions(SAMPLER)
-            raw.step_environment()
+    def in_graph_ms(with_step: bool) -> float:
+        repeats = max(d for d in (10, 5, 4, 3, 2, 1) if K % d == 0)
         torch.cuda.synchronize(device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -320,15 +323,14 @@ def run_engine(args):
                 raw.sample_actions(SAMPLER)
                 if with_step:
                     raw.step_environment()
-        graph.replay()
-        torch.cuda.synchronize(device)
-        rounds = max(1, K // repeats)
+        graph.replay()  # first replay uploads the graph
+        restart()
         start.record()
-        for _ in range(rounds):
+        for _ in range(K // repeats):
             graph.replay()
         stop.record()
         torch.cuda.synchronize(device)
-        return start.elapsed_time(stop) / (rounds * repeats)
+        return start.elapsed_time(stop) / K
 
     kernel_ms = max(in_graph_ms(True) - in_graph_ms(False), 1e-6)
     bytes_per_env = algorithmic_bytes(domain, raw, mean_tasks)
