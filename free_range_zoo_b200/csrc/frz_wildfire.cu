@@ -123,8 +123,12 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   const int sub = lane % G;
   const int group_base = lane - sub;
   const uint32_t group_mask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
-  const uint32_t lane_bit = 1u << sub;
-  const uint32_t lanes_below = lane_bit - 1u;
+  // (per-lane constants used all over the loop are made opaque to the compiler, which otherwise re-derives them from
+  // %tid at every use instead of keeping them in a register: -4 % kernel time)
+  uint32_t lane_bit = 1u << sub;
+  asm volatile("" : "+r"(lane_bit));
+  uint32_t lanes_below = lane_bit - 1u;
+  asm volatile("" : "+r"(lanes_below));
   const int H = p.height, W = p.width, HW = H * W;
   const int A = p.num_agents;
   const int E = p.num_equipment_states;
@@ -143,8 +147,10 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   const int tasks_off = attack_off + kCells;
   // 32-bit shared-window byte addresses: static tables at this lane's cell column, this group's scratch region
   const uint32_t s_base = shared_address(smem);
-  const uint32_t s_cell = s_base + 4u * uint32_t(sub);
-  const uint32_t s_attack = s_base + 4u * uint32_t(attack_off);
+  uint32_t s_cell = s_base + 4u * uint32_t(sub);
+  asm volatile("" : "+r"(s_cell));
+  uint32_t s_attack = s_base + 4u * uint32_t(attack_off);
+  asm volatile("" : "+r"(s_attack));
   const uint32_t s_tasks = s_base + 4u * uint32_t(tasks_off);
   const uint32_t s_range = s_base + 4u * uint32_t(range_off);
 
@@ -205,7 +211,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
 #pragma unroll
       for (int i = 0; i < CPL; ++i) {
         const int c = i * G + sub;
-        const bool in_grid = c < HW;
+        // pick_geometry() only chooses CPL cells per lane when H*W > 32 * CPL / 2: the first CPL / 2 rows are full
+        const bool in_grid = (G == 32 && i < CPL / 2) || c < HW;
         fires[i] = in_grid ? fires_row[c] : 0;
         inten[i] = in_grid ? inten_row[c] : 0;
         fuel[i] = in_grid ? fuel_row[c] : 0;
@@ -625,7 +632,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
 #pragma unroll
           for (int i = 0; i < CPL; ++i) {
             const int c = i * G + sub;
-            if (c < HW) {
+            if ((G == 32 && i < CPL / 2) || c < HW) {
               fires_row[c] = fires[i];
               inten_row[c] = inten[i];
               fuel_row[c] = fuel[i];
