@@ -504,20 +504,25 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         uint32_t putw[NW];
 #pragma unroll
         for (int w = 0; w < NW; ++w) putw[w] = 0u;
-        if (__any_sync(kFullMask, (n_putout | n_burned) != 0)) {  // warp-uniform test
-          float my_put_reward = 0.f, my_burn_reward = 0.f;
+        const bool localize = flags & FRZ_WF_LOCALIZE_PUTOUTS, scaled = flags & FRZ_WF_BURNOUT_SCALED;
+        if (__any_sync(kFullMask, n_putout != 0) && !localize) {  // warp-uniform tests
+          float my_put_reward = 0.f;
 #pragma unroll
-          for (int i = 0; i < CPL; ++i) {
-            const bool put = (putout_bits >> i) & 1u, burned = (burned_bits >> i) & 1u;
-            if (put || burned) {
-              const float cell_reward = __uint_as_float(lds_const(s_cell + 4u * (kRewardOff + i * G)));
-              if (put) my_put_reward += cell_reward;
-              if (burned) my_burn_reward += cell_reward;
-            }
-            if (flags & FRZ_WF_LOCALIZE_PUTOUTS) putw[(G == 32) ? i : 0] = group_ballot<G>(put, group_base, group_mask);
-          }
-          if (!(flags & FRZ_WF_LOCALIZE_PUTOUTS)) put_total = group_sum<G>(my_put_reward);
-          if (flags & FRZ_WF_BURNOUT_SCALED) burn_total = group_sum<G>(my_burn_reward);
+          for (int i = 0; i < CPL; ++i)
+            if ((putout_bits >> i) & 1u) my_put_reward += __uint_as_float(lds_const(s_cell + 4u * (kRewardOff + i * G)));
+          put_total = group_sum<G>(my_put_reward);
+        }
+        if (__any_sync(kFullMask, n_putout != 0) && localize) {
+#pragma unroll
+          for (int i = 0; i < CPL; ++i)
+            putw[(G == 32) ? i : 0] = group_ballot<G>((putout_bits >> i) & 1u, group_base, group_mask);
+        }
+        if (__any_sync(kFullMask, n_burned != 0) && scaled) {
+          float my_burn_reward = 0.f;
+#pragma unroll
+          for (int i = 0; i < CPL; ++i)
+            if ((burned_bits >> i) & 1u) my_burn_reward += __uint_as_float(lds_const(s_cell + 4u * (kRewardOff + i * G)));
+          burn_total = group_sum<G>(my_burn_reward);
         }
         const float penalty_total =
             (flags & FRZ_WF_BURNOUT_SCALED) ? -burn_total : __fmul_rn(p.burnout_penalty, float(n_burned));
