@@ -194,10 +194,38 @@ class raw_env(BatchedAECEnv):
         self._actions.fill_(-2)  # cybersecurity.py:233-236
         self._reset_masked(None)
         self._rebind_outputs()
+        if self.log_directory is not None:
+            self._log_environment(reset=True)
 
     def _reset_masked(self, mask: Optional[torch.Tensor]) -> None:
         _lib.check(self._lib.frz_cyber_reset(ctypes.byref(self._params), ctypes.byref(self._io), self.parallel_envs,
                                              _lib.pointer(mask), self._stream()), 'frz_cyber_reset')
+
+    # ------------------------------------------------------------------------------------------ logging tap
+
+    def _log_snapshot(self) -> Dict[str, torch.Tensor]:
+        s = self._state
+        return dict(super()._log_snapshot(), network_state=s.network_state, location=s.location, presence=self._presence)
+
+    def _log_state_columns(self, host) -> Dict[str, Any]:
+        """CybersecurityState.to_dataframe (utils/state.py:180-191): network state, defender locations, presence."""
+        from free_range_zoo_b200.utils.logging_tap import nested
+        B = self.parallel_envs
+        return {'network_state': [nested(host['network_state'][b]) for b in range(B)],
+                'location': [nested(host['location'][b]) for b in range(B)],
+                'presence': [nested(host['presence'][b] != 0) for b in range(B)]}
+
+    def _log_mappings(self, host, agent_index: int):
+        """cybersecurity.py:428-457: a present agent may act on every node, an absent one on none; the observation
+        mapping is the full node range wrapped in one more list (it is a [1, N] slice of a nested tensor)."""
+        nodes = list(range(self._n_nodes))
+        present = host['agent_task_count'][:, agent_index] > 0
+        return [str(nodes if here else []) for here in present], [str([nodes])] * self.parallel_envs
+
+    def _log_extra_columns(self, host, reset: bool) -> Dict[str, Any]:
+        """cybersecurity.py:580-584: the adjacency matrix on every row."""
+        adjacency = str(torch.as_tensor(self.network_config.adj_matrix).int().tolist())
+        return {'adj_matrix': [adjacency] * self.parallel_envs}
 
     # ------------------------------------------------------------------------------------------ step
 

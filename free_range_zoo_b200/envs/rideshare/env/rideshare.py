@@ -167,6 +167,8 @@ class raw_env(BatchedAECEnv):
             self._init_agents.copy_(starts.unsqueeze(0).expand_as(self._init_agents))
         self._reset_masked(None)
         self._rebind_outputs()
+        if self.log_directory is not None:
+            self._log_environment(reset=True)
 
     def _reset_masked(self, mask: Optional[torch.Tensor]) -> None:
         _lib.check(self._lib.frz_rideshare_reset(ctypes.byref(self._params), ctypes.byref(self._io), self.parallel_envs,
@@ -197,6 +199,26 @@ class raw_env(BatchedAECEnv):
                                                           self.parallel_envs, ctypes.c_uint64(sampler_seed),
                                                           self._stream()), 'frz_rideshare_sample_actions')
         return self._actions
+
+    # ------------------------------------------------------------------------------------------ logging tap
+
+    def _log_snapshot(self) -> Dict[str, torch.Tensor]:
+        return dict(super()._log_snapshot(), agents=self._state.agents, passengers=self._state.passenger_table,
+                    task_mask=self._task_mask)
+
+    def _log_state_columns(self, host) -> Dict[str, Any]:
+        """RideshareState.to_dataframe (envs/rideshare/env/structures/state.py:50-66): driver positions, then the rows of
+        the passenger table that belong to the environment (with their batch column)."""
+        from free_range_zoo_b200.utils.logging_tap import nested
+        B = self.parallel_envs
+        counts = host['env_task_count']
+        return {'agents': [nested(host['agents'][b]) for b in range(B)],
+                'passengers': [nested(host['passengers'][b, :counts[b]]) for b in range(B)]}
+
+    def _log_mappings(self, host, agent_index: int):
+        from free_range_zoo_b200.utils.logging_tap import index_list
+        cells = [index_list(row) for row in host['task_mask'][:, agent_index] != 0]
+        return cells, cells  # rideshare.py:394-395: the observation mapping is the action mapping
 
     # ------------------------------------------------------------------------------------------ views
 

@@ -259,6 +259,8 @@ class raw_env(BatchedAECEnv):
         self._reset_masked(None)
         self.infos = dict({agent: {} for agent in self.agents}, burnouts=self._burnouts, putouts=self._putouts)
         self._rebind_outputs()
+        if self.log_directory is not None:
+            self._log_environment(reset=True)
 
     def _reset_masked(self, mask: Optional[torch.Tensor]) -> None:
         """frz_wildfire_reset: restore initial rows, zero AEC fields (+ num_burnouts, wildfire.py:393), refresh."""
@@ -298,6 +300,37 @@ class raw_env(BatchedAECEnv):
                                                          self.parallel_envs, ctypes.c_uint64(sampler_seed),
                                                          self._stream()), 'frz_wildfire_sample_actions')
         return self._actions
+
+    # ------------------------------------------------------------------------------------------ logging tap
+
+    def _log_snapshot(self) -> Dict[str, torch.Tensor]:
+        s = self._state
+        return dict(super()._log_snapshot(), fires=s.fires, intensity=s.intensity, fuel=s.fuel,
+                    suppressants=s.suppressants, capacity=s.capacity, equipment=s.equipment,
+                    action_mask=self._action_mask, burnouts=self._burnouts, putouts=self._putouts)
+
+    def _log_state_columns(self, host) -> Dict[str, Any]:
+        """WildfireState.to_dataframe (utils/state.py:180-191): per-env cells, the shared agent positions last."""
+        from free_range_zoo_b200.utils.logging_tap import nested
+        B = self.parallel_envs
+        columns = {name: [nested(host[name][b]) for b in range(B)]
+                   for name in ('fires', 'intensity', 'fuel', 'suppressants', 'capacity', 'equipment')}
+        columns['agents'] = [str(torch.as_tensor(self.agent_config.agents).tolist())] * B
+        return columns
+
+    def _log_mappings(self, host, agent_index: int):
+        """(action map, observation map) cells: env-local task indices the agent may act on / observes."""
+        from free_range_zoo_b200.utils.logging_tap import index_list
+        counts = host['env_task_count']
+        slots = np.arange(host['action_mask'].shape[2])[None, :] < counts[:, None]
+        allowed = slots if self.show_bad_actions else (host['action_mask'][:, agent_index] != 0) & slots
+        return [index_list(row) for row in allowed], [index_list(row) for row in slots]
+
+    def _log_extra_columns(self, host, reset: bool) -> Dict[str, Any]:
+        """wildfire.py:755-762: the per-step burn-out / put-out counters (absent from infos right after a reset)."""
+        B = self.parallel_envs
+        return {'burnouts': [None] * B if reset else host['burnouts'].tolist(),
+                'putouts': [None] * B if reset else host['putouts'].tolist()}
 
     # ------------------------------------------------------------------------------------------ views
 

@@ -85,13 +85,14 @@ class BatchedAECEnv(ABC):
                                'there is no CPU fallback -- use the reference implementation on CPU.')
         if device.index is None:
             device = torch.device('cuda', torch.cuda.current_device())
-        if log_directory is not None:
-            raise NotImplementedError('CSV / SQL logging is outside the B200 step engine; pass log_directory=None')
+        if log_directory is not None and str(log_directory).startswith(('sqlite', 'postgres', 'mysql')):
+            raise NotImplementedError('only the CSV log format is implemented by the asynchronous logging tap')
         self.parallel_envs = int(parallel_envs)
         self.max_steps = max_steps
         self.device = device
         self.render_mode = render_mode
-        self.log_directory = None
+        self.log_directory = log_directory
+        self.override_initialization_check = override_initialization_check
         self.single_seeding = single_seeding
         self.log_description = None
         self.logger = None
@@ -106,6 +107,7 @@ class BatchedAECEnv(ABC):
                     setattr(self, key, value)
 
         self._lib = _lib.library()
+        self._tap = None  # asynchronous CSV logging (utils/logging_tap.py), created by the first reset
         self._control = torch.zeros(8, dtype=torch.int64, device=self.device)  # FrzControl, 64 bytes
         self._seed_value = None
         self._graph = None
@@ -265,6 +267,59 @@ class BatchedAECEnv(ABC):
         self.infos = infos
         self._mid_cycle = False
         self._rebind_outputs()
+        if self.log_directory is not None:
+            self._log_environment()
+
+    # ------------------------------------------------------------------------------------------ logging tap
+
+    def _log_environment(self, reset: bool = False) -> None:
+        """Queue one CSV row per environment (reference utils/env.py:256-271 -> CSVLogger); nothing here waits for the
+        device: see utils/logging_tap.py."""
+        if self._tap is None:
+            from free_range_zoo_b200.utils.logging_tap import LoggingTap
+            self._tap = LoggingTap(self.log_directory, self.parallel_envs, self.device, self._log_snapshot,
+                                   self._log_columns,
+                                   override_initialization_check=self.override_initialization_check)
+        self._tap.capture(reset, self.log_description)
+
+    def flush_logs(self) -> None:
+        """Wait until every queued log row is on disk."""
+        if self._tap is not None:
+            self._tap.flush()
+
+    def _log_snapshot(self) -> Dict[str, torch.Tensor]:
+        """Live device tensors the log rows are built from (domain tensors are added by the subclasses)."""
+        return dict(actions=self._actions, rewards=self._rewards, num_moves=self.num_moves, terminated=self._terminated,
+                    truncated=self._truncated, env_task_count=self.environment_task_count,
+                    agent_task_count=self._agent_task_count)
+
+    def _log_columns(self, host: Dict[str, Any], reset: bool) -> Dict[str, Any]:
+        """Ordered CSV columns from the host copy of a snapshot: state columns, the per-agent action / reward columns,
+        step, complete, the per-agent mappings, then the domain's extra columns (logging_handlers.py:77-100)."""
+        from free_range_zoo_b200.utils.logging_tap import nested
+        B = self.parallel_envs
+        columns = dict(self._log_state_columns(host))
+        finished = (host['terminated'] != 0) | (host['truncated'] != 0)
+        for index, agent in enumerate(self.possible_agents):
+            columns[f'{agent}_action'] = [None] * B if reset else [nested(host['actions'][b, index]) for b in range(B)]
+            columns[f'{agent}_rewards'] = [None] * B if reset else host['rewards'][:, index].astype(float).tolist()
+        columns['step'] = [-1] * B if reset else host['num_moves'].tolist()
+        columns['complete'] = [None] * B if reset else finished.tolist()
+        for index, agent in enumerate(self.possible_agents):
+            action_map, observation_map = self._log_mappings(host, index)
+            columns[f'{agent}_action_map'] = action_map
+            columns[f'{agent}_observation_map'] = observation_map
+        columns.update(self._log_extra_columns(host, reset))
+        return columns
+
+    def _log_state_columns(self, host) -> Dict[str, Any]:
+        raise NotImplementedError
+
+    def _log_mappings(self, host, agent_index: int):
+        raise NotImplementedError
+
+    def _log_extra_columns(self, host, reset: bool) -> Dict[str, Any]:
+        return {}
 
     def _rebind_outputs(self) -> None:
         """Re-create the lazily evaluated observation views after the device buffers changed."""

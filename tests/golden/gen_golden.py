@@ -236,11 +236,11 @@ def rideshare_actions(raw, gen, wild):
     return acts
 
 
-def gen_rideshare(name, preset, B, steps, seed, wild=0.0, preset_kwargs=None):
+def gen_rideshare(name, preset, B, steps, seed, wild=0.0, preset_kwargs=None, **env_kwargs):
     config = preset(ref_rs_conf, **(preset_kwargs or {}))
     K = int(config.passenger_config.schedule.shape[0])
     env = rideshare_v0.parallel_env(parallel_envs=B, max_steps=steps, configuration=config, device=torch.device('cpu'),
-                                    single_seeding=True)
+                                    single_seeding=True, **env_kwargs)
     env.reset(seed=seed)
     raw = ref_shim.raw(env)
     recorder = UniformRecorder(seed + 1)
