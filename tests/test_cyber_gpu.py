@@ -52,6 +52,8 @@ def legal_actions(oracle, rng):
     ('cyber_c3', 16384, 40, dict(show_bad_actions=False, partially_observable=True)),
     ('cyber_quirks', 5000, 30, dict(show_bad_actions=True, observe_other_location=True)),
     ('cyber_profile', 777, 12, {}),
+    ('cyber_c3', 1, 10, dict(show_bad_actions=False, partially_observable=True)),  # a single environment
+    ('cyber_c3', 129, 10, dict(show_bad_actions=False, partially_observable=True)),  # one full tile + 1
     # the kernel's other size classes: (16, 8, 8) tiled; runtime-loop tiled; too large for a tile -> direct kernel
     (('cyber_synthetic', dict(nodes=10, attackers=5, defenders=4)), 1500, 20, dict(show_bad_actions=True)),
     (('cyber_synthetic', dict(nodes=17, attackers=1, defenders=1)), 700, 20, dict(show_bad_actions=True)),

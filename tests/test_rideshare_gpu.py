@@ -56,6 +56,7 @@ def policy_actions(oracle, rng, wild):
     ('rideshare_quirks', dict(parallel_envs=200), 200, 40, 0.2),
     ('rideshare_quirks', dict(parallel_envs=128, diagonal=False, fast=True), 128, 40, 0.1),
     ('rideshare_profile', {}, 100, 20, 0.0),
+    ('rideshare_c2', {}, 1, 30, 0.0),  # a single environment
     ('rideshare_c2', dict(rows=48, horizon=30), 150, 50, 0.2),  # more than 32 rows per table: two rows per lane
     ('rideshare_c2', dict(rows=61, horizon=20), 100, 40, 0.2),  # ... and a row count that is not a multiple of 4
 ])

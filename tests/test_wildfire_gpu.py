@@ -43,6 +43,8 @@ def test_matches_reference_trajectory(name):
     ('wildfire_quirks', 2048, 30, dict(show_bad_actions=True, observe_other_power=True)),
     ('wildfire_3x3', 4099, 40, {}),
     ('wildfire_profile', 1000, 15, {}),
+    ('wildfire_large', 1, 10, {}),  # a single environment
+    ('wildfire_3x3', 3, 12, {}),  # fewer environments than one warp holds
     # the kernel's other geometries: 2 and 8 cells per lane, rows of >= 32 cells (word-crossing neighbours), 20 agents
     (('wildfire_large', dict(height=7, width=8, num_agents=5, seed=5)), 700, 20, {}),
     (('wildfire_large', dict(height=12, width=16, num_agents=12, seed=6)), 300, 20, {}),
@@ -185,3 +187,23 @@ def test_partial_reset_restores_selected_envs():
     assert (raw._cumulative[picked] == 0).all() and (raw.num_burnouts[picked] == 0).all()
     lit = (raw.state().fires > 0).flatten(1).sum(1).int()
     assert torch.equal(lit, raw.environment_task_count)
+
+
+def test_action_mapping_wrapper_returns_the_reference_mappings():
+    """wrappers/action_task.py: observations come back as (observation, {'agent_action_mapping': jagged indices});
+    the mappings equal the reference's recorded ones on a golden trajectory."""
+    from free_range_zoo_b200.wrappers import action_mapping_wrapper_v0
+    meta, gold = G.load('wildfire_c4')
+    env = action_mapping_wrapper_v0(make_env(getattr(presets, meta['preset'])(), meta['B'], meta['max_steps'], **meta['env_kwargs']))
+    observations, _ = env.reset(seed=0)
+    agents = env.agents
+    for t in range(3):
+        for i, agent in enumerate(agents):
+            observation, extra = observations[agent]
+            mapping = extra['agent_action_mapping'].to_padded_tensor(-100).cpu().numpy()
+            want = gold['action_map'][t][i]
+            assert np.array_equal(mapping, want[:, :mapping.shape[1]]) and (want[:, mapping.shape[1]:] == -100).all()
+            assert observation['self'].shape == (meta['B'], 4)
+        env.unwrapped.inject_uniforms(torch.from_numpy(gold['u_field'][t]), torch.from_numpy(gold['u_agent'][t]))
+        actions = torch.from_numpy(gold['actions'][t]).cuda()
+        observations, _, _, _, _ = env.step({a: actions[:, i] for i, a in enumerate(agents)})
