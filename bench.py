@@ -38,6 +38,11 @@ WORKLOADS = {
     'wildfire_c4': dict(domain='wildfire', preset='wildfire_large', envs=65536, kwargs={}),
     'wildfire_c1': dict(domain='wildfire', preset='wildfire_3x3', envs=1024, kwargs={}),
     'rideshare_c2': dict(domain='rideshare', preset='rideshare_c2', envs=16384, kwargs={}),
+    # extra wildfire geometries (kernel tuning; not named by BASELINE.json)
+    'wildfire_5x6': dict(domain='wildfire', preset='wildfire_large', envs=262144, kwargs={},
+                         preset_kwargs=dict(height=5, width=6, num_agents=6, seed=21)),
+    'wildfire_7x8': dict(domain='wildfire', preset='wildfire_large', envs=262144, kwargs={},
+                         preset_kwargs=dict(height=7, width=8, num_agents=5, seed=5)),
     'cyber_c3': dict(domain='cybersecurity', preset='cyber_c3', envs=16384,
                      kwargs=dict(show_bad_actions=False, partially_observable=True)),
 }
@@ -131,7 +136,7 @@ def _oracle_rollout(job):
 
     from free_range_zoo_b200 import presets
     spec = WORKLOADS[workload]
-    config = getattr(presets, spec['preset'])()
+    config = getattr(presets, spec['preset'])(**spec.get('preset_kwargs', {}))
     rng = np.random.default_rng(seed)
     if spec['domain'] == 'wildfire':
         from oracle.wildfire import WildfireOracle
@@ -248,7 +253,7 @@ def run_engine(args):
     spec = WORKLOADS[args.workload]
     domain = spec['domain']
     B = args.parallel_envs or spec['envs']
-    config = getattr(presets, spec['preset'])()
+    config = getattr(presets, spec['preset'])(**spec.get('preset_kwargs', {}))
     module = importlib.import_module(f'free_range_zoo_b200.envs.{domain}_v0')
     env = module.parallel_env(parallel_envs=B, max_steps=1 << 30, configuration=config, device=device,
                               env_offset=rank * B, **spec['kwargs'])

@@ -74,6 +74,24 @@ __host__ __device__ inline int static_smem_words(int cells, int agents, int stat
   return 4 * cells + states * cells + agents * states * words;
 }
 
+// Row ballots -> the group's bit words (bit c = cell c).  Row i of a group holds cells i*G .. i*G+G-1, so 32 / G rows
+// share one word: for 32-lane groups a row IS a word; for 16-lane groups the group's halfword of two consecutive row
+// ballots is packed with one byte permute; one-row groups just shift their lanes down.
+template <int G, int CPL, int NW>
+__device__ __forceinline__ void assemble_words(const uint32_t (&rows)[CPL], uint32_t (&words)[NW], int group_base,
+                                               uint32_t group_mask, uint32_t half_selector) {
+  if constexpr (G == 32) {
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) words[i] = rows[i];
+  } else if constexpr (CPL == 1) {
+    words[0] = (rows[0] >> group_base) & group_mask;
+  } else {
+    static_assert(G == 16, "multi-row sub-warp groups are 16 lanes wide");
+#pragma unroll
+    for (int w = 0; w < NW; ++w) words[w] = __byte_perm(rows[2 * w], (2 * w + 1 < CPL) ? rows[(2 * w + 1 < CPL) ? 2 * w + 1 : 0] : 0u, half_selector);
+  }
+}
+
 // the NW range-mask words of one (agent, equipment state) row; one 16-byte load when the row is four words
 template <int NW>
 __device__ __forceinline__ void load_range_words(uint32_t address, uint32_t (&words)[NW]) {
@@ -113,7 +131,10 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   // Philox words per lane: two per cell (a cell consumes either its fire-increase or its fire-decrease draw, never
   // both, so the two events share a word; the other word is the spread draw) and four per agent
   constexpr int kCalls = (2 * CPL + 3) / 4;
-  static_assert(G == 32 || CPL == 1, "sub-warp groups hold one cell per lane");
+  static_assert(G == 32 || G == 16 || CPL == 1, "8-lane groups hold one cell per lane");
+  constexpr int RPW = (CPL == 1) ? 1 : 32 / G;  // grid rows (of G cells) per 32-bit word
+  // rows that the geometry choice guarantees to lie entirely inside the grid (pick_geometry())
+  constexpr int kFullRows = (G == 32) ? CPL / 2 : (CPL - 1);
   extern __shared__ __align__(16) uint32_t smem[];
 
   const int lane = threadIdx.x & 31;
@@ -127,8 +148,9 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   // %tid at every use instead of keeping them in a register: -4 % kernel time)
   uint32_t lane_bit = 1u << sub;
   asm volatile("" : "+r"(lane_bit));
-  uint32_t lanes_below = lane_bit - 1u;
-  asm volatile("" : "+r"(lanes_below));
+  // this lane's cell of row i is bit (i % RPW) * G + sub of word i / RPW
+  const auto row_bit = [&](int i) { return lane_bit << ((i % RPW) * G); };
+  const uint32_t half_selector = (group_base & 16) ? 0x7632u : 0x5410u;
   const int H = p.height, W = p.width, HW = H * W;
   const int A = p.num_agents;
   const int E = p.num_equipment_states;
@@ -212,7 +234,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       for (int i = 0; i < CPL; ++i) {
         const int c = i * G + sub;
         // pick_geometry() only chooses CPL cells per lane when H*W > 32 * CPL / 2: the first CPL / 2 rows are full
-        const bool in_grid = (G == 32 && i < CPL / 2) || c < HW;
+        const bool in_grid = i < kFullRows || c < HW;
         fires[i] = in_grid ? fires_row[c] : 0;
         inten[i] = in_grid ? inten_row[c] : 0;
         fuel[i] = in_grid ? fuel_row[c] : 0;
@@ -225,13 +247,13 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         equip = min(max(io.equipment[agent_at], 0), E - 1);
       }
 
-      uint32_t litw[NW];
+      uint32_t litw[NW], rows[CPL];
       int n_before = 0;  // tasks published by the previous launch: rows / mask bytes beyond are already padding
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) {
-        litw[(G == 32) ? i : 0] = group_ballot<G>(fires[i] > 0, group_base, group_mask);
-        n_before += __popc(litw[(G == 32) ? i : 0]);
-      }
+      for (int i = 0; i < CPL; ++i) rows[i] = __ballot_sync(kFullMask, fires[i] > 0);
+      assemble_words<G, CPL, NW>(rows, litw, group_base, group_mask, half_selector);
+#pragma unroll
+      for (int w = 0; w < NW; ++w) n_before += __popc(litw[w]);
       if (mode != kStep) n_before = HW;  // refresh / reset: (re)write every row
 
       float reward = 0.f, cumulative = 0.f;
@@ -350,15 +372,27 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           if (!inject_agent) {
             uint32_t words[4];
             bool have_words = false;
-            if constexpr (G == 32 && CPL == 4) {
-              // lanes whose fourth cell lies outside the grid never use their last two words: agent a takes the pairs
-              // of lanes 31 - a and 31 - A - a (the host checked that those lanes exist for this grid)
+            // Words this lane never consumes: 4 * kCalls - 2 * CPL at the end of its last call (kSpareOwn: 0 or 2), and
+            // the two words of its last cell when that cell lies outside the grid ("spare lanes": the top lanes of the
+            // group).  When the host found enough spare lanes for this grid, the agents' four words come from there
+            // instead of from a Philox call of their own.
+            constexpr int kSpareOwn = 4 * kCalls - 2 * CPL;
+            if constexpr (CPL > 1) {
               if (derived.spare_lanes_feed_agents) {
-                const int first = (31 - sub) & 31, second = (31 - A - sub) & 31;
-                words[0] = __shfl_sync(kFullMask, bits[6], first);
-                words[1] = __shfl_sync(kFullMask, bits[7], first);
-                words[2] = __shfl_sync(kFullMask, bits[6], second);
-                words[3] = __shfl_sync(kFullMask, bits[7], second);
+                const int first = group_base + ((G - 1 - sub) & (G - 1)), second = group_base + ((G - 1 - A - sub) & (G - 1));
+                const uint32_t a = __shfl_sync(kFullMask, bits[2 * CPL - 2], first);
+                const uint32_t b = __shfl_sync(kFullMask, bits[2 * CPL - 1], first);
+                if constexpr (kSpareOwn == 2) {
+                  words[0] = bits[2 * CPL];
+                  words[1] = bits[2 * CPL + 1];
+                  words[2] = a;
+                  words[3] = b;
+                } else {
+                  words[0] = a;
+                  words[1] = b;
+                  words[2] = __shfl_sync(kFullMask, bits[2 * CPL - 2], second);
+                  words[3] = __shfl_sync(kFullMask, bits[2 * CPL - 1], second);
+                }
                 have_words = true;
               }
             }
@@ -439,8 +473,9 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           putout_bits |= uint32_t(put) << i;
           fires[i] = f;
           inten[i] = it;
-          burnw[(G == 32) ? i : 0] = group_ballot<G>(burning && !burned && !put, group_base, group_mask);
+          rows[i] = __ballot_sync(kFullMask, burning && !burned && !put);
         }
+        assemble_words<G, CPL, NW>(rows, burnw, group_base, group_mask, half_selector);
         // the agents that scattered an attack clear it again: the table is all zero between environments
         __syncwarp();
         if (user) sts(s_attack + 4u * uint32_t(target), 0u);
@@ -452,9 +487,11 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           const bool unlit = f < 0 && it == 0 && (!use_fuel || fuel[i] > 0);
           if (__any_sync(kFullMask, unlit)) {
             // burning neighbours of cell c as bit c of four words: N = cell c-W, W = c-1, E = c+1, S = c+W
-            const uint32_t cur = burnw[(G == 32) ? i : 0];
-            const uint32_t prev = (G == 32 && i > 0) ? burnw[(G == 32 && i > 0) ? i - 1 : 0] : 0u;
-            const uint32_t next = (G == 32 && i + 1 < NW) ? burnw[(G == 32 && i + 1 < NW) ? i + 1 : 0] : 0u;
+            const int w = i / RPW;  // the word holding this row
+            const uint32_t cur = burnw[w];
+            const uint32_t prev = w > 0 ? burnw[w > 0 ? w - 1 : 0] : 0u;
+            const uint32_t next = w + 1 < NW ? burnw[w + 1 < NW ? w + 1 : 0] : 0u;
+            const uint32_t my_bit = row_bit(i);
             uint32_t north, south;
             if (W < 32) {
               north = __funnelshift_l(prev, cur, W);
@@ -464,22 +501,22 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
               south = 0u;
               const int q = W >> 5, r = W & 31;
 #pragma unroll
-              for (int w = 0; w < NW; ++w) {
-                if (w == i - q) north |= r ? (burnw[w] << r) : burnw[w];
-                if (r && w == i - q - 1) north |= burnw[w] >> (32 - r);
-                if (w == i + q) south |= r ? (burnw[w] >> r) : burnw[w];
-                if (r && w == i + q + 1) south |= burnw[w] << (32 - r);
+              for (int v = 0; v < NW; ++v) {
+                if (v == w - q) north |= r ? (burnw[v] << r) : burnw[v];
+                if (r && v == w - q - 1) north |= burnw[v] >> (32 - r);
+                if (v == w + q) south |= r ? (burnw[v] >> r) : burnw[v];
+                if (r && v == w + q + 1) south |= burnw[v] << (32 - r);
               }
             }
-            const uint32_t west = __funnelshift_l(prev, cur, 1) & derived.west_ok[(G == 32) ? i : 0];
-            const uint32_t east = __funnelshift_r(cur, next, 1) & derived.east_ok[(G == 32) ? i : 0];
+            const uint32_t west = __funnelshift_l(prev, cur, 1) & derived.west_ok[w];
+            const uint32_t east = __funnelshift_r(cur, next, 1) & derived.east_ok[w];
             // the conv sum in the reference's accumulation order N, W, E, S, starting from zero (spread_lut[1 << k] is
             // the weight of direction k; see spread_lut() on the host for the order)
             float prob = 0.f;
-            if (north & lane_bit) prob = p.spread_lut[1];
-            if (west & lane_bit) prob = __fadd_rn(prob, p.spread_lut[2]);
-            if (east & lane_bit) prob = __fadd_rn(prob, p.spread_lut[4]);
-            if (south & lane_bit) prob = __fadd_rn(prob, p.spread_lut[8]);
+            if (north & my_bit) prob = p.spread_lut[1];
+            if (west & my_bit) prob = __fadd_rn(prob, p.spread_lut[2]);
+            if (east & my_bit) prob = __fadd_rn(prob, p.spread_lut[4]);
+            if (south & my_bit) prob = __fadd_rn(prob, p.spread_lut[8]);
             prob = __fadd_rn(prob, p.p_random_ignition);
             if (unlit && uf[3 * i + 2] < prob) {
               f = -f;
@@ -488,8 +525,9 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           }
           fires[i] = f;
           inten[i] = it;
-          litw[(G == 32) ? i : 0] = group_ballot<G>(f > 0, group_base, group_mask);
+          rows[i] = __ballot_sync(kFullMask, f > 0);
         }
+        assemble_words<G, CPL, NW>(rows, litw, group_base, group_mask, half_selector);
 
         // ---------------------------------------------------------------- rewards + termination (wildfire.py:534-582)
         // burn-outs and put-outs are rare: count them with one reduction each and only then look at which cells
@@ -514,8 +552,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         }
         if (__any_sync(kFullMask, n_putout != 0) && localize) {
 #pragma unroll
-          for (int i = 0; i < CPL; ++i)
-            putw[(G == 32) ? i : 0] = group_ballot<G>((putout_bits >> i) & 1u, group_base, group_mask);
+          for (int i = 0; i < CPL; ++i) rows[i] = __ballot_sync(kFullMask, (putout_bits >> i) & 1u);
+          assemble_words<G, CPL, NW>(rows, putw, group_base, group_mask, half_selector);
         }
         if (__any_sync(kFullMask, n_burned != 0) && scaled) {
           float my_burn_reward = 0.f;
@@ -534,7 +572,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           int my_fuel = 0;
 #pragma unroll
           for (int i = 0; i < CPL; ++i) my_fuel += fuel[i];
-          dead = dead && group_sum<G>(my_fuel) <= 0;
+          const int fuel_left = group_sum<G>(my_fuel);  // every lane takes part: no short-circuit around the shuffles
+          dead = dead && fuel_left <= 0;
         }
         if (dead) {  // wildfire.py:570
 #pragma unroll
@@ -586,18 +625,18 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       }
       int4* const task_rows = reinterpret_cast<int4*>(io.task_obs);
       {
-        int rank = 0;
+        int rank = 0;  // lit cells in the words before the current one
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
-          const uint32_t word = litw[(G == 32) ? i : 0];
-          if (word & lane_bit) {
-            const int t = rank + __popc(word & lanes_below);  // env-local task index = rank in row-major lit order
+          const uint32_t word = litw[i / RPW], my_bit = row_bit(i);
+          if (i > 0 && i % RPW == 0) rank += __popc(litw[i > 0 ? i / RPW - 1 : 0]);
+          if (word & my_bit) {
+            const int t = rank + __popc(word & (my_bit - 1u));  // env-local task index = rank in row-major lit order
             sts(s_tasks + 4u * uint32_t(t), fighters[i]);
             if (valid)
               task_rows[cell_row + uint32_t(t)] = make_int4(int(lds_const(s_cell + 4u * (kYOff + i * G))), int(lds_const(s_cell + 4u * (kXOff + i * G))),
                                       fires[i], inten[i]);
           }
-          rank += __popc(word);
         }
       }
       // tasks of the previous launch that no longer exist: their rows go back to padding, their mask bytes to zero
@@ -637,7 +676,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
 #pragma unroll
           for (int i = 0; i < CPL; ++i) {
             const int c = i * G + sub;
-            if ((G == 32 && i < CPL / 2) || c < HW) {
+            if (i < kFullRows || c < HW) {
               fires_row[c] = fires[i];
               inten_row[c] = inten[i];
               fuel_row[c] = fuel[i];
@@ -720,6 +759,13 @@ __global__ void wildfire_sample_kernel(const FrzWildfireParams p, const FrzWildf
   }
 }
 
+// Largest grid (in cells) that is stepped by half-warp groups.  Measured on B200 at 262 144 envs: 5x6 / 6 agents 269 us
+// -> 178 us and 7x8 / 5 agents 310 -> 245 us with half-warp groups, but 10x10 / 10 agents (7 cells per lane, register
+// spills at 80 registers) 115 -> 124 us: beyond 4 cells per lane the 32-lane geometry wins.
+#ifndef FRZ_WF_HALF_WARP_CELLS
+#define FRZ_WF_HALF_WARP_CELLS 64
+#endif
+
 struct Geometry {
   int group, cells_per_lane;
 };
@@ -727,8 +773,11 @@ struct Geometry {
 bool pick_geometry(const FrzWildfireParams& p, Geometry* g) {
   const int HW = p.height * p.width, A = p.num_agents;
   if (A < 1 || A > FRZ_MAX_AGENTS || HW < 1 || HW > FRZ_MAX_CELLS) return false;
+  // Half-warp groups for small and mid-size grids whose agents fit 16 lanes: two environments share every instruction
+  // of the agent phase, and ceil(H*W / 16) cells per lane waste fewer lanes than a power-of-two count over 32 lanes.
   if (HW <= 8 && A <= 8) *g = {8, 1};
   else if (HW <= 16 && A <= 16) *g = {16, 1};
+  else if (HW <= FRZ_WF_HALF_WARP_CELLS && A <= 16) *g = {16, (HW + 15) / 16};
   else if (HW <= 32) *g = {32, 1};
   else if (HW <= 64) *g = {32, 2};
   else if (HW <= 128) *g = {32, 4};
@@ -764,10 +813,16 @@ void fold_configuration(const FrzWildfireParams& in, int group, int cells_per_la
     if (x > 0) derived->west_ok[c >> 5] |= 1u << (c & 31);
     if (x < W - 1) derived->east_ok[c >> 5] |= 1u << (c & 31);
   }
-  // Philox layout of the 4-cells-per-lane geometry: lanes whose fourth cell (96 + lane) is off-grid have two unused
-  // words each; two such lanes per agent replace a third Philox call
-  const int first_spare = HW - 96 > 0 ? HW - 96 : 0;
-  derived->spare_lanes_feed_agents = (group == 32 && cells_per_lane == 4 && 2 * in.num_agents <= 32 - first_spare) ? 1 : 0;
+  // Philox layout (see the kernel): lanes whose last cell is off-grid have two unused words; with an odd number of
+  // cells per lane every lane has two more.  The agents' four words are taken from those when enough lanes qualify.
+  derived->spare_lanes_feed_agents = 0;
+  if (cells_per_lane > 1) {
+    const int last_row_cells = HW - group * (cells_per_lane - 1);  // cells of the last row that are inside the grid
+    const int spare_lanes = group - (last_row_cells > 0 ? last_row_cells : 0);
+    const int calls = (2 * cells_per_lane + 3) / 4, spare_own = 4 * calls - 2 * cells_per_lane;
+    const int lanes_needed = spare_own == 2 ? in.num_agents : 2 * in.num_agents;
+    derived->spare_lanes_feed_agents = lanes_needed <= spare_lanes ? 1 : 0;
+  }
 }
 
 template <int G, int CPL, int MODE, bool INJECTED>
@@ -833,7 +888,14 @@ int dispatch(const FrzWildfireParams* p, const FrzWildfireBuffers* io, int B, in
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (g.group == 8) return launch_step<8, 1>(*p, *io, B, mode, s);
-  if (g.group == 16) return launch_step<16, 1>(*p, *io, B, mode, s);
+  if (g.group == 16) {
+    switch (g.cells_per_lane) {
+      case 1: return launch_step<16, 1>(*p, *io, B, mode, s);
+      case 2: return launch_step<16, 2>(*p, *io, B, mode, s);
+      case 3: return launch_step<16, 3>(*p, *io, B, mode, s);
+      default: return launch_step<16, 4>(*p, *io, B, mode, s);
+    }
+  }
   switch (g.cells_per_lane) {
     case 1: return launch_step<32, 1>(*p, *io, B, mode, s);
     case 2: return launch_step<32, 2>(*p, *io, B, mode, s);

@@ -27,7 +27,7 @@ def child(args):
     B = args.parallel_envs or spec['envs']
     device = torch.device('cuda', 0)
     module = importlib.import_module(f'free_range_zoo_b200.envs.{spec["domain"]}_v0')
-    env = module.parallel_env(parallel_envs=B, max_steps=1 << 30, configuration=getattr(presets, spec['preset'])(),
+    env = module.parallel_env(parallel_envs=B, max_steps=1 << 30, configuration=getattr(presets, spec['preset'])(**spec.get('preset_kwargs', {})),
                               device=device, **spec['kwargs'])
     raw = env.unwrapped
     env.reset(seed=2026)

@@ -51,6 +51,8 @@ def test_matches_reference_trajectory(name):
     (('wildfire_large', dict(height=4, width=40, num_agents=6, seed=7)), 300, 20, {}),
     (('wildfire_large', dict(height=3, width=33, num_agents=20, seed=8)), 300, 20, dict(show_bad_actions=True)),
     (('wildfire_large', dict(height=2, width=100, num_agents=7, seed=9)), 200, 15, {}),
+    (('wildfire_large', dict(height=3, width=33, num_agents=6, seed=10)), 300, 20, {}),  # half-warp groups, rows >= 32 cells
+    (('wildfire_large', dict(height=5, width=9, num_agents=16, seed=11)), 300, 20, {}),  # half-warp groups, 16 agents
 ])
 def test_matches_oracle_on_random_rollouts(preset, B, steps, kwargs):
     from oracle.wildfire import WildfireOracle
@@ -207,3 +209,38 @@ def test_action_mapping_wrapper_returns_the_reference_mappings():
         env.unwrapped.inject_uniforms(torch.from_numpy(gold['u_field'][t]), torch.from_numpy(gold['u_agent'][t]))
         actions = torch.from_numpy(gold['actions'][t]).cuda()
         observations, _, _, _, _ = env.step({a: actions[:, i] for i, a in enumerate(agents)})
+
+
+def test_burnt_out_and_live_environments_share_a_warp():
+    """Sub-warp groups: an environment with nothing lit (a termination candidate, which triggers the fuel reduction)
+    next to a live one in the same warp must step like the oracle -- every lane has to take part in the group-wide
+    shuffles whatever its own environment looks like."""
+    from oracle.wildfire import WildfireOracle
+    config = presets.wildfire_large(height=7, width=8, num_agents=5, seed=5)
+    B, steps = 64, 6
+    oracle = WildfireOracle(config, B, steps)
+    oracle.reset()
+    env = make_env(config, B, steps)
+    env.reset(seed=1)
+    state = env.unwrapped.state()
+    state.fires[::2] = -state.fires[::2].abs()  # every other environment: everything put out, fuel left
+    state.intensity[::2] = 0
+    oracle.fires[::2] = -np.abs(oracle.fires[::2])
+    oracle.intensity[::2] = 0
+    env.unwrapped.update_observations()
+    env.unwrapped.update_actions()
+    oracle.update_observations()
+    oracle.update_actions()
+    rng = np.random.default_rng(3)
+    H, W, A = oracle.H, oracle.W, oracle.A
+    for t in range(steps):
+        counts = oracle.agent_task_count
+        k = np.minimum((rng.random((B, A)) * (counts + 1)).astype(np.int64), counts)
+        actions = np.stack([k, np.where(k == counts, -1, 0)], axis=2).astype(np.int32)
+        u_field, u_agent = rng.random((3, B, H, W), dtype=np.float32), rng.random((5, B, A), dtype=np.float32)
+        assert oracle.step(actions, u_field, u_agent)
+        env.unwrapped.inject_uniforms(torch.from_numpy(u_field), torch.from_numpy(u_agent))
+        env.step(torch.from_numpy(actions).cuda())
+        want = {key: value[None] for key, value in oracle.outputs().items()}
+        G.compare({k_: v for k_, v in wildfire_outputs(env).items() if k_ in ('fires', 'intensity', 'fuel', 'rewards', 'terminated', 'env_task_count', 'agent_task_count')},
+                  want, 0, context=f'mixed t={t}')
