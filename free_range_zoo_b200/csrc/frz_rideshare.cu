@@ -7,10 +7,15 @@
 //
 // The reference keeps all passengers of all environments in one flat table [N_total, 11] sorted by environment and
 // re-sorts / compacts it with `unique`, boolean-mask indexing and a stable `argsort` every step.  Here environment b
-// owns rows passengers[b, 0:count[b]] (same relative order).  One warp owns one environment: the rows are staged in
-// shared memory with coalesced loads, lane p owns table row p (and p+32 when K > 32), lane a owns agent a.  Task
-// lists, conflict detection, compaction and the per-class "last row" reward quirk are ballots, match_any and
-// popcounts; agent -> passenger effects travel through shuffles.
+// owns rows passengers[b, 0:count[b]] (same relative order).
+//
+// Mapping: a group of G lanes (8, 16 or 32, chosen from the table capacity and the number of drivers) owns one
+// environment, so a warp steps 4, 2 or 1 environments at once.  The environment's rows live in shared memory for the
+// whole step (double buffered: cp.async streams the group's next environment while this one is stepped) and are
+// edited in place; lane s of the group looks after rows s, s+G, ... (PPL of them) and driver s.  Task lists, conflict
+// detection, compaction and the per-class "last row" reward quirk are ballots (cut to the group's lanes), match_any
+// and popcounts on 64-bit row masks.
+#include <algorithm>
 #include <climits>
 #include <math_constants.h>
 
@@ -23,17 +28,11 @@ constexpr int kRsThreads = 128;
 constexpr int kCols = FRZ_RS_PASSENGER_COLUMNS;
 enum RsMode { kRsStep = 0, kRsRefresh = 1, kRsEntryRefresh = 2 };
 enum Col { cBatch = 0, cY, cX, cDestY, cDestX, cFare, cState, cAssoc, cEntered, cAccepted, cPicked };
+constexpr int kRemoved = -7;  // scratch value of the state column: the row left the table in this step
 
 // stay, N, E, S, W, NW, NE, SE, SW (transitions/movement.py:27-45)
 __constant__ int kDirY[9] = {0, -1, 0, 1, 0, -1, -1, 1, 1};
 __constant__ int kDirX[9] = {0, 0, 1, 0, -1, -1, 1, 1, -1};
-
-template <int PPL>
-__device__ __forceinline__ uint64_t ballot_rows(const bool (&pred)[PPL]) {
-  uint64_t mask = __ballot_sync(kFullMask, pred[0]);
-  if (PPL == 2) mask |= uint64_t(__ballot_sync(kFullMask, pred[PPL - 1])) << 32;
-  return mask;
-}
 
 __device__ __forceinline__ int select_bit64(uint64_t mask, int k) {
   const uint32_t lo = uint32_t(mask);
@@ -46,106 +45,136 @@ __device__ __forceinline__ int select_bit64(uint64_t mask, int k) {
 // > 1e-3 apart, far above an fp32 ulp), so argmin, ties, "== 0" and "< 1e-6" give the same answers on the squares.
 __device__ __forceinline__ int squared(int dy, int dx) { return dy * dy + dx * dx; }
 
+// Row mask of one environment from per-lane predicates: bit (s + G * i) = predicate i of the group's lane s.  Every
+// lane of the warp must call it (the ballots are warp-wide); each lane receives its own group's mask.
+template <int G, int PPL>
+__device__ __forceinline__ uint64_t group_rows(const bool (&pred)[PPL], int group_base) {
+  constexpr uint32_t lanes = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+  uint64_t mask = 0;
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    const uint32_t ballot = __ballot_sync(kFullMask, pred[i]);
+    mask |= uint64_t((ballot >> group_base) & lanes) << (G * i);
+  }
+  return mask;
+}
+
+template <int G>
+__device__ __forceinline__ int group_min(int v) {
+#pragma unroll
+  for (int offset = G / 2; offset >= 1; offset >>= 1) v = min(v, __shfl_xor_sync(kFullMask, v, offset, G));
+  return v;
+}
+
 // MODE is a template parameter so that the refresh / reset variants carry none of the step's code.
-template <int PPL, int MODE>
+template <int G, int PPL, int MODE>
 __global__ void __launch_bounds__(kRsThreads)
 rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid_constant__ FrzRideshareBuffers io,
                       const int B, const uint8_t* __restrict__ entry_mask) {
+  static_assert(G * PPL <= 64, "row masks are 64 bits wide");
   extern __shared__ int smem[];
+  constexpr int kGroupsPerWarp = 32 / G;
+  constexpr int kGroupsPerCta = (kRsThreads / 32) * kGroupsPerWarp;
   const int lane = threadIdx.x & 31;
   // broadcast from lane 0: makes the warp index, hence the environment loop and every ballot, provably warp-uniform
   const int warp = __shfl_sync(kFullMask, int(threadIdx.x >> 5), 0);
-  constexpr int warps = kRsThreads / 32;
+  const int sub = lane % G, group_base = lane - sub;
   const int K = p.capacity, A = p.num_agents, S = p.schedule_rows;
-  // this warp's two passenger-table buffers as 32-bit shared-window addresses: the rows of the environment being
+  // this group's two passenger-table buffers as 32-bit shared-window addresses: the rows of the environment being
   // stepped are read / written as [table + 4 * index] while cp.async fills the other buffer with the next one's
   const uint32_t table_bytes = uint32_t(K * kCols) * 4u;
-  const uint32_t tables = shared_address(smem) + uint32_t(warp) * 2u * table_bytes;
-  const uint32_t lanes_below = (1u << lane) - 1u;
+  const uint32_t tables = shared_address(smem) + uint32_t(warp * kGroupsPerWarp + lane / G) * 2u * table_bytes;
+  const uint64_t rows_below = (uint64_t(1) << sub) - 1u;  // rows before this lane's first row
 
   FrzControl* control = io.control;
   const uint32_t alive_prev = control->alive;
   const uint32_t agents_with_tasks = control->agents_with_tasks;
   const bool skip = (MODE == kRsStep) && ((alive_prev & 3u) != 3u);  // utils/env.py:212
-  const bool is_agent = lane < A;
+  const bool is_agent = sub < A;
   const bool fast = p.flags & FRZ_RS_FAST_TRAVEL, diagonal = p.flags & FRZ_RS_DIAGONAL_TRAVEL;
   const int directions = diagonal ? 9 : 5;
-  // task-mask stores: lane -> (agent, four consecutive table rows)
+  // task-mask stores: work item -> (agent, four consecutive table rows)
   const int quads = (K + 3) >> 2;
   const uint32_t inverse_quads = (65536u + uint32_t(quads) - 1u) / uint32_t(quads);  // item / quads for item < 512
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
 
   if (!skip) {
-    // software pipeline: while environment e is stepped, the rows of this warp's next environment stream into the
+    // software pipeline: while environment e is stepped, the rows of this group's next environment stream into the
     // other buffer (cp.async, 4 bytes per lane per instruction: rows are 44 bytes, so nothing wider stays aligned)
-    const int stride = gridDim.x * warps;
+    const int stride = gridDim.x * kGroupsPerCta;
     const auto prefetch_rows = [&](int env, int rows, uint32_t buffer) {
       const int* source = io.passengers + uint32_t(env) * uint32_t(K * kCols);
-      for (int i = lane; i < rows * kCols; i += 32) cp_async_4(buffer + 4u * i, source + i);
+      for (int i = sub; i < rows * kCols; i += G) cp_async_4(buffer + 4u * i, source + i);
       cp_async_commit();
     };
-    int env = blockIdx.x * warps + warp;
-    int n_next = env < B ? min(io.env_task_count[env], K) : 0;
+    int env0 = (blockIdx.x * (kRsThreads / 32) + warp) * kGroupsPerWarp;  // first environment of this warp
+    int n_next = 0;
     uint32_t parity = 0;
-    if (env < B) prefetch_rows(env, n_next, tables);
-    for (; env < B; env += stride) {
+    if (env0 < B) {
+      const int first = min(env0 + lane / G, B - 1);
+      n_next = min(io.env_task_count[first], K);
+      prefetch_rows(first, n_next, tables);
+    }
+    for (; env0 < B; env0 += stride) {
+      const int env = min(env0 + lane / G, B - 1);
+      const bool valid = env0 + lane / G < B;  // groups past the end of the batch replay the last environment, storing nothing
       const uint32_t table = tables + parity * table_bytes;
-      const uint32_t agent_at = uint32_t(env) * uint32_t(A) + uint32_t(lane);
-      const uint32_t table_at = uint32_t(env) * uint32_t(K * kCols);
+      const uint32_t agent_at = uint32_t(env) * uint32_t(A) + uint32_t(sub);
       const int n_before = n_next;
-      int* const global_rows = io.passengers + table_at;
-      const int env_after = env + stride;
-      n_next = env_after < B ? min(io.env_task_count[env_after], K) : 0;  // needed by the prefetch issued below
-      cp_async_wait_all();
+      int* const global_rows = io.passengers + uint32_t(env) * uint32_t(K * kCols);
+      const bool more = env0 + stride < B;
+      const int env_after = min(env0 + stride + lane / G, B - 1);
+      if (more) n_next = min(io.env_task_count[env_after], K);  // needed by the prefetch issued below
 
       int agent_y = 0, agent_x = 0;
+      int2 act = make_int2(0, -100);
       if (is_agent) {
         const int2 at = reinterpret_cast<const int2*>(io.agents)[agent_at];
         agent_y = at.x;
         agent_x = at.y;
+        if (MODE == kRsStep) act = reinterpret_cast<const int2*>(io.actions)[agent_at];
       }
       const int t_now = io.num_moves[env];
       int n_kept = n_before, fare_won = 0;
       float move_cost = 0.f;
-      bool noop = false, accept = false;
+      const bool noop = act.y == -1, accept = act.y == 0, pick = act.y == 1, drop = act.y == 2;
+      cp_async_wait_all();
       __syncwarp();
 
-      if (MODE == kRsStep) {
-        // rows owned by this lane
-        int row[PPL][kCols];
-        bool valid[PPL];
+      // state / association columns of this lane's rows (kept in registers, refreshed after every edit phase)
+      int state[PPL], assoc[PPL];
+      bool present[PPL];
+      const auto load_rows = [&](int count) {
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-          const int r = lane + 32 * i;
-          valid[i] = r < n_before;
-#pragma unroll
-          for (int c = 0; c < kCols; ++c) row[i][c] = valid[i] ? int(lds(table + 4u * (r * kCols + c))) : -1;
+          const int r = sub + G * i;
+          present[i] = r < count;
+          state[i] = present[i] ? int(lds(table + 4u * uint32_t(r * kCols + cState))) : -1;
+          assoc[i] = present[i] ? int(lds(table + 4u * uint32_t(r * kCols + cAssoc))) : -1;
         }
+      };
+      bool pred[PPL];
 
+      if (MODE == kRsStep) {
+        load_rows(n_before);
         // ---------------------------------------------------------------- task lists (rideshare.py:374-386)
-        bool pred[PPL];
 #pragma unroll
-        for (int i = 0; i < PPL; ++i) pred[i] = valid[i] && row[i][cState] == 0;
-        const uint64_t unaccepted = ballot_rows<PPL>(pred);
+        for (int i = 0; i < PPL; ++i) pred[i] = present[i] && state[i] == 0;
+        const uint64_t unaccepted = group_rows<G, PPL>(pred, group_base);
         uint64_t mine = 0;
         for (int a = 0; a < A; ++a) {
 #pragma unroll
-          for (int i = 0; i < PPL; ++i) pred[i] = valid[i] && row[i][cAssoc] == a;
-          const uint64_t own = ballot_rows<PPL>(pred);
-          if (lane == a) mine = unaccepted | own;
+          for (int i = 0; i < PPL; ++i) pred[i] = present[i] && assoc[i] == a;
+          const uint64_t own = group_rows<G, PPL>(pred, group_base);
+          if (sub == a) mine = unaccepted | own;
         }
 
         // ---------------------------------------------------------------- decode (rideshare.py:255-300)
-        int2 act = make_int2(0, -100);
-        if (is_agent) act = reinterpret_cast<const int2*>(io.actions)[agent_at];
-        noop = act.y == -1;
-        accept = act.y == 0;
-        const bool pick = act.y == 1, drop = act.y == 2;
         int target = -1;
         // the reference only resolves targets of agents that have a task in SOME environment (rideshare.py:276)
-        if (is_agent && !noop && ((agents_with_tasks >> lane) & 1u)) {
+        if (is_agent && !noop && ((agents_with_tasks >> sub) & 1u)) {
           if (act.x >= 0 && act.x < __popcll(mine)) target = select_bit64(mine, act.x);
-          else if (accept || pick || drop) faults |= FRZ_FAULT_BAD_TASK_INDEX;
+          else if (valid && (accept || pick || drop)) faults |= FRZ_FAULT_BAD_TASK_INDEX;
         }
         const bool has_vector = target >= 0 && (accept || pick || drop);
         int goal_y = 0, goal_x = 0, fare_target = 0;
@@ -179,73 +208,82 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         }
         agent_y += move_y;
         agent_x += move_x;
+        __syncwarp();  // every lane has read its goal from the table
         // riding passengers travel with their driver; association -1 wraps to the last agent like the tensor index
 #pragma unroll
         for (int i = 0; i < PPL; ++i) {
-          int driver = row[i][cAssoc] < 0 ? row[i][cAssoc] + A : row[i][cAssoc];
-          driver = min(max(driver, 0), 31);
+          int driver = assoc[i] < 0 ? assoc[i] + A : assoc[i];
+          driver = group_base + min(max(driver, 0), G - 1);
           const int dy = __shfl_sync(kFullMask, move_y, driver), dx = __shfl_sync(kFullMask, move_x, driver);
-          if (valid[i] && row[i][cState] == 2) {
-            row[i][cY] += dy;
-            row[i][cX] += dx;
+          if (present[i] && state[i] == 2 && (dy | dx) != 0) {
+            const uint32_t t = table + 4u * uint32_t((sub + G * i) * kCols);
+            sts(t + 4u * cY, uint32_t(int(lds(t + 4u * cY)) + dy));
+            sts(t + 4u * cX, uint32_t(int(lds(t + 4u * cX)) + dx));
           }
         }
 
         // ---------------------------------------------------------------- accept conflicts (passenger_state.py:50-74)
         int claim = (accept && target >= 0) ? target : -1;
         {
-          const unsigned key = claim >= 0 ? unsigned(claim) : (0x80000000u | unsigned(lane));
+          const unsigned key = claim >= 0 ? (unsigned(group_base) << 8 | unsigned(claim)) : (0x80000000u | unsigned(lane));
           const bool duplicated = __popc(__match_any_sync(kFullMask, key)) > 1;
           if (__any_sync(kFullMask, duplicated)) {
             // among ALL duplicated claims of the environment only the closest claimant (first on ties) survives
             const int contest = duplicated ? distance2 : INT_MAX;
-            const int closest = __reduce_min_sync(kFullMask, contest);
-            const int keeper = __ffs(__ballot_sync(kFullMask, duplicated && contest == closest)) - 1;
-            if (duplicated && lane != keeper) claim = -1;
+            const int closest = group_min<G>(contest);
+            const uint32_t tied = (__ballot_sync(kFullMask, duplicated && contest == closest) >> group_base);
+            const int keeper = __ffs(G == 32 ? tied : (tied & ((1u << G) - 1u))) - 1;
+            if (duplicated && sub != keeper) claim = -1;
           }
         }
         const int picked = (pick && target >= 0 && distance2 == 0) ? target : -1;   // passenger_state.py:89-92 (< 1e-6)
         const int dropped = (drop && target >= 0 && distance2 == 0) ? target : -1;  // passenger_exit.py:40-45 (== 0)
         fare_won = dropped >= 0 ? fare_target : 0;
 
-        // ---------------------------------------------------------------- apply to the rows (accept, then pick, exit)
-        bool keep[PPL];
-#pragma unroll
-        for (int i = 0; i < PPL; ++i) keep[i] = valid[i];
-        for (int a = 0; a < A; ++a) {
-          const int c = __shfl_sync(kFullMask, claim, a);
-#pragma unroll
-          for (int i = 0; i < PPL; ++i) {
-            if (valid[i] && c == lane + 32 * i) {
-              row[i][cState] = 1;
-              row[i][cAccepted] = t_now;
-              row[i][cAssoc] = a;
-            }
-          }
+        // ---------------------------------------------------------------- apply: the drivers edit the rows in place
+        if (claim >= 0) {  // accept: all accepts land before any pick, like the reference's transition
+          const uint32_t t = table + 4u * uint32_t(claim * kCols);
+          sts(t + 4u * cState, 1u);
+          sts(t + 4u * cAccepted, uint32_t(t_now));
+          sts(t + 4u * cAssoc, uint32_t(sub));
         }
-        for (int a = 0; a < A; ++a) {  // all accepts land before any pick, like the reference's transition
-          const int k = __shfl_sync(kFullMask, picked, a), d = __shfl_sync(kFullMask, dropped, a);
-#pragma unroll
-          for (int i = 0; i < PPL; ++i) {
-            if (valid[i] && k == lane + 32 * i) {
-              row[i][cState] = 2;
-              row[i][cPicked] = t_now;
-            }
-            if (d == lane + 32 * i) keep[i] = false;
-          }
+        __syncwarp();
+        if (picked >= 0) {
+          const uint32_t t = table + 4u * uint32_t(picked * kCols);
+          sts(t + 4u * cState, 2u);
+          sts(t + 4u * cPicked, uint32_t(t_now));
         }
+        __syncwarp();
+        if (dropped >= 0) sts(table + 4u * uint32_t(dropped * kCols + cState), uint32_t(kRemoved));  // after the picks
+        __syncwarp();
 
         // ---------------------------------------------------------------- exit: order-preserving compaction
-        const uint64_t kept = ballot_rows<PPL>(keep);
-        n_kept = __popcll(kept);
-        __syncwarp();  // every read of the old table (targets) is done
+        if (__any_sync(kFullMask, dropped >= 0)) {
 #pragma unroll
-        for (int i = 0; i < PPL; ++i) {
-          if (keep[i]) {
-            const uint64_t below = (i == 0) ? uint64_t(lanes_below) : ((uint64_t(lanes_below) << 32) | 0xffffffffull);
-            const uint32_t out = table + 4u * uint32_t(__popcll(kept & below) * kCols);
+          for (int i = 0; i < PPL; ++i) {
+            const int r = sub + G * i;
+            pred[i] = r < n_before && int(lds(table + 4u * uint32_t(r * kCols + cState))) != kRemoved;
+          }
+          const uint64_t kept = group_rows<G, PPL>(pred, group_base);
+          n_kept = __popcll(kept);
+          // rows move down to their rank among the kept rows; slab by slab (rows s + G * i for all lanes s), read then
+          // write: a row lands either in an earlier slab (done) or on a row of this slab that was just read
 #pragma unroll
-            for (int c = 0; c < kCols; ++c) sts(out + 4u * c, uint32_t(row[i][c]));
+          for (int i = 0; i < PPL; ++i) {
+            const int r = sub + G * i;
+            const int to = __popcll(kept & ((rows_below << (G * i)) | ((uint64_t(1) << (G * i)) - 1u)));
+            const bool moves = pred[i] && to != r;
+            int row[kCols];
+            if (moves) {
+#pragma unroll
+              for (int c = 0; c < kCols; ++c) row[c] = int(lds(table + 4u * uint32_t(r * kCols + c)));
+            }
+            __syncwarp();
+            if (moves) {
+#pragma unroll
+              for (int c = 0; c < kCols; ++c) sts(table + 4u * uint32_t(to * kCols + c), uint32_t(row[c]));
+            }
+            __syncwarp();
           }
         }
       }
@@ -253,24 +291,25 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
       // ------------------------------------------------------------------ entry (passenger_entry.py:25-72)
       int n_rows = n_kept;
       const bool admits = MODE == kRsStep || (MODE == kRsEntryRefresh && (entry_mask == nullptr || entry_mask[env]));
-      if (admits) {
+      {
         const int t_entry = (MODE == kRsStep) ? t_now + 1 : t_now;  // rideshare.py:307 vs :212
         // rows of the time-sorted schedule that enter at t_entry: [schedule_index[t], schedule_index[t + 1])
         int lo = S, hi = S;
-        if (t_entry >= 0 && t_entry <= p.schedule_horizon) {
+        if (admits && t_entry >= 0 && t_entry <= p.schedule_horizon) {
           lo = io.schedule_index[t_entry];
           hi = io.schedule_index[t_entry + 1];
         }
-        if (lo < hi) {
+        if (__any_sync(kFullMask, lo < hi)) {  // (environments of one warp may be at different steps after a partial reset)
           const int64_t global_env = p.env_offset + env;
-          for (int base = lo; base < hi; base += 32) {
-            const int r = base + lane;
+          constexpr uint32_t lanes = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+          for (int base = 0; __any_sync(kFullMask, lo + base < hi); base += G) {
+            const int r = lo + base + sub;
             const bool now = r < hi;
             const int* s = io.schedule + r * 7;
             const int batch = now ? s[1] : 0;
             const bool enters = now && (batch == -1 || batch == global_env);
-            const unsigned entering = __ballot_sync(kFullMask, enters);
-            const int slot = n_rows + __popc(entering & lanes_below);
+            const uint32_t entering = (__ballot_sync(kFullMask, enters) >> group_base) & lanes;
+            const int slot = n_rows + __popc(entering & ((1u << sub) - 1u));
             if (enters) {
               if (slot < K) {
                 const uint32_t out = table + 4u * uint32_t(slot * kCols);
@@ -285,7 +324,7 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
                 sts(out + 4u * cEntered, uint32_t(t_entry));
                 sts(out + 4u * cAccepted, uint32_t(-1));
                 sts(out + 4u * cPicked, uint32_t(-1));
-              } else {
+              } else if (valid) {
                 faults |= FRZ_FAULT_TABLE_FULL;
               }
             }
@@ -294,25 +333,19 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         }
       }
       __syncwarp();
-
-      if (env_after < B) prefetch_rows(env_after, n_next, tables + (parity ^ 1u) * table_bytes);
+      if (more) prefetch_rows(env_after, n_next, tables + (parity ^ 1u) * table_bytes);
       parity ^= 1u;
 
-      // ------------------------------------------------------------------ the new table, one row per lane again
-      int state[PPL], assoc[PPL], stamp[PPL];
-      bool present[PPL];
+      // ------------------------------------------------------------------ the new table
+      load_rows(n_rows);
 #pragma unroll
       for (int i = 0; i < PPL; ++i) {
-        const int r = lane + 32 * i;
-        present[i] = r < n_rows;
-        const uint32_t t = table + 4u * uint32_t(r * kCols);
-        state[i] = present[i] ? int(lds(t + 4u * cState)) : -1;
-        assoc[i] = present[i] ? int(lds(t + 4u * cAssoc)) : -1;
-        stamp[i] = present[i] ? int(lds(t + 4u * (state[i] == 0 ? cEntered : (state[i] == 1 ? cAccepted : cPicked)))) : 0;
+        const int r = sub + G * i;
         // task observation row (rideshare.py:398-416) + padding of rows that just became free
-        if (r < K && (present[i] || r < n_before || MODE != kRsStep)) {
+        if (valid && r < K && (present[i] || r < n_before || MODE != kRsStep)) {
           int4 head = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD), tail = head;
           if (present[i]) {
+            const uint32_t t = table + 4u * uint32_t(r * kCols);
             head = make_int4(int(lds(t + 4u * cY)), int(lds(t + 4u * cX)), int(lds(t + 4u * cDestY)), int(lds(t + 4u * cDestX)));
             tail = make_int4(state[i] == 1 ? assoc[i] : FRZ_PAD, state[i] == 2 ? assoc[i] : FRZ_PAD, int(lds(t + 4u * cFare)),
                              int(lds(t + 4u * cEntered)));
@@ -323,55 +356,52 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         }
       }
 
-      // per-agent counts; lane a keeps agent a's
+      // row masks by passenger state, per-agent counts; lane a of the group keeps agent a's
+      uint64_t in_state[3];
+#pragma unroll
+      for (int cls = 0; cls < 3; ++cls) {
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) pred[i] = present[i] && state[i] == cls;
+        in_state[cls] = group_rows<G, PPL>(pred, group_base);
+      }
       int associated = 0, n_accepted = 0, n_riding = 0, n_tasks = 0;
       uint64_t members_mine = 0;
-      bool pred[PPL];
-#pragma unroll
-      for (int i = 0; i < PPL; ++i) pred[i] = present[i] && state[i] == 0;
-      const uint64_t unaccepted = ballot_rows<PPL>(pred);
       for (int a = 0; a < A; ++a) {
 #pragma unroll
         for (int i = 0; i < PPL; ++i) pred[i] = present[i] && assoc[i] == a;
-        const uint64_t own = ballot_rows<PPL>(pred);
-#pragma unroll
-        for (int i = 0; i < PPL; ++i) pred[i] = present[i] && assoc[i] == a && state[i] == 1;
-        const uint64_t own_accepted = ballot_rows<PPL>(pred);
-#pragma unroll
-        for (int i = 0; i < PPL; ++i) pred[i] = present[i] && assoc[i] == a && state[i] == 2;
-        const uint64_t own_riding = ballot_rows<PPL>(pred);
-        if (lane == a) {
+        const uint64_t own = group_rows<G, PPL>(pred, group_base);
+        if (sub == a) {
           associated = __popcll(own);
-          n_accepted = __popcll(own_accepted);
-          n_riding = __popcll(own_riding);
-          members_mine = unaccepted | own;
+          n_accepted = __popcll(own & in_state[1]);
+          n_riding = __popcll(own & in_state[2]);
+          members_mine = in_state[0] | own;
           n_tasks = __popcll(members_mine);
         }
       }
-      // task mask [A, K] bytes: work item (agent, four consecutive rows) -> one 4-byte store; K is a multiple of 4 or
-      // the last quad of a row spills into bytes that the next agent's first quad rewrites (rows are written in order)
+      // task mask [A, K] bytes: work item (agent, four consecutive rows) -> one 4-byte store when K is a multiple of 4
       {
-        uint32_t* const mask_words = reinterpret_cast<uint32_t*>(io.task_mask);
         const bool aligned = (K & 3) == 0;
-        if (aligned) {
-          const uint32_t mask_at = uint32_t(env) * uint32_t(A * quads);
-          for (int first = 0; first < A * quads; first += 32) {
-            const int item = first + lane;
-            const int a = int((uint32_t(item) * inverse_quads) >> 16), q = item - a * quads;
-            const uint32_t lo = __shfl_sync(kFullMask, uint32_t(members_mine), a & 31);
-            const uint32_t hi = __shfl_sync(kFullMask, uint32_t(members_mine >> 32), a & 31);
-            const uint32_t nibble = ((q < 8 ? lo : hi) >> (4 * (q & 7))) & 0xfu;
-            if (item < A * quads) mask_words[mask_at + item] = (nibble * 0x00204081u) & 0x01010101u;
-          }
-        } else {
+        const int items = aligned ? A * quads : 0;
+        uint32_t* const mask_words = reinterpret_cast<uint32_t*>(io.task_mask);
+        const uint32_t mask_at = uint32_t(env) * uint32_t(A * quads);
+        for (int first = 0; first < items; first += G) {
+          const int item = first + sub;
+          const int a = int((uint32_t(item) * inverse_quads) >> 16), q = item - a * quads;
+          const int source = group_base + min(a, G - 1);
+          const uint32_t lo = __shfl_sync(kFullMask, uint32_t(members_mine), source);
+          const uint32_t hi = __shfl_sync(kFullMask, uint32_t(members_mine >> 32), source);
+          const uint32_t nibble = ((q < 8 ? lo : hi) >> (4 * (q & 7))) & 0xfu;
+          if (valid && item < items) mask_words[mask_at + item] = (nibble * 0x00204081u) & 0x01010101u;
+        }
+        if (!aligned) {
           for (int a = 0; a < A; ++a) {
-            const uint64_t members = (uint64_t(__shfl_sync(kFullMask, uint32_t(members_mine >> 32), a)) << 32) |
-                                     __shfl_sync(kFullMask, uint32_t(members_mine), a);
+            const uint64_t members = (uint64_t(__shfl_sync(kFullMask, uint32_t(members_mine >> 32), group_base + a)) << 32) |
+                                     __shfl_sync(kFullMask, uint32_t(members_mine), group_base + a);
             uint8_t* mask_row = io.task_mask + (uint32_t(env) * uint32_t(A) + uint32_t(a)) * uint32_t(K);
 #pragma unroll
             for (int i = 0; i < PPL; ++i) {
-              const int r = lane + 32 * i;
-              if (r < K) mask_row[r] = (members >> r) & 1u;
+              const int r = sub + G * i;
+              if (valid && r < K) mask_row[r] = (members >> r) & 1u;
             }
           }
         }
@@ -383,35 +413,25 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         if (p.flags & FRZ_RS_WAITING_COSTS) {
           // `global[idx] += v` with duplicate indices keeps ONE write per statement: the last row of the class
           int elapsed_unaccepted = 0;
-          bool any_unaccepted = false;
-          for (int cls = 0; cls < 3; ++cls) {
 #pragma unroll
-            for (int i = 0; i < PPL; ++i) pred[i] = present[i] && state[i] == cls;
-            const uint64_t members = ballot_rows<PPL>(pred);
-            if (members) {
-              const int last = 63 - __clzll(members);
-              int when = __shfl_sync(kFullMask, stamp[0], last & 31);
-              if (PPL == 2) {
-                const int upper = __shfl_sync(kFullMask, stamp[PPL - 1], last & 31);
-                when = last >= 32 ? upper : when;
-              }
+          for (int cls = 0; cls < 3; ++cls) {
+            if (in_state[cls]) {
+              const int last = 63 - __clzll(in_state[cls]);
+              const int when = int(lds(table + 4u * uint32_t(last * kCols + (cls == 0 ? cEntered : (cls == 1 ? cAccepted : cPicked)))));
               const int elapsed = t_now - when;
               shared = __fadd_rn(shared, __fmul_rn(elapsed >= p.wait_limit[cls] ? 1.f : 0.f, p.general_wait_cost));
-              if (cls == 0) {
-                any_unaccepted = true;
-                elapsed_unaccepted = elapsed;
-              }
+              if (cls == 0) elapsed_unaccepted = elapsed;
             }
           }
-          if (any_unaccepted)
+          if (in_state[0])
             shared = __fadd_rn(shared, __fmul_rn(elapsed_unaccepted >= p.long_wait_time ? 1.f : 0.f, p.long_wait_cost));
           const int free_slots = A * p.pool_limit - n_rows;
-          const float unserved = __fmul_rn(__popcll(unaccepted) >= free_slots ? 1.f : 0.f, -0.5f);
+          const float unserved = __fmul_rn(__popcll(in_state[0]) >= free_slots ? 1.f : 0.f, -0.5f);
           shared = __fadd_rn(shared, __fmul_rn(unserved, float(free_slots)));
         }
         const int moves = t_now + 1;
         const bool truncated = moves >= p.max_steps;
-        if (is_agent) {
+        if (is_agent && valid) {
           float reward = associated > p.pool_limit ? p.pool_limit_cost : 0.f;
           reward = __fadd_rn(reward, __fmul_rn(noop ? 1.f : 0.f, p.noop_cost));
           reward = __fadd_rn(reward, __fmul_rn(accept ? 1.f : 0.f, p.accept_cost));
@@ -424,22 +444,24 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
           io.cumulative_rewards[agent_at] = __fadd_rn(io.cumulative_rewards[agent_at], reward);
           reinterpret_cast<int2*>(io.agents)[agent_at] = make_int2(agent_y, agent_x);
         }
-        if (lane == 0) {
+        if (sub == 0 && valid) {
           io.num_moves[env] = moves;
           io.truncated[env] = truncated;
         }
-        alive_bits |= 1u | (truncated ? 0u : 2u);  // rideshare never terminates (rideshare.py:252)
+        if (valid) alive_bits |= 1u | (truncated ? 0u : 2u);  // rideshare never terminates (rideshare.py:252)
       }
 
       // ------------------------------------------------------------------ publish
-      if (is_agent) {
-        io.agent_task_count[agent_at] = n_tasks;
-        if (n_tasks > 0) agent_bits |= 1u << lane;
-        reinterpret_cast<int4*>(io.self_obs)[agent_at] = make_int4(agent_y, agent_x, n_accepted, n_riding);
+      if (valid) {
+        if (is_agent) {
+          io.agent_task_count[agent_at] = n_tasks;
+          if (n_tasks > 0) agent_bits |= 1u << sub;
+          reinterpret_cast<int4*>(io.self_obs)[agent_at] = make_int4(agent_y, agent_x, n_accepted, n_riding);
+        }
+        if (sub == 0) io.env_task_count[env] = n_rows;
+        if (admits)
+          for (int i = sub; i < n_rows * kCols; i += G) global_rows[i] = int(lds(table + 4u * i));
       }
-      if (lane == 0) io.env_task_count[env] = n_rows;
-      if (admits)
-        for (int i = lane; i < n_rows * kCols; i += 32) global_rows[i] = int(lds(table + 4u * i));
       __syncwarp();
     }
   }
@@ -520,15 +542,32 @@ int rideshare_validate(const FrzRideshareParams* p, const FrzRideshareBuffers* i
   return FRZ_OK;
 }
 
+// Lanes per environment and rows per lane: the smallest group that holds the drivers and keeps at most 4 rows per lane.
+template <int G, int PPL, int MODE>
+int rideshare_launch_geometry(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, cudaStream_t s,
+                              const uint8_t* entry_mask) {
+  constexpr int groups_per_cta = (kRsThreads / 32) * (32 / G);
+  const size_t smem = size_t(groups_per_cta) * 2 * p->capacity * kCols * sizeof(int);  // two table buffers per group
+  auto kernel = rideshare_step_kernel<G, PPL, MODE>;
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    return check_launch("rideshare shared memory");
+  const int ctas_per_sm = int(std::min<size_t>(12, std::max<size_t>(1, (200 * 1024) / (smem + 1024))));
+  const int grid = persistent_grid((B + groups_per_cta - 1) / groups_per_cta, ctas_per_sm);
+  kernel<<<grid, kRsThreads, smem, s>>>(*p, *io, B, entry_mask);
+  return check_launch("rideshare_step_kernel");
+}
+
 template <int MODE>
 int rideshare_launch_mode(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, cudaStream_t s,
                           const uint8_t* entry_mask) {
-  const int warps = kRsThreads / 32;
-  const size_t smem = size_t(warps) * 2 * p->capacity * kCols * sizeof(int);  // two table buffers per warp
-  const int grid = persistent_grid((B + warps - 1) / warps, 12);
-  if (p->capacity <= 32) rideshare_step_kernel<1, MODE><<<grid, kRsThreads, smem, s>>>(*p, *io, B, entry_mask);
-  else rideshare_step_kernel<2, MODE><<<grid, kRsThreads, smem, s>>>(*p, *io, B, entry_mask);
-  return check_launch("rideshare_step_kernel");
+  const int K = p->capacity, A = p->num_agents;
+  if (A <= 8 && K <= 8) return rideshare_launch_geometry<8, 1, MODE>(p, io, B, s, entry_mask);
+  if (A <= 8 && K <= 16) return rideshare_launch_geometry<8, 2, MODE>(p, io, B, s, entry_mask);
+  if (A <= 8 && K <= 32) return rideshare_launch_geometry<8, 4, MODE>(p, io, B, s, entry_mask);
+  if (A <= 16 && K <= 32) return rideshare_launch_geometry<16, 2, MODE>(p, io, B, s, entry_mask);
+  if (A <= 16) return rideshare_launch_geometry<16, 4, MODE>(p, io, B, s, entry_mask);
+  if (K <= 32) return rideshare_launch_geometry<32, 1, MODE>(p, io, B, s, entry_mask);
+  return rideshare_launch_geometry<32, 2, MODE>(p, io, B, s, entry_mask);
 }
 
 int rideshare_launch(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, int mode, void* stream,
