@@ -246,6 +246,17 @@ def rideshare_quirks(ns=None, parallel_envs: int = 16, diagonal: bool = True, fa
                                   long_wait_time=5, general_wait_cost=-0.15, long_wait_cost=-0.4))
 
 
+def rideshare_synthetic(ns=None, drivers: int = 20, rows: int = 64, horizon: int = 25, height: int = 12, width: int = 9,
+                        seed: int = 55):
+    """Parity-only: many drivers on a non-square grid with a dense schedule (exercises the widest kernel geometry)."""
+    gen = torch.Generator().manual_seed(seed)
+    starts = torch.stack([torch.randint(0, height, (drivers, ), generator=gen),
+                          torch.randint(0, width, (drivers, ), generator=gen)], dim=1).tolist()
+    return _rideshare(ns, height=height, width=width, starts=starts, pool_limit=2, diagonal=True, fast=False,
+                      schedule=synthetic_schedule(rows, horizon, height, width, seed=seed + 1),
+                      reward=dict(use_waiting_costs=True, use_variable_move_cost=True))
+
+
 # ------------------------------------------------------------------------------------------------ cybersecurity
 
 

@@ -58,6 +58,7 @@ def legal_actions(oracle, rng):
     (('cyber_synthetic', dict(nodes=10, attackers=5, defenders=4)), 1500, 20, dict(show_bad_actions=True)),
     (('cyber_synthetic', dict(nodes=17, attackers=1, defenders=1)), 700, 20, dict(show_bad_actions=True)),
     (('cyber_synthetic', dict(nodes=20, attackers=9, defenders=9)), 300, 15, dict(show_bad_actions=True)),
+    (('cyber_synthetic', dict(nodes=32, attackers=16, defenders=16)), 150, 10, dict(show_bad_actions=True)),  # size limits
 ])
 def test_matches_oracle_on_random_rollouts(preset, B, steps, kwargs):
     from oracle.cybersecurity import CybersecurityOracle

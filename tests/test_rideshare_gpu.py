@@ -59,6 +59,9 @@ def policy_actions(oracle, rng, wild):
     ('rideshare_c2', {}, 1, 30, 0.0),  # a single environment
     ('rideshare_c2', dict(rows=48, horizon=30), 150, 50, 0.2),  # more than 32 rows per table: two rows per lane
     ('rideshare_c2', dict(rows=61, horizon=20), 100, 40, 0.2),  # ... and a row count that is not a multiple of 4
+    ('rideshare_synthetic', dict(drivers=20, rows=64), 60, 30, 0.2),  # 32-lane groups: 20 drivers, a full 64-row table
+    ('rideshare_synthetic', dict(drivers=12, rows=40), 80, 30, 0.2),  # 16-lane groups, 4 rows per lane
+    ('rideshare_synthetic', dict(drivers=32, rows=24), 50, 30, 0.1),  # the engine's driver limit
 ])
 def test_matches_oracle_on_random_rollouts(preset, preset_kwargs, B, steps, wild):
     from oracle.rideshare import RideshareOracle

@@ -53,6 +53,7 @@ def test_matches_reference_trajectory(name):
     (('wildfire_large', dict(height=2, width=100, num_agents=7, seed=9)), 200, 15, {}),
     (('wildfire_large', dict(height=3, width=33, num_agents=6, seed=10)), 300, 20, {}),  # half-warp groups, rows >= 32 cells
     (('wildfire_large', dict(height=5, width=9, num_agents=16, seed=11)), 300, 20, {}),  # half-warp groups, 16 agents
+    (('wildfire_large', dict(height=16, width=16, num_agents=32, seed=12)), 100, 12, {}),  # the engine's size limits
 ])
 def test_matches_oracle_on_random_rollouts(preset, B, steps, kwargs):
     from oracle.wildfire import WildfireOracle
