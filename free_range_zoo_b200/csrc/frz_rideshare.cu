@@ -46,17 +46,28 @@ __device__ __forceinline__ int select_bit64(uint64_t mask, int k) {
 __device__ __forceinline__ int squared(int dy, int dx) { return dy * dy + dx * dx; }
 
 // Row mask of one environment from per-lane predicates: bit (s + G * i) = predicate i of the group's lane s.  Every
-// lane of the warp must call it (the ballots are warp-wide); each lane receives its own group's mask.
+// lane of the warp must call it (the ballots are warp-wide); each lane receives its own group's mask.  The group's
+// byte / halfword of up to four ballots is packed with byte permutes (`pack` = the group's selector, see the kernel).
 template <int G, int PPL>
-__device__ __forceinline__ uint64_t group_rows(const bool (&pred)[PPL], int group_base) {
-  constexpr uint32_t lanes = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
-  uint64_t mask = 0;
+__device__ __forceinline__ uint64_t group_rows(const bool (&pred)[PPL], int group_base, uint32_t pack) {
+  uint32_t ballot[PPL];
 #pragma unroll
-  for (int i = 0; i < PPL; ++i) {
-    const uint32_t ballot = __ballot_sync(kFullMask, pred[i]);
-    mask |= uint64_t((ballot >> group_base) & lanes) << (G * i);
+  for (int i = 0; i < PPL; ++i) ballot[i] = __ballot_sync(kFullMask, pred[i]);
+  if constexpr (G == 32) {
+    return uint64_t(ballot[0]) | (PPL > 1 ? uint64_t(ballot[PPL - 1]) << 32 : 0);
+  } else if constexpr (PPL == 1) {
+    return uint64_t((ballot[0] >> group_base) & ((1u << G) - 1u));
+  } else if constexpr (G == 16) {  // halfwords: rows (0, 1) -> low word, rows (2, 3) -> high word
+    const uint32_t lo = __byte_perm(ballot[0], ballot[1], pack);
+    const uint32_t hi = PPL > 2 ? __byte_perm(ballot[2], ballot[PPL - 1], pack) : 0u;
+    return uint64_t(lo) | (uint64_t(hi) << 32);
+  } else {  // G == 8, bytes: byte i of the result is the group's byte of ballot i
+    static_assert(G == 8 && (PPL == 2 || PPL == 4), "8-lane groups hold 1, 2 or 4 rows per lane");
+    const uint32_t lo = __byte_perm(ballot[0], ballot[1], pack);  // bytes 0, 1 valid
+    if constexpr (PPL == 2) return uint64_t(lo & 0xffffu);
+    const uint32_t hi = __byte_perm(ballot[2], ballot[PPL - 1], pack);
+    return uint64_t(__byte_perm(lo, hi, 0x5410));
   }
-  return mask;
 }
 
 template <int G>
@@ -85,6 +96,10 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
   const uint32_t table_bytes = uint32_t(K * kCols) * 4u;
   const uint32_t tables = shared_address(smem) + uint32_t(warp * kGroupsPerWarp + lane / G) * 2u * table_bytes;
   const uint64_t rows_below = (uint64_t(1) << sub) - 1u;  // rows before this lane's first row
+  // byte-permute selector that pulls this group's slice out of two ballots (group_rows): 16-lane groups take halfword
+  // g of each, 8-lane groups byte g of each
+  const uint32_t pack = (G == 16) ? ((group_base & 16) ? 0x7632u : 0x5410u)
+                                  : (uint32_t(group_base >> 3) | ((4u + uint32_t(group_base >> 3)) << 4));
 
   FrzControl* control = io.control;
   const uint32_t alive_prev = control->alive;
@@ -160,12 +175,12 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         // ---------------------------------------------------------------- task lists (rideshare.py:374-386)
 #pragma unroll
         for (int i = 0; i < PPL; ++i) pred[i] = present[i] && state[i] == 0;
-        const uint64_t unaccepted = group_rows<G, PPL>(pred, group_base);
+        const uint64_t unaccepted = group_rows<G, PPL>(pred, group_base, pack);
         uint64_t mine = 0;
         for (int a = 0; a < A; ++a) {
 #pragma unroll
           for (int i = 0; i < PPL; ++i) pred[i] = present[i] && assoc[i] == a;
-          const uint64_t own = group_rows<G, PPL>(pred, group_base);
+          const uint64_t own = group_rows<G, PPL>(pred, group_base, pack);
           if (sub == a) mine = unaccepted | own;
         }
 
@@ -264,7 +279,7 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
             const int r = sub + G * i;
             pred[i] = r < n_before && int(lds(table + 4u * uint32_t(r * kCols + cState))) != kRemoved;
           }
-          const uint64_t kept = group_rows<G, PPL>(pred, group_base);
+          const uint64_t kept = group_rows<G, PPL>(pred, group_base, pack);
           n_kept = __popcll(kept);
           // rows move down to their rank among the kept rows; slab by slab (rows s + G * i for all lanes s), read then
           // write: a row lands either in an earlier slab (done) or on a row of this slab that was just read
@@ -362,14 +377,14 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
       for (int cls = 0; cls < 3; ++cls) {
 #pragma unroll
         for (int i = 0; i < PPL; ++i) pred[i] = present[i] && state[i] == cls;
-        in_state[cls] = group_rows<G, PPL>(pred, group_base);
+        in_state[cls] = group_rows<G, PPL>(pred, group_base, pack);
       }
       int associated = 0, n_accepted = 0, n_riding = 0, n_tasks = 0;
       uint64_t members_mine = 0;
       for (int a = 0; a < A; ++a) {
 #pragma unroll
         for (int i = 0; i < PPL; ++i) pred[i] = present[i] && assoc[i] == a;
-        const uint64_t own = group_rows<G, PPL>(pred, group_base);
+        const uint64_t own = group_rows<G, PPL>(pred, group_base, pack);
         if (sub == a) {
           associated = __popcll(own);
           n_accepted = __popcll(own & in_state[1]);
