@@ -72,8 +72,9 @@ class BatchedAECEnv(ABC):
             max_steps: truncation horizon
             parallel_envs: number of environments stepped together
             device: must be a CUDA device -- there is no CPU path
-            render_mode / log_directory / override_initialization_check: accepted; logging and rendering are host-side
-                subsystems outside this engine (log_directory must be None)
+            render_mode: accepted; rendering is a host-side subsystem outside this engine
+            log_directory / override_initialization_check: a directory turns on the asynchronous CSV logging tap
+                (utils/logging_tap.py; same files as the reference's CSVLogger); SQL connection strings are refused
             single_seeding / buffer_size: accepted and ignored -- randomness is counter-based Philox generated inside
                 the step kernel, keyed by (seed, global env index, step), so there are no generator states to juggle
             env_offset: global index of this shard's first environment (multi-GPU sharding keeps trajectories invariant)
