@@ -68,7 +68,14 @@ __device__ __forceinline__ uint32_t group_ballot(bool pred, int group_base, uint
 //   static again (sizes depend on the configuration, so they come last: every offset above is a constant)
 //     cell_agents[E][kCells]   bit a = agent a reaches cell c when its equipment is in state e
 //     range_mask[A][E][NW]     bit c = cell c is within agent a's reach in equipment state e
-__host__ __device__ constexpr int group_smem_words(int cells) { return 2 * cells; }
+//     (half-warp groups with more than 4 cells per lane only) fires, intensity, fuel [kCells each]: the cell state
+//     stays here instead of in registers, padded so that the two groups of a warp hit different banks
+__host__ __device__ constexpr bool cells_in_smem(int group, int cells_per_lane) { return group == 16 && cells_per_lane > 4; }
+__host__ __device__ constexpr int group_smem_words(int group, int cells_per_lane) {
+  const int cells = group * cells_per_lane;
+  const int words = cells_in_smem(group, cells_per_lane) ? 5 * cells : 2 * cells;
+  return (group == 16 && words % 32 == 0) ? words + 16 : words;
+}
 __host__ __device__ inline int static_smem_words(int cells, int agents, int states) {
   const int words = (cells + 31) / 32;
   return 4 * cells + states * cells + agents * states * words;
@@ -163,9 +170,10 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   // word offsets into smem[] (see the layout above): everything but the range-mask base is a compile-time constant
   // plus, for the per-group region, one per-thread register -- shared memory is only ever addressed as smem[offset]
   constexpr int kYOff = 0, kXOff = kCells, kIgnitionOff = 2 * kCells, kRewardOff = 3 * kCells, kRegionOff = 4 * kCells;
-  constexpr int kCellAgentsOff = kRegionOff + (kThreads / 32) * kGroupsPerWarp * group_smem_words(kCells);
+  constexpr int kCellAgentsOff = kRegionOff + (kThreads / 32) * kGroupsPerWarp * group_smem_words(G, CPL);
+  constexpr bool kCellsInSmem = cells_in_smem(G, CPL);
   const int range_off = kCellAgentsOff + E * kCells;
-  const int attack_off = kRegionOff + (warp_in_cta * kGroupsPerWarp + lane / G) * group_smem_words(kCells);
+  const int attack_off = kRegionOff + (warp_in_cta * kGroupsPerWarp + lane / G) * group_smem_words(G, CPL);
   const int tasks_off = attack_off + kCells;
   // 32-bit shared-window byte addresses: static tables at this lane's cell column, this group's scratch region
   const uint32_t s_base = shared_address(smem);
@@ -175,6 +183,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   asm volatile("" : "+r"(s_attack));
   const uint32_t s_tasks = s_base + 4u * uint32_t(tasks_off);
   const uint32_t s_range = s_base + 4u * uint32_t(range_off);
+  const uint32_t s_state = s_tasks + 4u * uint32_t(kCells + sub);  // this lane's column of the group's state planes
 
   for (int i = threadIdx.x; i < E * kCells; i += kThreads) {
     const int e = i / kCells, c = i - e * kCells;
@@ -229,15 +238,28 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       int* const fuel_row = io.fuel + cell_row;
 
       // ------------------------------------------------------------------ load
-      int fires[CPL], inten[CPL], fuel[CPL];
+      // cell state of this lane's cells: plane 0 fires, 1 intensity, 2 fuel -- in registers, or (large half-warp
+      // geometries, where 3 * CPL registers per lane would spill) in the group's shared-memory planes
+      int cell_regs[3][kCellsInSmem ? 1 : CPL] = {};
+      const auto cell = [&](int plane, int i) -> int {
+        if constexpr (kCellsInSmem) return int(lds(s_state + 4u * uint32_t(plane * kCells + i * G)));
+        else return cell_regs[plane][i];
+      };
+      const auto set_cell = [&](int plane, int i, int value) {
+        if constexpr (kCellsInSmem) sts(s_state + 4u * uint32_t(plane * kCells + i * G), uint32_t(value));
+        else cell_regs[plane][i] = value;
+      };
+      uint32_t litw[NW], rows[CPL];
 #pragma unroll
       for (int i = 0; i < CPL; ++i) {
         const int c = i * G + sub;
-        // pick_geometry() only chooses CPL cells per lane when H*W > 32 * CPL / 2: the first CPL / 2 rows are full
+        // pick_geometry() only chooses CPL cells per lane when the rows before the last one are full
         const bool in_grid = i < kFullRows || c < HW;
-        fires[i] = in_grid ? fires_row[c] : 0;
-        inten[i] = in_grid ? inten_row[c] : 0;
-        fuel[i] = in_grid ? fuel_row[c] : 0;
+        const int f = in_grid ? fires_row[c] : 0;
+        set_cell(0, i, f);
+        set_cell(1, i, in_grid ? inten_row[c] : 0);
+        set_cell(2, i, in_grid ? fuel_row[c] : 0);
+        rows[i] = __ballot_sync(kFullMask, f > 0);
       }
       float supp = 0.f, cap = 0.f;
       int equip = 0;
@@ -247,10 +269,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         equip = min(max(io.equipment[agent_at], 0), E - 1);
       }
 
-      uint32_t litw[NW], rows[CPL];
       int n_before = 0;  // tasks published by the previous launch: rows / mask bytes beyond are already padding
-#pragma unroll
-      for (int i = 0; i < CPL; ++i) rows[i] = __ballot_sync(kFullMask, fires[i] > 0);
       assemble_words<G, CPL, NW>(rows, litw, group_base, group_mask, half_selector);
 #pragma unroll
       for (int w = 0; w < NW; ++w) n_before += __popc(litw[w]);
@@ -450,7 +469,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
           const float attack = __uint_as_float(lds(s_attack + 4u * uint32_t(i * G + sub)));
-          int f = fires[i], it = inten[i];
+          int f = cell(0, i), it = cell(1, i);
           // fire_increase.py:43-95
           const bool burning = f > 0 && it > 0;
           const float diff = __fadd_rn(f > 0 ? float(f) : 0.f, -attack);
@@ -466,13 +485,13 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           const bool shrink = met && uf[3 * i + 1] < prob_down;
           it -= shrink ? 1 : 0;
           const bool put = shrink && it <= 0;
-          if (burned) fuel[i] = max(fuel[i] - 1, 0);  // burn-out clamps the fuel (fire_increase.py:90) ...
-          if (put) fuel[i] -= 1;                      // ... putting out does not (fire_decrease.py:75)
+          if (burned) set_cell(2, i, max(cell(2, i) - 1, 0));  // burn-out clamps the fuel (fire_increase.py:90) ...
+          if (put) set_cell(2, i, cell(2, i) - 1);             // ... putting out does not (fire_decrease.py:75)
           if (burned || put) f = -f;
           burned_bits |= uint32_t(burned) << i;
           putout_bits |= uint32_t(put) << i;
-          fires[i] = f;
-          inten[i] = it;
+          if (!kCellsInSmem || burned || put) set_cell(0, i, f);
+          if (!kCellsInSmem || grow || shrink) set_cell(1, i, it);
           rows[i] = __ballot_sync(kFullMask, burning && !burned && !put);
         }
         assemble_words<G, CPL, NW>(rows, burnw, group_base, group_mask, half_selector);
@@ -483,8 +502,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         // ---------------------------------------------------------------- fire spread (fire_spreads.py:33-59)
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
-          int f = fires[i], it = inten[i];
-          const bool unlit = f < 0 && it == 0 && (!use_fuel || fuel[i] > 0);
+          int f = cell(0, i), it = cell(1, i);
+          const bool unlit = f < 0 && it == 0 && (!use_fuel || cell(2, i) > 0);
           if (__any_sync(kFullMask, unlit)) {
             // burning neighbours of cell c as bit c of four words: N = cell c-W, W = c-1, E = c+1, S = c+W
             const int w = i / RPW;  // the word holding this row
@@ -521,10 +540,16 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             if (unlit && uf[3 * i + 2] < prob) {
               f = -f;
               it = int(lds_const(s_cell + 4u * (kIgnitionOff + i * G)));
+              if (kCellsInSmem) {
+                set_cell(0, i, f);
+                set_cell(1, i, it);
+              }
             }
           }
-          fires[i] = f;
-          inten[i] = it;
+          if (!kCellsInSmem) {
+            set_cell(0, i, f);
+            set_cell(1, i, it);
+          }
           rows[i] = __ballot_sync(kFullMask, f > 0);
         }
         assemble_words<G, CPL, NW>(rows, litw, group_base, group_mask, half_selector);
@@ -571,13 +596,13 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         if (use_fuel && __any_sync(kFullMask, dead)) {
           int my_fuel = 0;
 #pragma unroll
-          for (int i = 0; i < CPL; ++i) my_fuel += fuel[i];
+          for (int i = 0; i < CPL; ++i) my_fuel += cell(2, i);
           const int fuel_left = group_sum<G>(my_fuel);  // every lane takes part: no short-circuit around the shuffles
           dead = dead && fuel_left <= 0;
         }
         if (dead) {  // wildfire.py:570
 #pragma unroll
-          for (int i = 0; i < CPL; ++i) fires[i] = 0;
+          for (int i = 0; i < CPL; ++i) set_cell(0, i, 0);
 #pragma unroll
           for (int w = 0; w < NW; ++w) litw[w] = 0;
         }
@@ -635,7 +660,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             sts(s_tasks + 4u * uint32_t(t), fighters[i]);
             if (valid)
               task_rows[cell_row + uint32_t(t)] = make_int4(int(lds_const(s_cell + 4u * (kYOff + i * G))), int(lds_const(s_cell + 4u * (kXOff + i * G))),
-                                      fires[i], inten[i]);
+                                      cell(0, i), cell(1, i));
           }
         }
       }
@@ -653,6 +678,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       if (valid) {
         // action mask [A, mask_stride] bytes indexed by env-local task.  Lane (slot, agent) = (sub / A, sub % A) packs
         // the agent's bit of four consecutive tasks into one 4-byte store; G / A such quads are done per pass.
+        // (A flattened (quad, agent) item list keeps more lanes busy but measured 3 % slower: this form has
+        // loop-invariant shift amounts and row addresses.)
         const uint32_t mask_at = (uint32_t(env) * uint32_t(A) + uint32_t(mask_agent)) * uint32_t(mask_words_row);
         uint32_t* const mask_words = reinterpret_cast<uint32_t*>(io.action_mask);
         for (int first = 0; first < quads; first += mask_slots) {
@@ -677,9 +704,9 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           for (int i = 0; i < CPL; ++i) {
             const int c = i * G + sub;
             if (i < kFullRows || c < HW) {
-              fires_row[c] = fires[i];
-              inten_row[c] = inten[i];
-              fuel_row[c] = fuel[i];
+              fires_row[c] = cell(0, i);
+              inten_row[c] = cell(1, i);
+              fuel_row[c] = cell(2, i);
             }
           }
           if (is_agent) {
@@ -759,11 +786,13 @@ __global__ void wildfire_sample_kernel(const FrzWildfireParams p, const FrzWildf
   }
 }
 
-// Largest grid (in cells) that is stepped by half-warp groups.  Measured on B200 at 262 144 envs: 5x6 / 6 agents 269 us
-// -> 178 us and 7x8 / 5 agents 310 -> 245 us with half-warp groups, but 10x10 / 10 agents (7 cells per lane, register
-// spills at 80 registers) 115 -> 124 us: beyond 4 cells per lane the 32-lane geometry wins.
+// Largest grid (in cells) that is stepped by half-warp groups (when the agents fit 16 lanes).  Measured on B200:
+//   5x6 / 6 agents (262 144 envs)    32-lane groups 269 us   half-warp groups 178 us
+//   7x8 / 5 agents (262 144 envs)                   310 us                    245 us
+//   10x10 / 10 agents (65 536 envs)                 116 us                    110 us with the cell state in shared
+//                                                   memory (124 us with 7 cells per lane in registers: spills)
 #ifndef FRZ_WF_HALF_WARP_CELLS
-#define FRZ_WF_HALF_WARP_CELLS 64
+#define FRZ_WF_HALF_WARP_CELLS 128
 #endif
 
 struct Geometry {
@@ -834,7 +863,7 @@ int launch_variant(const FrzWildfireParams& caller_params, const FrzWildfireBuff
   static size_t cached_smem = ~size_t(0);
   const int groups_per_cta = (kThreads / 32) * (32 / G);
   const size_t smem = (size_t(static_smem_words(G * CPL, p.num_agents, p.num_equipment_states)) +
-                       size_t(groups_per_cta) * group_smem_words(G * CPL)) * sizeof(uint32_t);
+                       size_t(groups_per_cta) * group_smem_words(G, CPL)) * sizeof(uint32_t);
   auto kernel = wildfire_step_kernel<G, CPL, MODE, INJECTED>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
@@ -893,7 +922,11 @@ int dispatch(const FrzWildfireParams* p, const FrzWildfireBuffers* io, int B, in
       case 1: return launch_step<16, 1>(*p, *io, B, mode, s);
       case 2: return launch_step<16, 2>(*p, *io, B, mode, s);
       case 3: return launch_step<16, 3>(*p, *io, B, mode, s);
-      default: return launch_step<16, 4>(*p, *io, B, mode, s);
+      case 4: return launch_step<16, 4>(*p, *io, B, mode, s);
+      case 5: return launch_step<16, 5>(*p, *io, B, mode, s);
+      case 6: return launch_step<16, 6>(*p, *io, B, mode, s);
+      case 7: return launch_step<16, 7>(*p, *io, B, mode, s);
+      default: return launch_step<16, 8>(*p, *io, B, mode, s);
     }
   }
   switch (g.cells_per_lane) {
