@@ -92,10 +92,17 @@ __device__ __forceinline__ void assemble_words(const uint32_t (&rows)[CPL], uint
     for (int i = 0; i < CPL; ++i) words[i] = rows[i];
   } else if constexpr (CPL == 1) {
     words[0] = (rows[0] >> group_base) & group_mask;
-  } else {
-    static_assert(G == 16, "multi-row sub-warp groups are 16 lanes wide");
+  } else if constexpr (G == 16) {
 #pragma unroll
     for (int w = 0; w < NW; ++w) words[w] = __byte_perm(rows[2 * w], (2 * w + 1 < CPL) ? rows[(2 * w + 1 < CPL) ? 2 * w + 1 : 0] : 0u, half_selector);
+  } else {  // G == 8: up to four rows share the one word; byte i = the group's byte of row ballot i
+    static_assert(G == 8 && CPL <= 4, "8-lane groups hold at most 4 cells per lane");
+    const uint32_t lo = __byte_perm(rows[0], rows[1], half_selector);  // bytes 0, 1
+    const uint32_t hi = CPL > 2 ? __byte_perm(rows[2], rows[CPL - 1], half_selector) : 0u;
+    uint32_t word = __byte_perm(lo, hi, 0x5410);
+    if (CPL == 2) word &= 0xffffu;
+    if (CPL == 3) word &= 0xffffffu;
+    words[0] = word;
   }
 }
 
@@ -138,7 +145,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   // Philox words per lane: two per cell (a cell consumes either its fire-increase or its fire-decrease draw, never
   // both, so the two events share a word; the other word is the spread draw) and four per agent
   constexpr int kCalls = (2 * CPL + 3) / 4;
-  static_assert(G == 32 || G == 16 || CPL == 1, "8-lane groups hold one cell per lane");
+  static_assert(G == 32 || G == 16 || CPL <= 4, "8-lane groups hold at most four cells per lane (one mask word)");
   constexpr int RPW = (CPL == 1) ? 1 : 32 / G;  // grid rows (of G cells) per 32-bit word
   // rows that the geometry choice guarantees to lie entirely inside the grid (pick_geometry())
   constexpr int kFullRows = (G == 32) ? CPL / 2 : (CPL - 1);
@@ -157,7 +164,10 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   asm volatile("" : "+r"(lane_bit));
   // this lane's cell of row i is bit (i % RPW) * G + sub of word i / RPW
   const auto row_bit = [&](int i) { return lane_bit << ((i % RPW) * G); };
-  const uint32_t half_selector = (group_base & 16) ? 0x7632u : 0x5410u;
+  // byte-permute selector that pulls this group's slice out of two row ballots (assemble_words): halfword g for
+  // 16-lane groups, byte g for 8-lane groups
+  const uint32_t half_selector = (G == 16) ? ((group_base & 16) ? 0x7632u : 0x5410u)
+                                           : (uint32_t(group_base >> 3) | ((4u + uint32_t(group_base >> 3)) << 4));
   const int H = p.height, W = p.width, HW = H * W;
   const int A = p.num_agents;
   const int E = p.num_equipment_states;
@@ -787,7 +797,8 @@ __global__ void wildfire_sample_kernel(const FrzWildfireParams p, const FrzWildf
 }
 
 // Largest grid (in cells) that is stepped by half-warp groups (when the agents fit 16 lanes).  Measured on B200:
-//   5x6 / 6 agents (262 144 envs)    32-lane groups 269 us   half-warp groups 178 us
+//   3x3 / 3 agents (524 288 envs)    16-lane groups 258 us   8-lane groups, 2 cells per lane 157 us
+//   5x6 / 6 agents (262 144 envs)    32-lane groups 269 us   half-warp groups 178 us   8-lane groups 159 us
 //   7x8 / 5 agents (262 144 envs)                   310 us                    245 us
 //   10x10 / 10 agents (65 536 envs)                 116 us                    110 us with the cell state in shared
 //                                                   memory (124 us with 7 cells per lane in registers: spills)
@@ -805,6 +816,7 @@ bool pick_geometry(const FrzWildfireParams& p, Geometry* g) {
   // Half-warp groups for small and mid-size grids whose agents fit 16 lanes: two environments share every instruction
   // of the agent phase, and ceil(H*W / 16) cells per lane waste fewer lanes than a power-of-two count over 32 lanes.
   if (HW <= 8 && A <= 8) *g = {8, 1};
+  else if (HW <= 32 && A <= 8) *g = {8, (HW + 7) / 8};  // four environments per warp
   else if (HW <= 16 && A <= 16) *g = {16, 1};
   else if (HW <= FRZ_WF_HALF_WARP_CELLS && A <= 16) *g = {16, (HW + 15) / 16};
   else if (HW <= 32) *g = {32, 1};
@@ -916,7 +928,14 @@ int dispatch(const FrzWildfireParams* p, const FrzWildfireBuffers* io, int B, in
     }
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (g.group == 8) return launch_step<8, 1>(*p, *io, B, mode, s);
+  if (g.group == 8) {
+    switch (g.cells_per_lane) {
+      case 1: return launch_step<8, 1>(*p, *io, B, mode, s);
+      case 2: return launch_step<8, 2>(*p, *io, B, mode, s);
+      case 3: return launch_step<8, 3>(*p, *io, B, mode, s);
+      default: return launch_step<8, 4>(*p, *io, B, mode, s);
+    }
+  }
   if (g.group == 16) {
     switch (g.cells_per_lane) {
       case 1: return launch_step<16, 1>(*p, *io, B, mode, s);
