@@ -14,8 +14,9 @@ One JSON line is printed by rank 0:
   value         whole-job env-steps/s, inputs resident in HBM, [sample_actions -> step] captured in one CUDA graph
   roofline      the step kernel alone: algorithmic bytes per launch / CUDA-event duration of the
                 launch, against the measured HBM copy bandwidth of MEASURED_PEAKS.json
-  e2e           the same metric through the public Parallel API with HOST buffers: pinned actions H2D + step +
-                rewards / dones D2H + stream sync, every step
+  e2e           the same metric through the public Parallel API with HOST buffers (``parallel_env.step_host``):
+                page-locked actions H2D + step + rewards / dones D2H + stream sync, every step; upload, kernel and
+                download are pipelined over slices of the batch inside frz_<domain>_step_host
   cpu_baseline  the CPU oracle port of the same workload on the box's host cores (bounded sample, rank 0, N=1)
 ``--impl reference`` times the CPU oracle port (the reference's algorithm restated in numpy -- the Python reference
 and its uninstallable dependencies cannot travel to the GPU box) on all host cores and prints the same line shape.
@@ -352,18 +353,13 @@ def run_engine(args):
         host_actions[t].copy_(raw._actions, non_blocking=True)
         raw.step_all()
     torch.cuda.synchronize(device)
-    host_rewards = torch.empty((B, agents), dtype=torch.float32).pin_memory()
-    host_done = torch.empty((2, B), dtype=torch.uint8).pin_memory()
-    staged = raw._actions  # the engine's own device action table: the H2D copy lands where the kernel reads
     env.reset(seed=SEED)
 
     def e2e_step(t):
-        staged.copy_(host_actions[t], non_blocking=True)  # H2D from pinned memory
-        env.step(staged)  # public API: Parallel step
-        host_rewards.copy_(raw._rewards, non_blocking=True)  # D2H of the step's results
-        host_done[0].copy_(raw._terminated, non_blocking=True)
-        host_done[1].copy_(raw._truncated, non_blocking=True)
-        torch.cuda.current_stream(device).synchronize()  # the caller reads rewards / dones before acting again
+        # public API with HOST buffers: page-locked actions in, page-locked rewards / terminated / truncated out; the
+        # upload, the fused step and the download are pipelined over slices of the batch (frz_<domain>_step_host);
+        # the call returns after the stream synchronised, i.e. when the caller can read the results
+        return env.step_host(host_actions[t], args.host_chunks or None)
 
     for t in range(W):
         e2e_step(t)
@@ -375,8 +371,12 @@ def run_engine(args):
     barrier()
     e2e_ms = max_over_ranks(start.elapsed_time(stop))
     e2e_value = world * B * K / (e2e_ms * 1e-3)
-    h2d = staged.numel() * 4
-    d2h = host_rewards.numel() * 4 + host_done.numel()
+    host_rewards, host_done = raw._host_state['rewards'], raw._host_state['done']  # what the last step_host returned
+    host_terminated, host_truncated = host_done[0], host_done[1]
+    h2d = host_actions[0].numel() * 4
+    d2h = host_rewards.numel() * 4 + host_terminated.numel() + host_truncated.numel()
+    # the host copies are the device's results (checked outside the timed region)
+    assert torch.equal(host_rewards, raw._rewards.cpu()) and torch.equal(host_terminated, raw._terminated.cpu())
 
     # ---- episode statistics: the only collective, off the step path
     stats = all_reduce_statistics(episode_statistics(raw._cumulative, raw.terminated, raw.truncated, raw.num_moves))
@@ -403,7 +403,8 @@ def run_engine(args):
                 'mean_tasks_per_env': mean_tasks,
             },
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': e2e_ms / K},
+                    'ms_per_step': e2e_ms / K, 'api': 'parallel_env.step_host (frz_<domain>_step_host)',
+                    'slices': raw._host_state['chunks']},
             'gpu_launches': 2 * K,
             'clocks': clocks.summary(),
             'stats': {'env_steps_executed': float(stats[0]), 'terminated_envs': float(stats[1]),
@@ -429,6 +430,8 @@ def main():
     parser.add_argument('--impl', default='engine', choices=['engine', 'reference'])
     parser.add_argument('--workload', default='wildfire_c4', choices=sorted(WORKLOADS))
     parser.add_argument('--parallel-envs', type=int, default=0, help='override parallel_envs per GPU')
+    parser.add_argument('--host-chunks', type=int, default=0,
+                        help='slices of the pipelined host-buffer step of the e2e leg (0 = the engine\'s default)')
     args = parser.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -127,6 +127,15 @@ class RideshareBuffers(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in _RS_POINTERS]
 
 
+MAX_CHUNKS = 16
+
+
+class HostStep(C.Structure):
+    """FrzHostStep: page-locked host buffers, per-slice control blocks (device) and streams of the pipelined host step."""
+    _fields_ = [('actions', C.c_void_p), ('rewards', C.c_void_p), ('terminated', C.c_void_p), ('truncated', C.c_void_p),
+                ('chunk_controls', C.c_void_p), ('streams', C.POINTER(C.c_void_p)), ('chunks', C.c_int32)]
+
+
 _lib = None
 
 
@@ -159,8 +168,12 @@ def library() -> C.CDLL:
                                         C.c_void_p]
     lib.frz_rideshare_sample_actions.argtypes = [C.POINTER(RideshareParams), C.POINTER(RideshareBuffers), C.c_int32,
                                                  C.c_uint64, C.c_void_p]
-    if lib.frz_version() != 1:
-        raise RuntimeError(f'libfrz.so ABI version {lib.frz_version()} != 1; rebuild the library')
+    for name, params, buffers in (('frz_wildfire_step_host', WildfireParams, WildfireBuffers),
+                                  ('frz_cyber_step_host', CyberParams, CyberBuffers),
+                                  ('frz_rideshare_step_host', RideshareParams, RideshareBuffers)):
+        getattr(lib, name).argtypes = [C.POINTER(params), C.POINTER(buffers), C.c_int32, C.POINTER(HostStep), C.c_void_p]
+    if lib.frz_version() != 2:
+        raise RuntimeError(f'libfrz.so ABI version {lib.frz_version()} != 2; rebuild the library')
     _lib = lib
     return lib
 

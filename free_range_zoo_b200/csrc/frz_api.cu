@@ -33,7 +33,59 @@ __global__ void control_init_kernel(FrzControl* control, uint64_t seed) {
   control->agents_with_tasks_acc = 0;
   control->agents_with_tasks = 0;
 }
+
+// every chunk block starts the step as a copy of the main block (seed, step counter, published flags)
+__global__ void control_broadcast_kernel(const FrzControl* main_block, FrzControl* chunk_blocks, int count) {
+  const int i = threadIdx.x;
+  if (i >= count) return;
+  FrzControl block = *main_block;
+  block.ctas_done = 0;
+  block.alive_acc = 0;
+  block.agents_with_tasks_acc = 0;
+  block.error_word = 0;
+  chunk_blocks[i] = block;
+}
+
+// the main block ends the step with what one launch over the whole batch would have published: the flags are ORs over
+// the slices, the step counter is the slices' common one
+__global__ void control_merge_kernel(FrzControl* main_block, const FrzControl* chunk_blocks, int count) {
+  unsigned alive = 0, agents = 0, faults = 0;
+  for (int i = 0; i < count; ++i) {
+    alive |= chunk_blocks[i].alive;
+    agents |= chunk_blocks[i].agents_with_tasks;
+    faults |= chunk_blocks[i].error_word;
+  }
+  if (chunk_blocks[0].step != main_block->step) {  // the slices stepped (no "every environment is done" early-out)
+    main_block->alive = alive;
+    main_block->agents_with_tasks = agents;
+    main_block->step = chunk_blocks[0].step;
+  }
+  main_block->error_word |= faults;
+}
 }  // namespace
+
+int control_broadcast(FrzControl* main_block, FrzControl* chunk_blocks, int count, cudaStream_t stream) {
+  control_broadcast_kernel<<<1, 32, 0, stream>>>(main_block, chunk_blocks, count);
+  return check_launch("control_broadcast_kernel");
+}
+
+int control_merge(FrzControl* main_block, FrzControl* chunk_blocks, int count, cudaStream_t stream) {
+  control_merge_kernel<<<1, 1, 0, stream>>>(main_block, chunk_blocks, count);
+  return check_launch("control_merge_kernel");
+}
+
+cudaEvent_t* pipeline_events() {
+  static thread_local cudaEvent_t events[1 + FRZ_MAX_CHUNKS];
+  static thread_local int device_of_events = -1;
+  int device = 0;
+  cudaGetDevice(&device);
+  if (device_of_events != device) {  // (events belong to the device they were created on)
+    for (auto& event : events)
+      if (cudaEventCreateWithFlags(&event, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    device_of_events = device;
+  }
+  return events;
+}
 
 }  // namespace frz
 

@@ -21,6 +21,12 @@ inline int persistent_grid(int work_ctas, int ctas_per_sm) {
   return work_ctas < cap ? (work_ctas < 1 ? 1 : work_ctas) : cap;
 }
 
+// pipelined host-buffer step (frz_host.cuh): chunk control blocks <- main block before the slices run, main block <-
+// OR of the chunks' published flags afterwards; events[0] = "broadcast done", events[1 + i] = "slice i done"
+int control_broadcast(FrzControl* main_block, FrzControl* chunk_blocks, int count, cudaStream_t stream);
+int control_merge(FrzControl* main_block, FrzControl* chunk_blocks, int count, cudaStream_t stream);
+cudaEvent_t* pipeline_events();
+
 // ---------------------------------------------------------------------------------------------- Philox4x32-10
 
 struct Philox {

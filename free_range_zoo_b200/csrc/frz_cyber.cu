@@ -14,6 +14,7 @@
 // tabulated on the host with the reference's own torch.tanh and indexed here by the set of agents acting on the node,
 // so the threshold compare is bit-exact.
 #include "frz_common.cuh"
+#include "frz_host.cuh"
 
 namespace frz {
 namespace {
@@ -577,6 +578,48 @@ int frz_cyber_step(const FrzCyberParams* params, const FrzCyberBuffers* io, int3
     return FRZ_ERR_NULL;
   }
   return frz::cyber_launch(params, io, parallel_envs, frz::kCyStep, stream);
+}
+
+int frz_cyber_step_host(const FrzCyberParams* params, const FrzCyberBuffers* io, int32_t parallel_envs,
+                        const FrzHostStep* host, void* stream) {
+  const int status = frz::cyber_validate(params, io, parallel_envs, "frz_cyber_step_host");
+  if (status != FRZ_OK) return status;
+  if (io->actions == nullptr || io->rewards == nullptr) {
+    frz::set_error("frz_cyber_step_host: actions / rewards is NULL");
+    return FRZ_ERR_NULL;
+  }
+  if (io->network_uniforms != nullptr || io->agent_uniforms != nullptr) {
+    frz::set_error("frz_cyber_step_host: injected uniforms are not supported on the pipelined host path");
+    return FRZ_ERR_UNSUPPORTED;
+  }
+  const size_t N = size_t(params->num_nodes), att = size_t(params->num_attackers), dfd = size_t(params->num_defenders);
+  const size_t n = att + dfd;
+  const frz::HostArrays arrays{io->actions, io->rewards, io->terminated, io->truncated, io->control, int(n)};
+  return frz::run_host_pipeline(
+      "frz_cyber_step_host", host, arrays, parallel_envs, static_cast<cudaStream_t>(stream),
+      [&](int first, int count, FrzControl* control, cudaStream_t slice_stream) {
+        FrzCyberParams p = *params;
+        p.env_offset += first;
+        FrzCyberBuffers slice = *io;
+        const size_t e = size_t(first);
+        slice.network_state += e * N;
+        slice.location += e * dfd;
+        slice.presence += e * n;
+        slice.actions += e * n * 2;
+        slice.rewards += e * n;
+        slice.cumulative_rewards += e * n;
+        slice.terminated += e;
+        slice.truncated += e;
+        slice.num_moves += e;
+        slice.env_task_count += e;
+        slice.agent_task_count += e * n;
+        slice.attacker_self += e * att * 2;
+        slice.defender_self += e * dfd * 3;
+        slice.task_obs += e * N * 2;
+        slice.monitored += e * dfd;
+        slice.control = control;
+        return frz::cyber_launch(&p, &slice, count, frz::kCyStep, slice_stream);
+      });
 }
 
 int frz_cyber_refresh(const FrzCyberParams* params, const FrzCyberBuffers* io, int32_t parallel_envs, void* stream) {

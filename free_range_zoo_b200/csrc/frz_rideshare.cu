@@ -10,9 +10,10 @@
 // owns rows passengers[b, 0:count[b]] (same relative order).
 //
 // Mapping: a group of G lanes (8, 16 or 32, chosen from the table capacity and the number of drivers) owns one
-// environment, so a warp steps 4, 2 or 1 environments at once.  The environment's rows live in shared memory for the
-// whole step (double buffered: cp.async streams the group's next environment while this one is stepped) and are
-// edited in place; lane s of the group looks after rows s, s+G, ... (PPL of them) and driver s.  Task lists, conflict
+// environment, so a warp steps 4, 2 or 1 environments at once.  The environment's rows are staged in shared memory
+// (cp.async) for the whole step and edited in place; lane s of the group looks after rows s, s+G, ... (PPL of them)
+// and driver s.  One table buffer per group: double buffering (prefetching the group's next environment) halved the
+// resident warps and measured 8 % slower than letting twice as many warps cover the staging latency.  Task lists, conflict
 // detection, compaction and the per-class "last row" reward quirk are ballots (cut to the group's lanes), match_any
 // and popcounts on 64-bit row masks.
 #include <algorithm>
@@ -20,6 +21,7 @@
 #include <math_constants.h>
 
 #include "frz_common.cuh"
+#include "frz_host.cuh"
 
 namespace frz {
 namespace {
@@ -81,7 +83,7 @@ __device__ __forceinline__ int group_min(int v) {
 template <int G, int PPL, int MODE>
 __global__ void __launch_bounds__(kRsThreads)
 rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid_constant__ FrzRideshareBuffers io,
-                      const int B, const uint8_t* __restrict__ entry_mask) {
+                      const int B, const uint8_t* __restrict__ entry_mask, const int batch_base) {
   static_assert(G * PPL <= 64, "row masks are 64 bits wide");
   extern __shared__ int smem[];
   constexpr int kGroupsPerWarp = 32 / G;
@@ -91,10 +93,9 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
   const int warp = __shfl_sync(kFullMask, int(threadIdx.x >> 5), 0);
   const int sub = lane % G, group_base = lane - sub;
   const int K = p.capacity, A = p.num_agents, S = p.schedule_rows;
-  // this group's two passenger-table buffers as 32-bit shared-window addresses: the rows of the environment being
-  // stepped are read / written as [table + 4 * index] while cp.async fills the other buffer with the next one's
+  // this group's passenger-table buffer as a 32-bit shared-window address: rows are read / written as [table + 4 * index]
   const uint32_t table_bytes = uint32_t(K * kCols) * 4u;
-  const uint32_t tables = shared_address(smem) + uint32_t(warp * kGroupsPerWarp + lane / G) * 2u * table_bytes;
+  const uint32_t table = shared_address(smem) + uint32_t(warp * kGroupsPerWarp + lane / G) * table_bytes;
   const uint64_t rows_below = (uint64_t(1) << sub) - 1u;  // rows before this lane's first row
   // byte-permute selector that pulls this group's slice out of two ballots (group_rows): 16-lane groups take halfword
   // g of each, 8-lane groups byte g of each
@@ -114,32 +115,17 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
 
   if (!skip) {
-    // software pipeline: while environment e is stepped, the rows of this group's next environment stream into the
-    // other buffer (cp.async, 4 bytes per lane per instruction: rows are 44 bytes, so nothing wider stays aligned)
     const int stride = gridDim.x * kGroupsPerCta;
-    const auto prefetch_rows = [&](int env, int rows, uint32_t buffer) {
-      const int* source = io.passengers + uint32_t(env) * uint32_t(K * kCols);
-      for (int i = sub; i < rows * kCols; i += G) cp_async_4(buffer + 4u * i, source + i);
-      cp_async_commit();
-    };
-    int env0 = (blockIdx.x * (kRsThreads / 32) + warp) * kGroupsPerWarp;  // first environment of this warp
-    int n_next = 0;
-    uint32_t parity = 0;
-    if (env0 < B) {
-      const int first = min(env0 + lane / G, B - 1);
-      n_next = min(io.env_task_count[first], K);
-      prefetch_rows(first, n_next, tables);
-    }
-    for (; env0 < B; env0 += stride) {
+    for (int env0 = (blockIdx.x * (kRsThreads / 32) + warp) * kGroupsPerWarp; env0 < B; env0 += stride) {
       const int env = min(env0 + lane / G, B - 1);
       const bool valid = env0 + lane / G < B;  // groups past the end of the batch replay the last environment, storing nothing
-      const uint32_t table = tables + parity * table_bytes;
       const uint32_t agent_at = uint32_t(env) * uint32_t(A) + uint32_t(sub);
-      const int n_before = n_next;
       int* const global_rows = io.passengers + uint32_t(env) * uint32_t(K * kCols);
-      const bool more = env0 + stride < B;
-      const int env_after = min(env0 + stride + lane / G, B - 1);
-      if (more) n_next = min(io.env_task_count[env_after], K);  // needed by the prefetch issued below
+      // stage the environment's live rows (cp.async, 4 bytes per lane per instruction: rows are 44 bytes, so nothing
+      // wider stays aligned); the other warps of the SM cover the latency
+      const int n_before = min(io.env_task_count[env], K);
+      for (int i = sub; i < n_before * kCols; i += G) cp_async_4(table + 4u * i, global_rows + i);
+      cp_async_commit();
 
       int agent_y = 0, agent_x = 0;
       int2 act = make_int2(0, -100);
@@ -328,7 +314,7 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
             if (enters) {
               if (slot < K) {
                 const uint32_t out = table + 4u * uint32_t(slot * kCols);
-                sts(out + 4u * cBatch, uint32_t(env));
+                sts(out + 4u * cBatch, uint32_t(batch_base + env));  // index in the caller's batch (a slice starts at batch_base)
                 sts(out + 4u * cY, uint32_t(s[2]));
                 sts(out + 4u * cX, uint32_t(s[3]));
                 sts(out + 4u * cDestY, uint32_t(s[4]));
@@ -348,8 +334,6 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         }
       }
       __syncwarp();
-      if (more) prefetch_rows(env_after, n_next, tables + (parity ^ 1u) * table_bytes);
-      parity ^= 1u;
 
       // ------------------------------------------------------------------ the new table
       load_rows(n_rows);
@@ -560,37 +544,43 @@ int rideshare_validate(const FrzRideshareParams* p, const FrzRideshareBuffers* i
 // Lanes per environment and rows per lane: the smallest group that holds the drivers and keeps at most 4 rows per lane.
 template <int G, int PPL, int MODE>
 int rideshare_launch_geometry(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, cudaStream_t s,
-                              const uint8_t* entry_mask) {
+                              const uint8_t* entry_mask, int batch_base) {
   constexpr int groups_per_cta = (kRsThreads / 32) * (32 / G);
-  const size_t smem = size_t(groups_per_cta) * 2 * p->capacity * kCols * sizeof(int);  // two table buffers per group
+  const size_t smem = size_t(groups_per_cta) * p->capacity * kCols * sizeof(int);  // one table buffer per group
   auto kernel = rideshare_step_kernel<G, PPL, MODE>;
   if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
     return check_launch("rideshare shared memory");
-  const int ctas_per_sm = int(std::min<size_t>(12, std::max<size_t>(1, (200 * 1024) / (smem + 1024))));
+  static int ctas_per_sm = 0;  // per instantiation; re-queried when the table capacity (hence the footprint) changes
+  static size_t cached_smem = ~size_t(0);
+  if (smem != cached_smem) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kRsThreads, smem);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    cached_smem = smem;
+  }
   const int grid = persistent_grid((B + groups_per_cta - 1) / groups_per_cta, ctas_per_sm);
-  kernel<<<grid, kRsThreads, smem, s>>>(*p, *io, B, entry_mask);
+  kernel<<<grid, kRsThreads, smem, s>>>(*p, *io, B, entry_mask, batch_base);
   return check_launch("rideshare_step_kernel");
 }
 
 template <int MODE>
 int rideshare_launch_mode(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, cudaStream_t s,
-                          const uint8_t* entry_mask) {
+                          const uint8_t* entry_mask, int batch_base) {
   const int K = p->capacity, A = p->num_agents;
-  if (A <= 8 && K <= 8) return rideshare_launch_geometry<8, 1, MODE>(p, io, B, s, entry_mask);
-  if (A <= 8 && K <= 16) return rideshare_launch_geometry<8, 2, MODE>(p, io, B, s, entry_mask);
-  if (A <= 8 && K <= 32) return rideshare_launch_geometry<8, 4, MODE>(p, io, B, s, entry_mask);
-  if (A <= 16 && K <= 32) return rideshare_launch_geometry<16, 2, MODE>(p, io, B, s, entry_mask);
-  if (A <= 16) return rideshare_launch_geometry<16, 4, MODE>(p, io, B, s, entry_mask);
-  if (K <= 32) return rideshare_launch_geometry<32, 1, MODE>(p, io, B, s, entry_mask);
-  return rideshare_launch_geometry<32, 2, MODE>(p, io, B, s, entry_mask);
+  if (A <= 8 && K <= 8) return rideshare_launch_geometry<8, 1, MODE>(p, io, B, s, entry_mask, batch_base);
+  if (A <= 8 && K <= 16) return rideshare_launch_geometry<8, 2, MODE>(p, io, B, s, entry_mask, batch_base);
+  if (A <= 8 && K <= 32) return rideshare_launch_geometry<8, 4, MODE>(p, io, B, s, entry_mask, batch_base);
+  if (A <= 16 && K <= 32) return rideshare_launch_geometry<16, 2, MODE>(p, io, B, s, entry_mask, batch_base);
+  if (A <= 16) return rideshare_launch_geometry<16, 4, MODE>(p, io, B, s, entry_mask, batch_base);
+  if (K <= 32) return rideshare_launch_geometry<32, 1, MODE>(p, io, B, s, entry_mask, batch_base);
+  return rideshare_launch_geometry<32, 2, MODE>(p, io, B, s, entry_mask, batch_base);
 }
 
 int rideshare_launch(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, int mode, void* stream,
-                     const uint8_t* entry_mask = nullptr) {
+                     const uint8_t* entry_mask = nullptr, int batch_base = 0) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (mode == kRsStep) return rideshare_launch_mode<kRsStep>(p, io, B, s, entry_mask);
-  if (mode == kRsRefresh) return rideshare_launch_mode<kRsRefresh>(p, io, B, s, entry_mask);
-  return rideshare_launch_mode<kRsEntryRefresh>(p, io, B, s, entry_mask);
+  if (mode == kRsStep) return rideshare_launch_mode<kRsStep>(p, io, B, s, entry_mask, batch_base);
+  if (mode == kRsRefresh) return rideshare_launch_mode<kRsRefresh>(p, io, B, s, entry_mask, batch_base);
+  return rideshare_launch_mode<kRsEntryRefresh>(p, io, B, s, entry_mask, batch_base);
 }
 
 }  // namespace
@@ -607,6 +597,41 @@ int frz_rideshare_step(const FrzRideshareParams* params, const FrzRideshareBuffe
     return FRZ_ERR_NULL;
   }
   return frz::rideshare_launch(params, io, parallel_envs, frz::kRsStep, stream);
+}
+
+int frz_rideshare_step_host(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
+                            const FrzHostStep* host, void* stream) {
+  const int status = frz::rideshare_validate(params, io, parallel_envs, "frz_rideshare_step_host");
+  if (status != FRZ_OK) return status;
+  if (io->actions == nullptr || io->rewards == nullptr) {
+    frz::set_error("frz_rideshare_step_host: actions / rewards is NULL");
+    return FRZ_ERR_NULL;
+  }
+  const size_t A = size_t(params->num_agents), K = size_t(params->capacity);
+  const frz::HostArrays arrays{io->actions, io->rewards, io->terminated, io->truncated, io->control, params->num_agents};
+  return frz::run_host_pipeline(
+      "frz_rideshare_step_host", host, arrays, parallel_envs, static_cast<cudaStream_t>(stream),
+      [&](int first, int count, FrzControl* control, cudaStream_t slice_stream) {
+        FrzRideshareParams p = *params;
+        p.env_offset += first;  // schedule rows name global environment indices
+        FrzRideshareBuffers slice = *io;
+        const size_t e = size_t(first);
+        slice.agents += e * A * 2;
+        slice.passengers += e * K * FRZ_RS_PASSENGER_COLUMNS;
+        slice.actions += e * A * 2;
+        slice.rewards += e * A;
+        slice.cumulative_rewards += e * A;
+        slice.terminated += e;
+        slice.truncated += e;
+        slice.num_moves += e;
+        slice.env_task_count += e;
+        slice.agent_task_count += e * A;
+        slice.task_mask += e * A * K;
+        slice.self_obs += e * A * 4;
+        slice.task_obs += e * K * FRZ_RS_TASK_COLUMNS;
+        slice.control = control;
+        return frz::rideshare_launch(&p, &slice, count, frz::kRsStep, slice_stream, nullptr, first);
+      });
 }
 
 int frz_rideshare_refresh(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,

@@ -13,14 +13,22 @@
 // attacks reach the cells through width-G shuffles in agent order (fp32 sums associate exactly as the reference's
 // per-agent loop), per-environment reductions are shuffles / popcounts.  All global traffic is issued as contiguous
 // per-environment rows ([B, H*W] / [B, A] layouts) so a warp's loads and stores coalesce.
+#include <cmath>
 #include <math_constants.h>
 
 #include "frz_common.cuh"
+#include "frz_host.cuh"
 
+#ifndef FRZ_BISECT
+#define FRZ_BISECT 0
+#endif
 namespace frz {
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef FRZ_WF_THREADS
+#define FRZ_WF_THREADS 256
+#endif
+constexpr int kThreads = FRZ_WF_THREADS;
 enum Mode { kStep = 0, kRefresh = 1 };
 
 template <int NW>
@@ -193,7 +201,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   asm volatile("" : "+r"(s_attack));
   const uint32_t s_tasks = s_base + 4u * uint32_t(tasks_off);
   const uint32_t s_range = s_base + 4u * uint32_t(range_off);
-  const uint32_t s_state = s_tasks + 4u * uint32_t(kCells + sub);  // this lane's column of the group's state planes
+  uint32_t* const my_state = smem + tasks_off + kCells + sub;  // this lane's column of the group's state planes
 
   for (int i = threadIdx.x; i < E * kCells; i += kThreads) {
     const int e = i / kCells, c = i - e * kCells;
@@ -229,7 +237,6 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   const float agent_yf = is_agent ? float(p.agent_y[sub]) : 0.f;
   const float agent_xf = is_agent ? float(p.agent_x[sub]) : 0.f;
   const int burned_state = p.num_fire_states - 1, almost_state = p.num_fire_states - 2;
-  const int mask_agent = sub % A, mask_slot = sub / A, mask_slots = G / A;  // action-mask builder: lane -> (slot, agent)
 
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
 
@@ -251,12 +258,14 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       // cell state of this lane's cells: plane 0 fires, 1 intensity, 2 fuel -- in registers, or (large half-warp
       // geometries, where 3 * CPL registers per lane would spill) in the group's shared-memory planes
       int cell_regs[3][kCellsInSmem ? 1 : CPL] = {};
+      // (the planes are private to the lane -- it only ever touches its own column -- so these are plain accesses the
+      // compiler may batch and interleave across the unrolled cell loops; the cross-lane tables go through lds / sts)
       const auto cell = [&](int plane, int i) -> int {
-        if constexpr (kCellsInSmem) return int(lds(s_state + 4u * uint32_t(plane * kCells + i * G)));
+        if constexpr (kCellsInSmem) return int(my_state[plane * kCells + i * G]);
         else return cell_regs[plane][i];
       };
       const auto set_cell = [&](int plane, int i, int value) {
-        if constexpr (kCellsInSmem) sts(s_state + 4u * uint32_t(plane * kCells + i * G), uint32_t(value));
+        if constexpr (kCellsInSmem) my_state[plane * kCells + i * G] = uint32_t(value);
         else cell_regs[plane][i] = value;
       };
       uint32_t litw[NW], rows[CPL];
@@ -362,65 +371,94 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         // ---------------------------------------------------------------- randomness
         // Agent events: 0 suppressant decrease, 1 equipment, 2 refill, 3 capacity pick, 4 tank switch (wildfire.py:492-513).
         // "decrease" needs a fight action and "refill" a refill action, so in Philox mode events 0 and 2 share one draw.
-        float ua[5], uf[3 * CPL];  // uf[3*i + event]: fire increase, fire decrease, fire spread of this lane's cell i
+        // Field events per cell: fire increase / decrease (a cell consumes one or the other: one word) and spread.
+        // Philox words of a lane, bits[4 * call + j].  Split layout (production path, when it needs no extra call):
+        // the first half of the calls feeds increase / decrease (word i = cell i), the second half -- generated only
+        // after that loop, so its words are not alive across it -- feeds the spread; used by the geometries that keep
+        // the cell state in shared memory (register-bound; measured 6 % slower on the others).  Otherwise the words of
+        // cell i are 2i and 2i + 1 and every call is made up front.
+        constexpr bool kSplit = !INJECTED && kCellsInSmem && 2 * ((CPL + 3) / 4) == kCalls;
+        constexpr int kCallsA = kSplit ? kCalls / 2 : kCalls;
+        const auto grow_word = [](int i) { return kSplit ? i : 2 * i; };
+        const auto spread_word = [](int i) { return kSplit ? 4 * kCallsA + i : 2 * i + 1; };
+        float ua[5], uf[INJECTED ? 3 * CPL : 1];  // uf[3*i + event]: injected / pre-converted uniforms (parity mode)
+        uint32_t bits[4 * kCalls];
         const bool inject_agent = INJECTED && io.agent_uniforms != nullptr;
         const bool inject_field = INJECTED && io.field_uniforms != nullptr;
-        if (inject_agent) {
+        const uint32_t env_lo = uint32_t(p.env_offset + e), env_hi = uint32_t(uint64_t(p.env_offset + e) >> 32);
+        const uint32_t step_lo = uint32_t(step), step_hi = uint32_t(step >> 32) ^ env_hi;
+        const auto draw = [&](int first_call, int last_call) {
 #pragma unroll
-          for (int ev = 0; ev < 5; ++ev)
-            ua[ev] = is_agent ? io.agent_uniforms[(size_t(ev) * B + e) * A + sub] : 1.f;
-        }
-        if (inject_field) {
-          const size_t plane = size_t(B) * HW;
-#pragma unroll
-          for (int i = 0; i < CPL; ++i) {
-            const int c = i * G + sub;
-#pragma unroll
-            for (int ev = 0; ev < 3; ++ev) uf[3 * i + ev] = c < HW ? io.field_uniforms[ev * plane + cell_row + c] : 1.f;
-          }
-        }
-        if (!inject_field || !inject_agent) {
-          const uint32_t env_lo = uint32_t(p.env_offset + e), env_hi = uint32_t(uint64_t(p.env_offset + e) >> 32);
-          const uint32_t step_lo = uint32_t(step), step_hi = uint32_t(step >> 32) ^ env_hi;
-          uint32_t bits[4 * kCalls];
-#pragma unroll
-          for (int k = 0; k < kCalls; ++k) {
+          for (int k = first_call; k < last_call; ++k) {
             const uint4 r = philox(env_lo, step_lo, uint32_t(k * G + sub), step_hi);
             bits[4 * k] = r.x;
             bits[4 * k + 1] = r.y;
             bits[4 * k + 2] = r.z;
             bits[4 * k + 3] = r.w;
           }
-          if (!inject_field) {
+        };
+        if (!inject_field || !inject_agent) draw(0, kCallsA);
+        if constexpr (INJECTED) {
+          const size_t plane = size_t(B) * HW;
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-              uf[3 * i] = uf[3 * i + 1] = u01(bits[2 * i]);
-              uf[3 * i + 2] = u01(bits[2 * i + 1]);
+          for (int i = 0; i < CPL; ++i) {
+            const int c = i * G + sub;
+            if (inject_field) {
+#pragma unroll
+              for (int ev = 0; ev < 3; ++ev) uf[3 * i + ev] = c < HW ? io.field_uniforms[ev * plane + cell_row + c] : 1.f;
+            } else {
+              uf[3 * i] = uf[3 * i + 1] = u01(bits[grow_word(i)]);
+              uf[3 * i + 2] = u01(bits[spread_word(i)]);
             }
           }
-          if (!inject_agent) {
+        }
+#if FRZ_BISECT == 2
+        float ufx[2 * CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) { ufx[2 * i] = u01(bits[grow_word(i)]); ufx[2 * i + 1] = u01(bits[spread_word(i)]); }
+#endif
+        const auto field_uniform = [&](int i, int event) -> float {  // event: 0 increase, 1 decrease, 2 spread
+          if constexpr (INJECTED) return uf[3 * i + event];
+#if FRZ_BISECT == 2
+          else return ufx[event == 2 ? 2 * i + 1 : 2 * i];
+#else
+          else return u01(bits[event == 2 ? spread_word(i) : grow_word(i)]);
+#endif
+        };
+
+        // ---------------------------------------------------------------- agent randomness + transitions
+        // Independent of the fire transitions (they only meet again in update_actions), so the phase runs before them
+        // or -- in the split Philox layout, where the agents' words exist only after the second half of the calls --
+        // after the spread.
+        const auto agent_phase = [&]() {
+          if (inject_agent) {
+#pragma unroll
+            for (int ev = 0; ev < 5; ++ev)
+              ua[ev] = is_agent ? io.agent_uniforms[(size_t(ev) * B + e) * A + sub] : 1.f;
+          } else {
             uint32_t words[4];
             bool have_words = false;
-            // Words this lane never consumes: 4 * kCalls - 2 * CPL at the end of its last call (kSpareOwn: 0 or 2), and
-            // the two words of its last cell when that cell lies outside the grid ("spare lanes": the top lanes of the
-            // group).  When the host found enough spare lanes for this grid, the agents' four words come from there
-            // instead of from a Philox call of their own.
+            // Words this lane never consumes: 4 * kCalls - 2 * CPL of its own (kSpareOwn: 0 or 2), and the two words of
+            // its last cell when that cell lies outside the grid ("spare lanes": the top lanes of the group).  When the
+            // host found enough spare lanes for this grid, the agents' four words come from there instead of from a
+            // Philox call of their own.
             constexpr int kSpareOwn = 4 * kCalls - 2 * CPL;
+            constexpr int kOwnA = kSplit ? CPL : 2 * CPL, kOwnB = kSplit ? 4 * kCallsA + CPL : 2 * CPL + 1;
             if constexpr (CPL > 1) {
               if (derived.spare_lanes_feed_agents) {
                 const int first = group_base + ((G - 1 - sub) & (G - 1)), second = group_base + ((G - 1 - A - sub) & (G - 1));
-                const uint32_t a = __shfl_sync(kFullMask, bits[2 * CPL - 2], first);
-                const uint32_t b = __shfl_sync(kFullMask, bits[2 * CPL - 1], first);
+                const uint32_t a = __shfl_sync(kFullMask, bits[grow_word(CPL - 1)], first);
+                const uint32_t b = __shfl_sync(kFullMask, bits[spread_word(CPL - 1)], first);
                 if constexpr (kSpareOwn == 2) {
-                  words[0] = bits[2 * CPL];
-                  words[1] = bits[2 * CPL + 1];
+                  words[0] = bits[kOwnA < 4 * kCalls ? kOwnA : 0];
+                  words[1] = bits[kOwnB < 4 * kCalls ? kOwnB : 0];
                   words[2] = a;
                   words[3] = b;
                 } else {
                   words[0] = a;
                   words[1] = b;
-                  words[2] = __shfl_sync(kFullMask, bits[2 * CPL - 2], second);
-                  words[3] = __shfl_sync(kFullMask, bits[2 * CPL - 1], second);
+                  words[2] = __shfl_sync(kFullMask, bits[grow_word(CPL - 1)], second);
+                  words[3] = __shfl_sync(kFullMask, bits[spread_word(CPL - 1)], second);
                 }
                 have_words = true;
               }
@@ -437,39 +475,48 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             ua[3] = u01(words[2]);
             ua[4] = u01(words[3]);
           }
-        }
 
-        // ---------------------------------------------------------------- agent transitions
-        // (the host folded the StochasticConfiguration switches into the thresholds: 2 = always, -1 = never)
-        // suppressant_decrease.py:34-63
-        const bool decrease = user && ua[0] < p.p_suppressant_decrease;
-        supp = fmaxf(decrease ? __fadd_rn(supp, -1.f) : supp, 0.f);
-        // equipment.py:42-77 -- masks from the pre-update state, one uniform for all three tests
-        {
-          const bool pristine = equip == E - 1, damaged = equip == 0;
-          const bool wearable = pristine || !damaged;  // pristine | intermediate
-          const bool repairs = damaged && ua[1] < p.p_repair;
-          const bool critical = pristine && ua[1] < p.p_critical;
-          const bool degrades = wearable && ua[1] < p.p_degrade && !critical;
-          if (repairs) equip = E - 1;
-          if (critical) equip = 0;
-          if (degrades) equip -= 1;
-        }
-        // suppressant_refill.py:43-74 -- bonus of the equipment state AFTER its transition
-        const bool increased = refill && ua[2] < p.p_refill;
-        if (increased) supp = __fadd_rn(cap, p.equipment_capacity_bonus[max(equip, 0)]);
-        // capacity.py:39-66 -- bucketize(right=False): first i with r <= cum[i]
-        if (__any_sync(kFullMask, increased)) {
-          int pick = p.num_capacities - 1;
-          for (int i = p.num_capacities - 1; i >= 0; --i)
-            if (ua[3] <= p.capacity_cum[i]) pick = i;
-          const bool switches = increased && ua[4] < p.p_tank_switch;
-          const float extra = __fadd_rn(supp, -cap);
-          if (switches) {
-            cap = p.capacity_value[pick];
-            supp = __fadd_rn(cap, extra);
+          // agent transitions (the host folded the StochasticConfiguration switches into the thresholds: 2 = always, -1 = never)
+          // suppressant_decrease.py:34-63
+          const bool decrease = user && ua[0] < p.p_suppressant_decrease;
+          supp = fmaxf(decrease ? __fadd_rn(supp, -1.f) : supp, 0.f);
+          // equipment.py:42-77 -- masks from the pre-update state, one uniform for all three tests
+          {
+            const bool pristine = equip == E - 1, damaged = equip == 0;
+            const bool wearable = pristine || !damaged;  // pristine | intermediate
+            const bool repairs = damaged && ua[1] < p.p_repair;
+            const bool critical = pristine && ua[1] < p.p_critical;
+            const bool degrades = wearable && ua[1] < p.p_degrade && !critical;
+            if (repairs) equip = E - 1;
+            if (critical) equip = 0;
+            if (degrades) equip -= 1;
           }
-        }
+          // suppressant_refill.py:43-74 -- bonus of the equipment state AFTER its transition
+          const bool increased = refill && ua[2] < p.p_refill;
+          if (increased) supp = __fadd_rn(cap, p.equipment_capacity_bonus[max(equip, 0)]);
+          // capacity.py:39-66 -- bucketize(right=False): first i with r <= cum[i]
+          if (__any_sync(kFullMask, increased)) {
+            // first i with r <= cum[i] == the number of entries below r (cum is non-decreasing; the host pads the unused
+            // entries with +inf), capped at the last capacity like the reference's default
+#if FRZ_BISECT == 1
+            int pick = p.num_capacities - 1;
+            for (int i = p.num_capacities - 1; i >= 0; --i)
+              if (ua[3] <= p.capacity_cum[i]) pick = i;
+#else
+            int pick = 0;
+#pragma unroll
+            for (int i = 0; i < FRZ_MAX_CAPACITIES; ++i) pick += ua[3] > p.capacity_cum[i] ? 1 : 0;
+            pick = min(pick, p.num_capacities - 1);
+#endif
+            const bool switches = increased && ua[4] < p.p_tank_switch;
+            const float extra = __fadd_rn(supp, -cap);
+            if (switches) {
+              cap = p.capacity_value[pick];
+              supp = __fadd_rn(cap, extra);
+            }
+          }
+        };
+        if constexpr (!kSplit) agent_phase();
 
         // ---------------------------------------------------------------- fire increase + decrease per cell
         // p.p_increase / p.p_burnout arrive clamped (and 1 when the increase is deterministic); a deterministic
@@ -484,7 +531,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           const bool burning = f > 0 && it > 0;
           const float diff = __fadd_rn(f > 0 ? float(f) : 0.f, -attack);
           const bool unmet = burning && diff > 0.f;
-          const bool grow = unmet && uf[3 * i] < (it == almost_state ? p.p_burnout : p.p_increase);
+          const bool grow = unmet && field_uniform(i, 0) < (it == almost_state ? p.p_burnout : p.p_increase);
           it += grow ? 1 : 0;
           const bool burned = grow && it >= burned_state;
           // fire_decrease.py:36-80 sees the post-increase state: a cell that just burned out is no longer lit, any other
@@ -492,7 +539,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           // rounded separately like the reference's two aten ops
           const bool met = burning && !burned && diff <= 0.f;
           const float prob_down = fminf(fmaxf(__fadd_rn(p.p_decrease, __fmul_rn(-diff, p.decrease_bonus)), 0.f), 1.f);
-          const bool shrink = met && uf[3 * i + 1] < prob_down;
+          const bool shrink = met && field_uniform(i, 1) < prob_down;
           it -= shrink ? 1 : 0;
           const bool put = shrink && it <= 0;
           if (burned) set_cell(2, i, max(cell(2, i) - 1, 0));  // burn-out clamps the fuel (fire_increase.py:90) ...
@@ -510,6 +557,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         if (user) sts(s_attack + 4u * uint32_t(target), 0u);
 
         // ---------------------------------------------------------------- fire spread (fire_spreads.py:33-59)
+        if constexpr (kSplit) draw(kCallsA, kCalls);
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
           int f = cell(0, i), it = cell(1, i);
@@ -525,17 +573,11 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             if (W < 32) {
               north = __funnelshift_l(prev, cur, W);
               south = __funnelshift_r(cur, next, W);
-            } else {  // a row is at least one word: the neighbour word is up to NW-1 words away
-              north = 0u;
-              south = 0u;
+            } else {  // a row is at least one word: the neighbour word is W / 32 (+ 1) words away
               const int q = W >> 5, r = W & 31;
-#pragma unroll
-              for (int v = 0; v < NW; ++v) {
-                if (v == w - q) north |= r ? (burnw[v] << r) : burnw[v];
-                if (r && v == w - q - 1) north |= burnw[v] >> (32 - r);
-                if (v == w + q) south |= r ? (burnw[v] >> r) : burnw[v];
-                if (r && v == w + q + 1) south |= burnw[v] << (32 - r);
-              }
+              const auto word_or_zero = [&](int v) { return (v >= 0 && v < NW) ? word_at<NW>(burnw, v) : 0u; };
+              north = __funnelshift_l(word_or_zero(w - q - 1), word_or_zero(w - q), r);
+              south = __funnelshift_r(word_or_zero(w + q), word_or_zero(w + q + 1), r);
             }
             const uint32_t west = __funnelshift_l(prev, cur, 1) & derived.west_ok[w];
             const uint32_t east = __funnelshift_r(cur, next, 1) & derived.east_ok[w];
@@ -547,7 +589,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             if (east & my_bit) prob = __fadd_rn(prob, p.spread_lut[4]);
             if (south & my_bit) prob = __fadd_rn(prob, p.spread_lut[8]);
             prob = __fadd_rn(prob, p.p_random_ignition);
-            if (unlit && uf[3 * i + 2] < prob) {
+            if (unlit && field_uniform(i, 2) < prob) {
               f = -f;
               it = int(lds_const(s_cell + 4u * (kIgnitionOff + i * G)));
               if (kCellsInSmem) {
@@ -563,6 +605,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           rows[i] = __ballot_sync(kFullMask, f > 0);
         }
         assemble_words<G, CPL, NW>(rows, litw, group_base, group_mask, half_selector);
+
+        if constexpr (kSplit) agent_phase();
 
         // ---------------------------------------------------------------- rewards + termination (wildfire.py:534-582)
         // burn-outs and put-outs are rare: count them with one reduction each and only then look at which cells
@@ -676,6 +720,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       }
       // tasks of the previous launch that no longer exist: their rows go back to padding, their mask bytes to zero
       const int quads = (n_rows + 3) >> 2;
+      const int quads_warp = __reduce_max_sync(kFullMask, quads);  // (every lane of the warp: not under `valid`)
       for (int first = n_lit; first < 4 * quads; first += G) {
         const int t = first + sub;
         if (t < 4 * quads) {
@@ -686,19 +731,37 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       __syncwarp();
 
       if (valid) {
-        // action mask [A, mask_stride] bytes indexed by env-local task.  Lane (slot, agent) = (sub / A, sub % A) packs
-        // the agent's bit of four consecutive tasks into one 4-byte store; G / A such quads are done per pass.
-        // (A flattened (quad, agent) item list keeps more lanes busy but measured 3 % slower: this form has
-        // loop-invariant shift amounts and row addresses.)
-        const uint32_t mask_at = (uint32_t(env) * uint32_t(A) + uint32_t(mask_agent)) * uint32_t(mask_words_row);
+        // action mask [A, mask_stride] bytes indexed by env-local task, four tasks per 4-byte store.  The group's
+        // lanes are cut into (agent slot, task quad): `span` = the smallest power of two that holds the quads of
+        // every environment of the warp (at most G), G / span agent slots.  A lane packs the fighter sets of its
+        // four tasks into byte planes (byte j of plane k = agents 8k .. 8k+7 of task 4q+j) and emits
+        // (plane >> (a & 7)) & 0x01010101 for the agents a = slot, slot + slots, ... -- lanes of one slot write
+        // consecutive words of one agent's row, and few tasks mean many slots, i.e. few passes over the agents.
         uint32_t* const mask_words = reinterpret_cast<uint32_t*>(io.action_mask);
-        for (int first = 0; first < quads; first += mask_slots) {
-          const int q = first + mask_slot;
-          if (mask_slot < mask_slots && q < quads) {
+        const uint32_t mask_env = uint32_t(env) * uint32_t(A) * uint32_t(mask_words_row);
+        const int span_shift = min(32 - __clz(max(quads_warp, 1) - 1), (G == 32) ? 5 : (G == 16) ? 4 : 3);
+        const int span = 1 << span_shift, slots = G >> span_shift;
+        const int slot = sub >> span_shift, quad_in_span = sub & (span - 1);
+        for (int first = 0; first < quads; first += span) {
+          const int q = first + quad_in_span;
+          if (q < quads) {
             const uint4 m = lds_v4(s_tasks + 16u * uint32_t(q));
-            const uint32_t lo = __byte_perm(m.x >> mask_agent, m.y >> mask_agent, 0x0040);
-            const uint32_t hi = __byte_perm(m.z >> mask_agent, m.w >> mask_agent, 0x0040);
-            mask_words[mask_at + uint32_t(q)] = __byte_perm(lo, hi, 0x5410) & 0x01010101u;
+            uint32_t planes[FRZ_MAX_AGENTS / 8];
+#pragma unroll
+            for (int k = 0; k < FRZ_MAX_AGENTS / 8; ++k) {
+              planes[k] = 0u;
+              if (k * 8 < A) {
+                const uint32_t lo = __byte_perm(m.x, m.y, uint32_t(k | ((4 + k) << 4)));
+                const uint32_t hi = __byte_perm(m.z, m.w, uint32_t(k | ((4 + k) << 4)));
+                planes[k] = __byte_perm(lo, hi, 0x5410);
+              }
+            }
+            for (int a = slot; a < A; a += slots) {
+              uint32_t plane = planes[0];
+#pragma unroll
+              for (int k = 1; k < FRZ_MAX_AGENTS / 8; ++k) plane = (a >> 3) == k ? planes[k] : plane;
+              mask_words[mask_env + uint32_t(a * mask_words_row + q)] = (plane >> (a & 7)) & 0x01010101u;
+            }
           }
         }
 
@@ -847,6 +910,7 @@ void fold_configuration(const FrzWildfireParams& in, int group, int cells_per_la
     out->p_decrease = 2.f;
     out->decrease_bonus = 0.f;
   }
+  for (int i = in.num_capacities; i < FRZ_MAX_CAPACITIES; ++i) out->capacity_cum[i] = INFINITY;  // capacity.py:52
   const int H = in.height, W = in.width, HW = H * W;
   for (int w = 0; w < FRZ_MAX_CELLS / 32; ++w) derived->west_ok[w] = derived->east_ok[w] = 0u;
   for (int c = 0; c < HW; ++c) {
@@ -967,6 +1031,50 @@ int frz_wildfire_step(const FrzWildfireParams* params, const FrzWildfireBuffers*
     return FRZ_ERR_NULL;
   }
   return frz::dispatch(params, io, parallel_envs, frz::kStep, stream);
+}
+
+int frz_wildfire_step_host(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
+                           const FrzHostStep* host, void* stream) {
+  if (params == nullptr || io == nullptr || io->actions == nullptr || io->control == nullptr || io->rewards == nullptr) {
+    frz::set_error("frz_wildfire_step_host: NULL params / buffers");
+    return FRZ_ERR_NULL;
+  }
+  if (io->field_uniforms != nullptr || io->agent_uniforms != nullptr) {
+    frz::set_error("frz_wildfire_step_host: injected uniforms are not supported on the pipelined host path");
+    return FRZ_ERR_UNSUPPORTED;
+  }
+  const size_t HW = size_t(params->height) * params->width, A = size_t(params->num_agents);
+  const frz::HostArrays arrays{io->actions, io->rewards, io->terminated, io->truncated, io->control, params->num_agents};
+  return frz::run_host_pipeline(
+      "frz_wildfire_step_host", host, arrays, parallel_envs, static_cast<cudaStream_t>(stream),
+      [&](int first, int count, FrzControl* control, cudaStream_t slice_stream) {
+        FrzWildfireParams p = *params;
+        p.env_offset += first;  // the Philox counters are keyed by the global environment index
+        FrzWildfireBuffers slice = *io;
+        const size_t e = size_t(first);
+        slice.fires += e * HW;
+        slice.intensity += e * HW;
+        slice.fuel += e * HW;
+        slice.suppressants += e * A;
+        slice.capacity += e * A;
+        slice.equipment += e * A;
+        slice.actions += e * A * 2;
+        slice.rewards += e * A;
+        slice.cumulative_rewards += e * A;
+        slice.terminated += e;
+        slice.truncated += e;
+        slice.num_moves += e;
+        slice.num_burnouts += e;
+        slice.burnouts += e;
+        slice.putouts += e;
+        slice.env_task_count += e;
+        slice.agent_task_count += e * A;
+        slice.action_mask += e * A * size_t(io->mask_stride);
+        slice.self_obs += e * A * 4;
+        slice.task_obs += e * HW * 4;
+        slice.control = control;
+        return frz::dispatch(&p, &slice, count, frz::kStep, slice_stream);
+      });
 }
 
 int frz_wildfire_refresh(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,

@@ -181,6 +181,9 @@ class raw_env(BatchedAECEnv):
                                                 self._stream()), 'frz_rideshare_step')
         return self._reward_views, self.terminations, self.infos
 
+    def _host_entry(self):
+        return self._lib.frz_rideshare_step_host
+
     def _refresh(self) -> None:
         _lib.check(self._lib.frz_rideshare_refresh(ctypes.byref(self._params), ctypes.byref(self._io),
                                                    self.parallel_envs, self._stream()), 'frz_rideshare_refresh')

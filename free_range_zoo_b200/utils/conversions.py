@@ -67,6 +67,15 @@ class batched_aec_to_batched_parallel_wrapper:
         self.agents = env.agents
         return self.observe(), env.rewards, env.terminations, env.truncations, env.infos
 
+    def step_host(self, host_actions: torch.Tensor, chunks=None):
+        """Parallel step with HOST buffers: page-locked int32 ``[B, A, 2]`` actions in, page-locked ``(rewards [B, A],
+        terminated [B], truncated [B])`` out; upload, step and download are pipelined over slices of the batch
+        (``BatchedAECEnv.step_host``).  Observations stay on the device: ``observe()``."""
+        env = self.aec_env.unwrapped
+        results = env.step_host(host_actions, chunks)
+        self.agents = env.agents
+        return results
+
     def observe(self) -> Dict[str, Any]:
         return {agent: self.aec_env.observe(agent) for agent in self.aec_env.agents}
 

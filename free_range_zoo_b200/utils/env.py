@@ -263,6 +263,67 @@ class BatchedAECEnv(ABC):
             self._actions.copy_(actions, non_blocking=True)
         self._advance()
 
+    # ------------------------------------------------------------------------------------------ host-buffer step
+
+    def _host_entry(self):
+        """The domain's ``frz_<domain>_step_host`` entry point."""
+        raise NotImplementedError
+
+    def _host_pipeline(self, chunks: Optional[int]):
+        """Page-locked result buffers, per-slice control blocks and streams of ``step_host`` (built once per slicing)."""
+        B, A = self.parallel_envs, len(self.possible_agents)
+        if chunks is None:  # one slice per 16 384 environments: below that the copies are too short to be worth hiding
+            chunks = max(1, min(8, B // 16384))
+        chunks = max(1, min(int(chunks), _lib.MAX_CHUNKS))
+        cached = getattr(self, '_host_state', None)
+        if cached is not None and cached['chunks'] == chunks:
+            return cached
+        state = dict(
+            chunks=chunks,
+            rewards=torch.empty((B, A), dtype=torch.float32).pin_memory(),
+            done=torch.empty((2, B), dtype=torch.uint8).pin_memory(),
+            controls=torch.zeros((chunks, 8), dtype=torch.int64, device=self.device),
+            streams=[torch.cuda.Stream(self.device) for _ in range(chunks)],
+        )
+        handles = (ctypes.c_void_p * chunks)(*[stream.cuda_stream for stream in state['streams']])
+        block = _lib.HostStep()
+        block.rewards = state['rewards'].data_ptr()
+        block.terminated = state['done'][0].data_ptr()
+        block.truncated = state['done'][1].data_ptr()
+        block.chunk_controls = state['controls'].data_ptr()
+        block.streams = ctypes.cast(handles, ctypes.POINTER(ctypes.c_void_p))
+        block.chunks = chunks
+        state.update(handles=handles, block=block)
+        self._host_state = state
+        return state
+
+    @torch.no_grad()
+    def step_host(self, host_actions: torch.Tensor, chunks: Optional[int] = None
+                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """One environment step for callers that live on the host: ``host_actions`` is a page-locked int32
+        ``[B, A, 2]`` CPU tensor (agent order = ``env.agents``); returns page-locked CPU tensors ``(rewards f32 [B, A],
+        terminated bool [B], truncated bool [B])`` that are valid when the call returns and are overwritten by the next
+        ``step_host``.  Equivalent to copying the actions to the device, ``step_all`` and copying the results back,
+        but the batch is cut into ``chunks`` slices whose uploads, step kernels and downloads overlap
+        (``frz_<domain>_step_host``, include/frz.h); the results are bit-identical.  Observations, masks and counts stay
+        on the device as usual."""
+        B, A = self.parallel_envs, len(self.possible_agents)
+        if (host_actions.device.type != 'cpu' or host_actions.dtype != torch.int32 or not host_actions.is_contiguous()
+                or tuple(host_actions.shape) != (B, A, 2) or not host_actions.is_pinned()):
+            raise ValueError(f'step_host expects a page-locked contiguous int32 CPU tensor of shape {(B, A, 2)} '
+                             '(torch.empty(..., dtype=torch.int32).pin_memory())')
+        state = self._host_pipeline(chunks)
+        state['block'].actions = host_actions.data_ptr()
+        _lib.check(self._host_entry()(ctypes.byref(self._params), ctypes.byref(self._io), B,
+                                      ctypes.byref(state['block']), self._stream()), 'step_host')
+        torch.cuda.current_stream(self.device).synchronize()
+        self._mid_cycle = False
+        self._rebind_outputs()
+        if self.log_directory is not None:
+            self._log_environment()
+        done = state['done'].view(torch.bool)
+        return state['rewards'], done[0], done[1]
+
     def _advance(self) -> None:
         _, _, infos = self.step_environment()
         self.infos = infos

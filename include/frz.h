@@ -11,7 +11,8 @@
  *
  * Conventions
  *  - Plain C, no torch types.  Every pointer inside a Frz*Buffers struct is a DEVICE pointer owned by the caller
- *    (a torch tensor's data_ptr()); the library allocates nothing, frees nothing and keeps no device state.
+ *    (a torch tensor's data_ptr()); the library allocates nothing, frees nothing and keeps no device state (the one
+ *    exception: frz_<domain>_step_host creates a handful of timing-disabled CUDA events on first use).
  *  - Every call only enqueues work on the caller's cudaStream_t (passed as void*): no synchronisation, no
  *    allocation, no host read-back -> capturable in a CUDA graph.  The step counter / seed / done flags live in the
  *    device-side FrzControl block and are advanced by the kernels themselves, so graph replays need no new arguments.
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FRZ_ABI_VERSION 1
+#define FRZ_ABI_VERSION 2
 
 #define FRZ_MAX_AGENTS 32      /* agents per environment (one warp lane each) */
 #define FRZ_MAX_EQUIPMENT 8    /* wildfire equipment states */
@@ -309,6 +310,36 @@ int frz_rideshare_reset(const FrzRideshareParams* params, const FrzRideshareBuff
 /* Uniform random legal actions: task k with id = passenger state, or noop (spaces/actions.py:10-50). */
 int frz_rideshare_sample_actions(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
                                  uint64_t sampler_seed, void* stream);
+
+/* ----------------------------------------------------------------------------------------------- host-buffer step */
+
+/* The same step for callers whose actions live in HOST memory and who read rewards / done flags on the host -- what
+ * a rollout loop around the reference's `env.step(actions)` does when the policy runs on the CPU
+ * (utils/conversions.py:39-99: actions in, rewards / terminations / truncations out).  The batch is cut into `chunks`
+ * contiguous slices of environments; slice i is uploaded, stepped and downloaded on streams[i], so its kernel overlaps
+ * the upload of slice i+1 and the download of slice i-1 (PCIe is full duplex) instead of the three waiting for each
+ * other.  Environments are independent and the Philox counters are keyed by the global environment index, so the
+ * result is bit-identical to frz_<domain>_step on the whole batch.  The call only enqueues work: the main stream
+ * (last argument) waits for every slice before it continues, so synchronising it makes the host buffers readable.
+ * Injected uniforms (parity mode) are not supported on this path. */
+#define FRZ_MAX_CHUNKS 16
+
+typedef struct {
+  const int32_t* actions;      /* HOST, page-locked: [B, A, 2] */
+  float* rewards;              /* HOST, page-locked: [B, A] */
+  uint8_t* terminated;         /* HOST, page-locked: [B] */
+  uint8_t* truncated;          /* HOST, page-locked: [B] */
+  FrzControl* chunk_controls;  /* DEVICE scratch owned by the caller: `chunks` control blocks (64 bytes each) */
+  void* const* streams;        /* `chunks` cudaStream_t of the caller, one per slice */
+  int32_t chunks;              /* 1 .. FRZ_MAX_CHUNKS */
+} FrzHostStep;
+
+int frz_wildfire_step_host(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
+                           const FrzHostStep* host, void* stream);
+int frz_cyber_step_host(const FrzCyberParams* params, const FrzCyberBuffers* io, int32_t parallel_envs,
+                        const FrzHostStep* host, void* stream);
+int frz_rideshare_step_host(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
+                            const FrzHostStep* host, void* stream);
 
 /* ----------------------------------------------------------------------------------------------- common */
 

@@ -46,7 +46,8 @@ def child(args):
     raw.check_errors()
 
     # launch-overhead-free estimate for small batches: K x [sample, step] in one CUDA graph minus K x [sample]
-    def graph_time(with_step: bool, repeats: int = 20) -> float:
+    # (same window of the same seeded rollout as the eager measurement: reset, warm-up steps, `steps` timed steps)
+    def graph_time(with_step: bool, repeats: int = 10) -> float:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -55,14 +56,19 @@ def child(args):
                 if with_step:
                     raw.step_environment()
         graph.replay()
+        env.reset(seed=2026)
+        for _ in range(args.warmup):
+            raw.sample_actions(2026)
+            raw.step_environment()
         torch.cuda.synchronize()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        replays = max(1, args.steps // repeats)
         start.record()
-        for _ in range(5):
+        for _ in range(replays):
             graph.replay()
         stop.record()
         torch.cuda.synchronize()
-        return start.elapsed_time(stop) / (5 * repeats)
+        return start.elapsed_time(stop) / (replays * repeats)
 
     graph_us = 1e3 * (graph_time(True) - graph_time(False))
     bytes_per_env = bench.algorithmic_bytes(spec['domain'], raw, float(raw.environment_task_count.float().mean().item()))

@@ -17,6 +17,7 @@ STRUCTS = {
     'FrzCyberBuffers': _lib.CyberBuffers,
     'FrzRideshareParams': _lib.RideshareParams,
     'FrzRideshareBuffers': _lib.RideshareBuffers,
+    'FrzHostStep': _lib.HostStep,
 }
 
 
@@ -30,10 +31,10 @@ def lib():
 
 def test_every_declared_symbol_is_exported(lib):
     declared = _lib.exported_symbols()
-    assert len(declared) == 15  # 3 library-wide + 4 per domain
+    assert len(declared) == 18  # 3 library-wide + 5 per domain
     missing = [name for name in declared if not hasattr(lib, name)]
     assert not missing, missing
-    assert lib.frz_version() == 1
+    assert lib.frz_version() == 2
 
 
 def test_ctypes_mirrors_match_the_c_layout(tmp_path):
@@ -65,6 +66,10 @@ def test_null_and_shape_errors_are_reported_without_a_gpu(lib):
     assert lib.frz_cyber_step(ctypes.byref(cy_params), ctypes.byref(cy_io), 4, None) == 1
     rs_params, rs_io = _lib.RideshareParams(), _lib.RideshareBuffers()
     assert lib.frz_rideshare_step(ctypes.byref(rs_params), ctypes.byref(rs_io), 4, None) == 1
+    # the host-buffer step checks its own block too
+    assert lib.frz_wildfire_step_host(None, None, 4, None, None) == 1
+    assert lib.frz_cyber_step_host(ctypes.byref(cy_params), ctypes.byref(cy_io), 4, None, None) == 1
+    assert lib.frz_rideshare_step_host(ctypes.byref(rs_params), ctypes.byref(rs_io), 4, None, None) == 1
     # non-NULL pointers but an unsupported shape -> FRZ_ERR_SHAPE before anything is launched
     dummy = ctypes.create_string_buffer(64)
     address = ctypes.addressof(dummy)

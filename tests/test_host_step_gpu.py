@@ -1,0 +1,106 @@
+"""Pipelined host-buffer step (frz_<domain>_step_host, include/frz.h) == the whole-batch device step, bit for bit.
+
+Two engines with the same seed run the same rollout: one is stepped on the device (``step_all``), the other receives
+the same actions from page-locked host memory through ``step_host`` with the batch cut into slices.  Every state
+array, every published output and the control block must be identical; the host-side rewards / done flags must equal
+the device's.
+"""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from free_range_zoo_b200 import presets
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ('wildfire', 'wildfire_large', {}, 5000, 3),
+    ('wildfire', 'wildfire_3x3', {}, 4096, 4),
+    ('rideshare', 'rideshare_c2', {}, 4100, 3),
+    ('cybersecurity', 'cyber_c3', dict(show_bad_actions=False, partially_observable=True), 6000, 5),
+]
+
+
+def make(domain, preset, kwargs, B, max_steps):
+    module = importlib.import_module(f'free_range_zoo_b200.envs.{domain}_v0')
+    return module.parallel_env(parallel_envs=B, max_steps=max_steps, configuration=getattr(presets, preset)(),
+                               device=torch.device('cuda:0'), **kwargs)
+
+
+def device_arrays(raw):
+    """Every tensor the step kernel reads or writes, by the name it has in the Frz*Buffers struct."""
+    return {name: tensor for name, tensor in raw._bound.items()
+            if tensor is not None and not name.startswith('init_') and name != 'control'}
+
+
+@pytest.mark.parametrize('domain,preset,kwargs,B,chunks', CASES)
+def test_host_step_equals_device_step(domain, preset, kwargs, B, chunks):
+    steps = 12
+    device_env, host_env = make(domain, preset, kwargs, B, 10), make(domain, preset, kwargs, B, 10)
+    device_env.reset(seed=11)
+    host_env.reset(seed=11)
+    reference, raw = device_env.unwrapped, host_env.unwrapped
+    A = len(raw.agents)
+    host_actions = torch.empty((B, A, 2), dtype=torch.int32).pin_memory()
+    for t in range(steps):  # runs past max_steps: the "every environment is done" early-out is covered too
+        reference.sample_actions(5)
+        host_actions.copy_(reference._actions)
+        torch.cuda.synchronize()
+        reference.step_all()
+        rewards, terminated, truncated = host_env.step_host(host_actions, chunks)
+        assert rewards.is_pinned() and rewards.device.type == 'cpu'
+        assert torch.equal(rewards, reference._rewards.cpu()), f'step {t}'
+        assert torch.equal(terminated, reference.terminated.cpu()) and torch.equal(truncated, reference.truncated.cpu())
+        ours, theirs = device_arrays(raw), device_arrays(reference)
+        assert ours.keys() == theirs.keys()
+        for name in ours:
+            if domain == 'rideshare' and name == 'passengers':  # rows beyond the count are undefined
+                K = raw._capacity
+                valid = (torch.arange(K, device='cuda')[None, :] < raw.environment_task_count[:, None])
+                assert torch.equal(ours[name].view(B, K, -1)[valid], theirs[name].view(B, K, -1)[valid]), (name, t)
+            else:
+                assert torch.equal(ours[name], theirs[name]), (name, t)
+        mine, other = raw.control_block(), reference.control_block()
+        for field in ('seed', 'step', 'alive', 'agents_with_tasks', 'error_word'):
+            assert mine[field] == other[field], (field, t)
+    assert reference.control_block()['step'] == 10  # two calls after the horizon were no-ops, on both engines
+    raw.check_errors()
+
+
+def test_host_step_mixes_with_device_steps_and_graphs():
+    """The main control block stays authoritative: host steps, eager device steps and graph replays interleave."""
+    B = 3072
+    a, b = make('wildfire', 'wildfire_large', {}, B, 50), make('wildfire', 'wildfire_large', {}, B, 50)
+    a.reset(seed=4)
+    b.reset(seed=4)
+    ra, rb = a.unwrapped, b.unwrapped
+    host_actions = torch.empty((B, len(ra.agents), 2), dtype=torch.int32).pin_memory()
+    for t in range(9):
+        ra.sample_actions(9)
+        ra.step_all()
+        rb.sample_actions(9)
+        if t % 3 == 1:
+            host_actions.copy_(rb._actions)
+            torch.cuda.synchronize()
+            rb.step_host(host_actions, chunks=2)
+        else:
+            rb.step_all()
+        assert torch.equal(ra.state().fires, rb.state().fires) and torch.equal(ra._rewards, rb._rewards), t
+        assert torch.equal(ra._action_mask, rb._action_mask), t
+
+
+def test_host_step_rejects_unpinned_or_misshaped_actions():
+    env = make('cybersecurity', 'cyber_c3', {}, 64, 10)
+    env.reset(seed=0)
+    raw = env.unwrapped
+    A = len(raw.agents)
+    with pytest.raises(ValueError):
+        raw.step_host(torch.zeros((64, A, 2), dtype=torch.int32))  # not page-locked
+    with pytest.raises(ValueError):
+        raw.step_host(torch.zeros((64, A), dtype=torch.int32).pin_memory())
+    with pytest.raises(ValueError):
+        raw.step_host(torch.zeros((64, A, 2), dtype=torch.int64).pin_memory())
+    rewards, terminated, truncated = env.step_host(torch.full((64, A, 2), -1, dtype=torch.int32).pin_memory())
+    assert rewards.shape == (64, A) and terminated.shape == (64, ) and not np.asarray(truncated).any()
