@@ -75,7 +75,7 @@ int control_merge(FrzControl* main_block, FrzControl* chunk_blocks, int count, c
 }
 
 cudaEvent_t* pipeline_events() {
-  static thread_local cudaEvent_t events[1 + FRZ_MAX_CHUNKS];
+  static thread_local cudaEvent_t events[1 + 2 * FRZ_MAX_CHUNKS];
   static thread_local int device_of_events = -1;
   int device = 0;
   cudaGetDevice(&device);

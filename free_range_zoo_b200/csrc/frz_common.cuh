@@ -22,7 +22,8 @@ inline int persistent_grid(int work_ctas, int ctas_per_sm) {
 }
 
 // pipelined host-buffer step (frz_host.cuh): chunk control blocks <- main block before the slices run, main block <-
-// OR of the chunks' published flags afterwards; events[0] = "broadcast done", events[1 + i] = "slice i done"
+// OR of the chunks' published flags afterwards; events[0] = "broadcast done", then FRZ_MAX_CHUNKS "slice i uploaded"
+// and FRZ_MAX_CHUNKS "slice i finished"
 int control_broadcast(FrzControl* main_block, FrzControl* chunk_blocks, int count, cudaStream_t stream);
 int control_merge(FrzControl* main_block, FrzControl* chunk_blocks, int count, cudaStream_t stream);
 cudaEvent_t* pipeline_events();

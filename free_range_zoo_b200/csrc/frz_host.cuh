@@ -2,12 +2,21 @@
 //
 // The caller's actions are in page-locked host memory and it wants rewards / done flags back in host memory.  Done
 // naively that is upload -> kernel -> download, each waiting for the previous one, and on a PCIe-attached B200 the two
-// copies cost more than the fused step itself.  Here the batch is cut into contiguous slices of environments; slice i
-// runs [upload, step kernel, download] on its own stream, so the kernel of slice i overlaps the upload of slice i+1
-// and the download of slice i-1 (the link is full duplex), and the kernels of neighbouring slices fill each other's
-// tails.  Every slice has its own control block (seed / step counter / published flags): they are copies of the main
-// block when the step starts and are folded back into it when the last slice has finished, so the flags the next
-// launch reads ("every environment is done", "agent a has a task somewhere") stay batch-wide like the reference's.
+// copies cost more than the fused step itself (65 536 wildfire environments: 105 us up, 105 us kernel, 60 us down).
+// Here the batch is cut into contiguous slices of environments:
+//   streams[0]      uploads the slices' actions back to back (one DMA queue, no gaps) and signals each one,
+//   streams[i]      steps slice i as soon as its actions have arrived and downloads the slice's rewards,
+//   the main stream steps slice 0, waits for every slice, downloads the done flags and folds the control blocks.
+// So the kernel of slice i overlaps the upload of slice i+1 and the download of slice i-1 (the link is full duplex),
+// and the kernels of neighbouring slices fill each other's tails.  The first slice is half as long as the others: the
+// kernels cannot start before it has arrived.  Every slice has its own control block (seed / step counter / published
+// flags): they are copies of the main block when the step starts and are folded back into it at the end, so the flags
+// the next launch reads ("every environment is done", "agent a has a task somewhere") stay batch-wide like the
+// reference's.
+//
+// Measured alternative, not kept: letting the kernel read the actions from / write the results to the page-locked host
+// buffers in place (mapped memory) -- the 4- and 1-byte accesses become tiny PCIe transactions and the step gets slower
+// than with the DMA copies (profiles/README.md).
 #pragma once
 
 #include "frz_common.cuh"
@@ -42,30 +51,56 @@ int run_host_pipeline(const char* what, const FrzHostStep* host, const HostArray
   }
   cudaEvent_t* const events = pipeline_events();
   if (events == nullptr) return check_launch("pipeline events");
+  cudaEvent_t const started = events[0];
+  cudaEvent_t* const uploaded = events + 1;                   // [slice]
+  cudaEvent_t* const finished = events + 1 + FRZ_MAX_CHUNKS;  // [slice]
 
-  int per_slice = (B + host->chunks - 1) / host->chunks;
-  per_slice = (per_slice + kSliceAlignment - 1) / kSliceAlignment * kSliceAlignment;
-  const int slices = (B + per_slice - 1) / per_slice;
+  // slice boundaries: the first slice is half as long as the others
+  int bounds[FRZ_MAX_CHUNKS + 1];
+  int slices = 0;
+  {
+    const int chunks = host->chunks;
+    const long long halves = 2LL * chunks - 1;  // the batch in units of half a regular slice
+    bounds[0] = 0;
+    for (int i = 1; i <= chunks; ++i) {
+      long long end = (long long)B * (2LL * i - 1) / halves;
+      end = (end + kSliceAlignment - 1) / kSliceAlignment * kSliceAlignment;
+      if (end > B || i == chunks) end = B;
+      if (end > bounds[slices]) bounds[++slices] = int(end);
+    }
+  }
   const size_t A = size_t(device.agents);
 
   int status = control_broadcast(device.control, host->chunk_controls, slices, main_stream);
   if (status != FRZ_OK) return status;
-  cudaEventRecord(events[0], main_stream);
+  cudaEventRecord(started, main_stream);
+  cudaStream_t upload_stream = static_cast<cudaStream_t>(host->streams[0]);
+  cudaStreamWaitEvent(upload_stream, started, 0);
   for (int i = 0; i < slices; ++i) {
-    const int first = i * per_slice, count = (B - first < per_slice) ? B - first : per_slice;
-    cudaStream_t stream = static_cast<cudaStream_t>(host->streams[i]);
-    cudaStreamWaitEvent(stream, events[0], 0);
+    const int first = bounds[i], count = bounds[i + 1] - first;
     cudaMemcpyAsync(const_cast<int32_t*>(device.actions) + size_t(first) * A * 2, host->actions + size_t(first) * A * 2,
-                    size_t(count) * A * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
+                    size_t(count) * A * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, upload_stream);
+    cudaEventRecord(uploaded[i], upload_stream);
+  }
+  for (int i = 0; i < slices; ++i) {
+    const int first = bounds[i], count = bounds[i + 1] - first;
+    // (slice 0 runs on the main stream: streams[0] is busy uploading the later slices)
+    cudaStream_t stream = (i == 0) ? main_stream : static_cast<cudaStream_t>(host->streams[i]);
+    cudaStreamWaitEvent(stream, uploaded[i], 0);
     status = launch_slice(first, count, host->chunk_controls + i, stream);
     if (status != FRZ_OK) return status;
     cudaMemcpyAsync(host->rewards + size_t(first) * A, device.rewards + size_t(first) * A, size_t(count) * A * sizeof(float),
                     cudaMemcpyDeviceToHost, stream);
-    cudaMemcpyAsync(host->terminated + first, device.terminated + first, size_t(count), cudaMemcpyDeviceToHost, stream);
-    cudaMemcpyAsync(host->truncated + first, device.truncated + first, size_t(count), cudaMemcpyDeviceToHost, stream);
-    cudaEventRecord(events[1 + i], stream);
+    if (i > 0) cudaEventRecord(finished[i], stream);
   }
-  for (int i = 0; i < slices; ++i) cudaStreamWaitEvent(main_stream, events[1 + i], 0);
+  for (int i = 1; i < slices; ++i) cudaStreamWaitEvent(main_stream, finished[i], 0);
+  // the done flags of the whole batch: one download when the two arrays are adjacent on both sides
+  if (device.truncated == device.terminated + B && host->truncated == host->terminated + B) {
+    cudaMemcpyAsync(host->terminated, device.terminated, 2 * size_t(B), cudaMemcpyDeviceToHost, main_stream);
+  } else {
+    cudaMemcpyAsync(host->terminated, device.terminated, size_t(B), cudaMemcpyDeviceToHost, main_stream);
+    cudaMemcpyAsync(host->truncated, device.truncated, size_t(B), cudaMemcpyDeviceToHost, main_stream);
+  }
   status = control_merge(device.control, host->chunk_controls, slices, main_stream);
   if (status != FRZ_OK) return status;
   return check_launch(what);

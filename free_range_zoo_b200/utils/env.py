@@ -31,6 +31,10 @@ from free_range_zoo_b200.utils.containers import ObservationDict
 from free_range_zoo_b200.utils.selector import AgentSelector
 
 
+# most slices ``step_host`` cuts a batch into by default (measured on B200, profiles/README.md)
+HOST_STEP_MAX_DEFAULT_CHUNKS = 5
+
+
 def _seed_to_u64(seed) -> int:
     """Fold whatever ``reset(seed=...)`` received (None / int / list / tensor) into one 64-bit Philox key."""
     if seed is None:
@@ -272,16 +276,17 @@ class BatchedAECEnv(ABC):
     def _host_pipeline(self, chunks: Optional[int]):
         """Page-locked result buffers, per-slice control blocks and streams of ``step_host`` (built once per slicing)."""
         B, A = self.parallel_envs, len(self.possible_agents)
-        if chunks is None:  # one slice per 16 384 environments: below that the copies are too short to be worth hiding
-            chunks = max(1, min(8, B // 16384))
+        if chunks is None:  # slices of >= 12 288 environments: below that the copies are too short to be worth hiding
+            chunks = max(1, min(HOST_STEP_MAX_DEFAULT_CHUNKS, B // 12288))
         chunks = max(1, min(int(chunks), _lib.MAX_CHUNKS))
         cached = getattr(self, '_host_state', None)
         if cached is not None and cached['chunks'] == chunks:
             return cached
         state = dict(
             chunks=chunks,
-            rewards=torch.empty((B, A), dtype=torch.float32).pin_memory(),
-            done=torch.empty((2, B), dtype=torch.uint8).pin_memory(),
+            # (initialised from the device: a step that is skipped because every environment is done writes nothing)
+            rewards=self._rewards.cpu().pin_memory(),
+            done=torch.stack([self._terminated, self._truncated]).cpu().pin_memory(),
             controls=torch.zeros((chunks, 8), dtype=torch.int64, device=self.device),
             streams=[torch.cuda.Stream(self.device) for _ in range(chunks)],
         )
@@ -293,7 +298,8 @@ class BatchedAECEnv(ABC):
         block.chunk_controls = state['controls'].data_ptr()
         block.streams = ctypes.cast(handles, ctypes.POINTER(ctypes.c_void_p))
         block.chunks = chunks
-        state.update(handles=handles, block=block)
+        done = state['done'].view(torch.bool)
+        state.update(handles=handles, block=block, terminated=done[0], truncated=done[1])
         self._host_state = state
         return state
 
@@ -316,13 +322,13 @@ class BatchedAECEnv(ABC):
         state['block'].actions = host_actions.data_ptr()
         _lib.check(self._host_entry()(ctypes.byref(self._params), ctypes.byref(self._io), B,
                                       ctypes.byref(state['block']), self._stream()), 'step_host')
-        torch.cuda.current_stream(self.device).synchronize()
+        # host-side bookkeeping while the device works; the views do not depend on the data
         self._mid_cycle = False
         self._rebind_outputs()
         if self.log_directory is not None:
             self._log_environment()
-        done = state['done'].view(torch.bool)
-        return state['rewards'], done[0], done[1]
+        torch.cuda.current_stream(self.device).synchronize()
+        return state['rewards'], state['terminated'], state['truncated']
 
     def _advance(self) -> None:
         _, _, infos = self.step_environment()

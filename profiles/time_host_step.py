@@ -1,0 +1,86 @@
+"""Development helper: where the time of ``env.step_host`` goes (wall clock per step, 65 536-env wildfire C4).
+
+    python profiles/time_host_step.py [--workload wildfire_c4] [--steps 40]
+
+Prints, per slice count: the bare C-ABI call + stream sync, and the full Python ``step_host``.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+
+    import bench
+    from free_range_zoo_b200 import _lib, presets
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--workload', default='wildfire_c4')
+    parser.add_argument('--parallel-envs', type=int, default=0)
+    parser.add_argument('--steps', type=int, default=40)
+    args = parser.parse_args()
+    spec = bench.WORKLOADS[args.workload]
+    B = args.parallel_envs or spec['envs']
+    device = torch.device('cuda', 0)
+    module = importlib.import_module(f'free_range_zoo_b200.envs.{spec["domain"]}_v0')
+    env = module.parallel_env(parallel_envs=B, max_steps=1 << 30, device=device,
+                              configuration=getattr(presets, spec['preset'])(**spec.get('preset_kwargs', {})), **spec['kwargs'])
+    raw = env.unwrapped
+    A = len(raw.agents)
+    steps = args.steps
+    host_actions = torch.empty((steps + 5, B, A, 2), dtype=torch.int32).pin_memory()
+    env.reset(seed=1)
+    for t in range(steps + 5):
+        raw.sample_actions(3)
+        host_actions[t].copy_(raw._actions, non_blocking=True)
+        raw.step_all()
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream(device)
+    for chunks in (1, 2, 3, 4, 5, 6, 8):
+        row = {'chunks': chunks}
+        for mode in ('abi_only', 'step_host'):
+            env.reset(seed=1)
+            state = raw._host_pipeline(chunks)
+            times = []
+            for t in range(steps + 5):
+                torch.cuda.synchronize()
+                begin = time.perf_counter()
+                if mode == 'abi_only':
+                    state['block'].actions = host_actions[t].data_ptr()
+                    _lib.check(raw._host_entry()(ctypes.byref(raw._params), ctypes.byref(raw._io), B,
+                                                 ctypes.byref(state['block']), raw._stream()))
+                    stream.synchronize()
+                else:
+                    env.step_host(host_actions[t], chunks)
+                times.append(time.perf_counter() - begin)
+            times = sorted(times[5:])
+            row[mode + '_us'] = round(1e6 * times[len(times) // 2], 1)
+        print(json.dumps(row), flush=True)
+    # the unpipelined sequence on one stream, for comparison
+    env.reset(seed=1)
+    rewards = torch.empty((B, A), dtype=torch.float32).pin_memory()
+    done = torch.empty((2, B), dtype=torch.uint8).pin_memory()
+    times = []
+    for t in range(steps + 5):
+        torch.cuda.synchronize()
+        begin = time.perf_counter()
+        raw._actions.copy_(host_actions[t], non_blocking=True)
+        raw.step_environment()
+        rewards.copy_(raw._rewards, non_blocking=True)
+        done[0].copy_(raw._terminated, non_blocking=True)
+        done[1].copy_(raw._truncated, non_blocking=True)
+        stream.synchronize()
+        times.append(time.perf_counter() - begin)
+    times = sorted(times[5:])
+    print(json.dumps({'serial_copy_step_copy_us': round(1e6 * times[len(times) // 2], 1)}))
+
+
+if __name__ == '__main__':
+    main()
