@@ -71,6 +71,17 @@ int run_host_pipeline(const char* what, const FrzHostStep* host, const HostArray
   }
   const size_t A = size_t(device.agents);
 
+  if (slices == 1) {  // nothing to overlap: upload, step and download on the caller's stream, on the main control block
+    cudaMemcpyAsync(const_cast<int32_t*>(device.actions), host->actions, size_t(B) * A * 2 * sizeof(int32_t),
+                    cudaMemcpyHostToDevice, main_stream);
+    const int launched = launch_slice(0, B, device.control, main_stream);
+    if (launched != FRZ_OK) return launched;
+    cudaMemcpyAsync(host->rewards, device.rewards, size_t(B) * A * sizeof(float), cudaMemcpyDeviceToHost, main_stream);
+    cudaMemcpyAsync(host->terminated, device.terminated, size_t(B), cudaMemcpyDeviceToHost, main_stream);
+    cudaMemcpyAsync(host->truncated, device.truncated, size_t(B), cudaMemcpyDeviceToHost, main_stream);
+    return check_launch(what);
+  }
+
   int status = control_broadcast(device.control, host->chunk_controls, slices, main_stream);
   if (status != FRZ_OK) return status;
   cudaEventRecord(started, main_stream);

@@ -531,7 +531,9 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           const bool burning = f > 0 && it > 0;
           const float diff = __fadd_rn(f > 0 ? float(f) : 0.f, -attack);
           const bool unmet = burning && diff > 0.f;
-          const bool grow = unmet && field_uniform(i, 0) < (it == almost_state ? p.p_burnout : p.p_increase);
+          // (one Philox word serves both events of a cell: convert it once)
+          const float u_up = field_uniform(i, 0), u_down = INJECTED ? field_uniform(i, 1) : u_up;
+          const bool grow = unmet && u_up < (it == almost_state ? p.p_burnout : p.p_increase);
           it += grow ? 1 : 0;
           const bool burned = grow && it >= burned_state;
           // fire_decrease.py:36-80 sees the post-increase state: a cell that just burned out is no longer lit, any other
@@ -539,7 +541,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           // rounded separately like the reference's two aten ops
           const bool met = burning && !burned && diff <= 0.f;
           const float prob_down = fminf(fmaxf(__fadd_rn(p.p_decrease, __fmul_rn(-diff, p.decrease_bonus)), 0.f), 1.f);
-          const bool shrink = met && field_uniform(i, 1) < prob_down;
+          const bool shrink = met && u_down < prob_down;
           it -= shrink ? 1 : 0;
           const bool put = shrink && it <= 0;
           if (burned) set_cell(2, i, max(cell(2, i) - 1, 0));  // burn-out clamps the fuel (fire_increase.py:90) ...
@@ -747,20 +749,28 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           if (q < quads) {
             const uint4 m = lds_v4(s_tasks + 16u * uint32_t(q));
             uint32_t planes[FRZ_MAX_AGENTS / 8];
+            planes[0] = __byte_perm(__byte_perm(m.x, m.y, 0x0040), __byte_perm(m.z, m.w, 0x0040), 0x5410);
 #pragma unroll
-            for (int k = 0; k < FRZ_MAX_AGENTS / 8; ++k) {
-              planes[k] = 0u;
-              if (k * 8 < A) {
-                const uint32_t lo = __byte_perm(m.x, m.y, uint32_t(k | ((4 + k) << 4)));
-                const uint32_t hi = __byte_perm(m.z, m.w, uint32_t(k | ((4 + k) << 4)));
-                planes[k] = __byte_perm(lo, hi, 0x5410);
+            for (int k = 1; k < FRZ_MAX_AGENTS / 8; ++k) planes[k] = 0u;
+            if (A > 8) {
+#pragma unroll
+              for (int k = 1; k < FRZ_MAX_AGENTS / 8; ++k) {
+                if (k * 8 < A) {
+                  const uint32_t lo = __byte_perm(m.x, m.y, uint32_t(k | ((4 + k) << 4)));
+                  const uint32_t hi = __byte_perm(m.z, m.w, uint32_t(k | ((4 + k) << 4)));
+                  planes[k] = __byte_perm(lo, hi, 0x5410);
+                }
               }
             }
-            for (int a = slot; a < A; a += slots) {
+            uint32_t at = mask_env + uint32_t(slot * mask_words_row + q);
+            const uint32_t stride = uint32_t(slots * mask_words_row);
+            for (int a = slot; a < A; a += slots, at += stride) {
               uint32_t plane = planes[0];
+              if (A > 8) {
 #pragma unroll
-              for (int k = 1; k < FRZ_MAX_AGENTS / 8; ++k) plane = (a >> 3) == k ? planes[k] : plane;
-              mask_words[mask_env + uint32_t(a * mask_words_row + q)] = (plane >> (a & 7)) & 0x01010101u;
+                for (int k = 1; k < FRZ_MAX_AGENTS / 8; ++k) plane = (a >> 3) == k ? planes[k] : plane;
+              }
+              mask_words[at] = (plane >> (a & 7)) & 0x01010101u;
             }
           }
         }

@@ -1,4 +1,5 @@
 set -x
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out/r1
 for w in wildfire_c4 wildfire_c1 rideshare_c2 cyber_c3; do
   python bench.py --workload $w > gpurun_out/r1/bench_$w.json 2> gpurun_out/r1/bench_$w.err || tail -5 gpurun_out/r1/bench_$w.err
@@ -7,6 +8,7 @@ python bench.py --workload wildfire_c4 --parallel-envs 262144 --steps 30 > gpuru
 python bench.py --workload wildfire_c1 --parallel-envs 524288 --steps 30 > gpurun_out/r1/bench_wildfire_c1_524288.json 2>gpurun_out/r1/e2.err
 python bench.py --workload rideshare_c2 --parallel-envs 524288 --steps 30 > gpurun_out/r1/bench_rideshare_c2_524288.json 2>gpurun_out/r1/e3.err
 python bench.py --workload cyber_c3 --parallel-envs 4194304 --steps 30 > gpurun_out/r1/bench_cyber_c3_4194304.json 2>gpurun_out/r1/e4.err
+python profiles/time_host_step.py > gpurun_out/r1/host_step.log 2>&1
 python bench.py --impl reference --steps 5 > gpurun_out/r1/bench_reference_wildfire_c4.json 2>gpurun_out/r1/e5.err
 python bench.py --steps 20 --warmup 3 > gpurun_out/r1/plain_c4.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1/launches_wildfire_c4.csv python bench.py --steps 20 --warmup 3 > gpurun_out/r1/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:wildfire_step -s 12 -c 1 -o gpurun_out/r1/wildfire_c4 python bench.py --steps 20 --warmup 3 > gpurun_out/r1/ncu_c4.log 2>&1
