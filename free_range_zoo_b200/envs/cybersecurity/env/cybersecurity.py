@@ -277,6 +277,19 @@ class raw_env(BatchedAECEnv):
             return lambda: torch.where(self._monitored[:, d].view(-1, 1, 1) != 0, self._task_obs, -100).to(torch.int64)
         return lambda: self._task_obs.to(torch.int64)
 
+    def _other_indices(self, count: int, index: int) -> torch.Tensor:
+        """Indices of the other agents of the same kind (device tensors built once: this runs every step)."""
+        cache = self.__dict__.setdefault('_other_index_cache', {})
+        if (count, index) not in cache:
+            cache[(count, index)] = torch.tensor([i for i in range(count) if i != index], dtype=torch.int64,
+                                                 device=self.device)
+        return cache[(count, index)]
+
+    def _node_indices(self) -> torch.Tensor:
+        if getattr(self, '_node_index_cache', None) is None:
+            self._node_index_cache = torch.arange(self._n_nodes, device=self.device).unsqueeze(0)
+        return self._node_index_cache
+
     def update_observation_views(self) -> None:
         B, N = self.parallel_envs, self._n_nodes
         self.observations = {}
@@ -287,7 +300,7 @@ class raw_env(BatchedAECEnv):
             else:
                 index, table, columns, count = (self.defender_name_mapping[agent], self._defender_self,
                                                 self._defender_columns, self._n_def)
-            others = torch.tensor([i for i in range(count) if i != index], dtype=torch.int64, device=self.device)
+            others = self._other_indices(count, index)
             self.observations[agent] = ObservationDict(
                 {
                     'self': table[:, index],
@@ -297,7 +310,7 @@ class raw_env(BatchedAECEnv):
                 batch_size=[B],
                 device=self.device,
             )
-        nodes = torch.arange(N, device=self.device).unsqueeze(0)
+        nodes = self._node_indices()
         self.agent_action_mapping = LazyDict({
             a: (lambda i=i: jagged_indices_from_mask(nodes < self._agent_task_count[:, i].unsqueeze(1)))
             for a, i in self.offset_agent_name_mapping.items()

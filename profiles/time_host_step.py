@@ -25,6 +25,7 @@ def main():
     parser.add_argument('--workload', default='wildfire_c4')
     parser.add_argument('--parallel-envs', type=int, default=0)
     parser.add_argument('--steps', type=int, default=40)
+    parser.add_argument('--slices', default='1,2,3,4,5,6,8')
     args = parser.parse_args()
     spec = bench.WORKLOADS[args.workload]
     B = args.parallel_envs or spec['envs']
@@ -43,7 +44,7 @@ def main():
         raw.step_all()
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream(device)
-    for chunks in (1, 2, 3, 4, 5, 6, 8):
+    for chunks in [int(c) for c in args.slices.split(',')]:
         row = {'chunks': chunks}
         for mode in ('abi_only', 'step_host'):
             env.reset(seed=1)
