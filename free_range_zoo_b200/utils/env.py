@@ -77,8 +77,9 @@ class BatchedAECEnv(ABC):
             parallel_envs: number of environments stepped together
             device: must be a CUDA device -- there is no CPU path
             render_mode: accepted; rendering is a host-side subsystem outside this engine
-            log_directory / override_initialization_check: a directory turns on the asynchronous CSV logging tap
-                (utils/logging_tap.py; same files as the reference's CSVLogger); SQL connection strings are refused
+            log_directory / override_initialization_check: a directory turns on the asynchronous logging tap
+                (utils/logging_tap.py; same files as the reference's CSVLogger), a ``sqlite://`` URL its SQL form
+                (utils/sql_tap.py; the reference's SQLLogger tables); other connection strings are refused
             single_seeding / buffer_size: accepted and ignored -- randomness is counter-based Philox generated inside
                 the step kernel, keyed by (seed, global env index, step), so there are no generator states to juggle
             env_offset: global index of this shard's first environment (multi-GPU sharding keeps trajectories invariant)
@@ -90,8 +91,9 @@ class BatchedAECEnv(ABC):
                                'there is no CPU fallback -- use the reference implementation on CPU.')
         if device.index is None:
             device = torch.device('cuda', torch.cuda.current_device())
-        if log_directory is not None and str(log_directory).startswith(('sqlite', 'postgres', 'mysql')):
-            raise NotImplementedError('only the CSV log format is implemented by the asynchronous logging tap')
+        if log_directory is not None and str(log_directory).startswith(('postgres', 'mysql')):
+            raise NotImplementedError('the asynchronous logging tap writes CSV files or sqlite:// databases; '
+                                      f'no driver for {log_directory!r} is available')
         self.parallel_envs = int(parallel_envs)
         self.max_steps = max_steps
         self.device = device
@@ -345,10 +347,16 @@ class BatchedAECEnv(ABC):
         device: see utils/logging_tap.py."""
         if self._tap is None:
             from free_range_zoo_b200.utils.logging_tap import LoggingTap
-            self._tap = LoggingTap(self.log_directory, self.parallel_envs, self.device, self._log_snapshot,
-                                   self._log_columns,
-                                   override_initialization_check=self.override_initialization_check)
-        self._tap.capture(reset, self.log_description)
+            if str(self.log_directory).startswith('sqlite://'):  # reference utils/env.py:65-86
+                from free_range_zoo_b200.utils.sql_tap import SqliteSink
+                sink = SqliteSink(self.log_directory, self.metadata['name'], self.parallel_envs)
+                self._tap = LoggingTap(self.log_directory, self.parallel_envs, self.device, self._log_snapshot,
+                                       self._log_records, sink=sink, agents=self.possible_agents)
+            else:
+                self._tap = LoggingTap(self.log_directory, self.parallel_envs, self.device, self._log_snapshot,
+                                       self._log_columns,
+                                       override_initialization_check=self.override_initialization_check)
+        self._tap.capture(reset, self.log_description, getattr(self, '_log_label', None))
 
     def flush_logs(self) -> None:
         """Wait until every queued log row is on disk."""
@@ -379,6 +387,20 @@ class BatchedAECEnv(ABC):
             columns[f'{agent}_observation_map'] = observation_map
         columns.update(self._log_extra_columns(host, reset))
         return columns
+
+    def _log_records(self, host: Dict[str, Any], reset: bool) -> Dict[str, Any]:
+        """The SQL sink's record of one snapshot (utils/sql_tap.py::SqliteSink.write): the same state / mapping cells as
+        the CSV columns, raw action and reward values per agent (logging_handlers.py:160-241)."""
+        state = dict(self._log_state_columns(host))
+        state.update({name: cells for name, cells in self._log_extra_columns(host, reset).items()
+                      if name not in ('burnouts', 'putouts')})
+        agents = {}
+        for index, agent in enumerate(self.possible_agents):
+            action_map, observation_map = self._log_mappings(host, index)
+            agents[agent] = dict(reward=host['rewards'][:, index], action_field=host['actions'][:, index, 1],
+                                 task_field=host['actions'][:, index, 0], action_map=action_map,
+                                 observation_map=observation_map)
+        return dict(timestep=host['num_moves'], state=state, agents=agents)
 
     def _log_state_columns(self, host) -> Dict[str, Any]:
         raise NotImplementedError
@@ -436,9 +458,11 @@ class BatchedAECEnv(ABC):
 
     # ------------------------------------------------------------------------------------------ CUDA graph
 
-    def capture_graph(self, sample: bool = False, sampler_seed: int = 2026) -> None:
-        """Capture ``[sample_actions ->] step`` in a CUDA graph; ``replay()`` then costs one graph launch per step.
-        Kernel arguments are pointer-stable and the step counter lives on the device, so the graph needs no updates."""
+    def capture_graph(self, sample: bool = False, sampler_seed: int = 2026, steps: int = 1) -> None:
+        """Capture ``steps`` x ``[sample_actions ->] step`` in a CUDA graph; ``replay()`` then costs one graph launch
+        per ``steps`` environment steps (small batches are bound by launch latency: several steps per launch keep the
+        kernels back to back).  Kernel arguments are pointer-stable and the step counter lives on the device, so the
+        graph needs no updates."""
         torch.cuda.synchronize(self.device)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -450,9 +474,10 @@ class BatchedAECEnv(ABC):
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            if sample:
-                self.sample_actions(sampler_seed)
-            self.step_environment()
+            for _ in range(max(1, int(steps))):
+                if sample:
+                    self.sample_actions(sampler_seed)
+                self.step_environment()
         self._graph = graph
 
     def replay(self) -> None:

@@ -1,4 +1,4 @@
-"""Asynchronous CSV logging tap.
+"""Asynchronous logging tap: CSV files, or the SQL tables of utils/sql_tap.py.
 
 The reference logs synchronously on the step path: after every environment step ``CSVLogger.log_environment``
 (free_range_zoo/utils/logging_handlers.py:52-111) pulls every state tensor to the host with ``.tolist()``, builds a
@@ -42,7 +42,7 @@ class LoggingTap:
     def __init__(self, log_directory: str, parallel_envs: int, device: torch.device,
                  snapshot: Callable[[], Dict[str, torch.Tensor]],
                  columns: Callable[[Dict[str, np.ndarray], bool], Dict[str, Sequence]], depth: int = 4,
-                 override_initialization_check: bool = False):
+                 override_initialization_check: bool = False, sink=None, agents: Sequence[str] = ()):
         """
         Args:
             log_directory: directory that receives ``<env index>.csv`` (created; must be empty unless overridden,
@@ -51,10 +51,14 @@ class LoggingTap:
             columns: turns the host copy of one snapshot into ordered CSV columns, each a length-B sequence; runs on the
                 writer thread
             depth: ring slots; ``capture`` blocks only when all of them are still being written
+            sink: optional row sink replacing the CSV files (utils/sql_tap.py::SqliteSink); ``columns`` then returns the
+                sink's record instead of CSV columns, ``agents`` are the names registered by every reset
         """
-        if not override_initialization_check and os.path.exists(log_directory) and os.listdir(log_directory):
-            raise FileExistsError('The logging output directory already exists. Set override_initialization_check or rename.')
-        os.makedirs(log_directory, exist_ok=True)
+        self._sink, self._agents = sink, tuple(agents)
+        if sink is None:
+            if not override_initialization_check and os.path.exists(log_directory) and os.listdir(log_directory):
+                raise FileExistsError('The logging output directory already exists. Set override_initialization_check or rename.')
+            os.makedirs(log_directory, exist_ok=True)
         self.log_directory, self.parallel_envs, self.device = log_directory, parallel_envs, device
         self._snapshot, self._columns, self._depth = snapshot, columns, depth
         self._slots: List[_Slot] = []
@@ -67,7 +71,7 @@ class LoggingTap:
 
     # ------------------------------------------------------------------------------------------ step path
 
-    def capture(self, reset: bool, description: Optional[str]) -> None:
+    def capture(self, reset: bool, description: Optional[str], label: Optional[str] = None) -> None:
         """Queue one log row per environment for the current device state."""
         if self._error is not None:
             raise RuntimeError('the logging tap failed') from self._error
@@ -90,7 +94,7 @@ class LoggingTap:
                 slot.host[name].copy_(slot.device[name], non_blocking=True)
             landed = torch.cuda.Event()
             landed.record(self._copy_stream)
-        self._queue.put((slot, landed, reset, description))
+        self._queue.put((slot, landed, reset, description, label))
 
     def flush(self) -> None:
         """Block until every queued row is on disk."""
@@ -102,6 +106,8 @@ class LoggingTap:
         self.flush()
         self._queue.put(None)
         self._writer.join()
+        if self._sink is not None:
+            self._sink.close()
 
     # ------------------------------------------------------------------------------------------ writer thread
 
@@ -123,10 +129,15 @@ class LoggingTap:
             if item is None:
                 self._queue.task_done()
                 return
-            slot, landed, reset, description = item
+            slot, landed, reset, description, label = item
             try:
                 landed.synchronize()
                 host = {name: tensor.numpy() for name, tensor in slot.host.items()}
+                if self._sink is not None:
+                    if reset:
+                        self._sink.reset(label, description, self._agents)
+                    self._sink.write(self._columns(host, reset), reset)
+                    continue
                 columns = dict(self._columns(host, reset))
                 columns['description'] = [description] * self.parallel_envs
                 names = list(columns)
