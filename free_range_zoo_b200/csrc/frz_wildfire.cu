@@ -19,9 +19,6 @@
 #include "frz_common.cuh"
 #include "frz_host.cuh"
 
-#ifndef FRZ_BISECT
-#define FRZ_BISECT 0
-#endif
 namespace frz {
 namespace {
 
@@ -412,18 +409,9 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             }
           }
         }
-#if FRZ_BISECT == 2
-        float ufx[2 * CPL];
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) { ufx[2 * i] = u01(bits[grow_word(i)]); ufx[2 * i + 1] = u01(bits[spread_word(i)]); }
-#endif
         const auto field_uniform = [&](int i, int event) -> float {  // event: 0 increase, 1 decrease, 2 spread
           if constexpr (INJECTED) return uf[3 * i + event];
-#if FRZ_BISECT == 2
-          else return ufx[event == 2 ? 2 * i + 1 : 2 * i];
-#else
           else return u01(bits[event == 2 ? spread_word(i) : grow_word(i)]);
-#endif
         };
 
         // ---------------------------------------------------------------- agent randomness + transitions
@@ -498,16 +486,10 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           if (__any_sync(kFullMask, increased)) {
             // first i with r <= cum[i] == the number of entries below r (cum is non-decreasing; the host pads the unused
             // entries with +inf), capped at the last capacity like the reference's default
-#if FRZ_BISECT == 1
-            int pick = p.num_capacities - 1;
-            for (int i = p.num_capacities - 1; i >= 0; --i)
-              if (ua[3] <= p.capacity_cum[i]) pick = i;
-#else
             int pick = 0;
 #pragma unroll
             for (int i = 0; i < FRZ_MAX_CAPACITIES; ++i) pick += ua[3] > p.capacity_cum[i] ? 1 : 0;
             pick = min(pick, p.num_capacities - 1);
-#endif
             const bool switches = increased && ua[4] < p.p_tank_switch;
             const float extra = __fadd_rn(supp, -cap);
             if (switches) {
