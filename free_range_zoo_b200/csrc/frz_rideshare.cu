@@ -110,6 +110,7 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
   const bool fast = p.flags & FRZ_RS_FAST_TRAVEL, diagonal = p.flags & FRZ_RS_DIAGONAL_TRAVEL;
   const int directions = diagonal ? 9 : 5;
   // task-mask stores: work item -> (agent, four consecutive table rows)
+  const bool wide_rows = (K & 3) == 0;  // every environment's table starts on a 16-byte boundary
   const int quads = (K + 3) >> 2;
   const uint32_t inverse_quads = (65536u + uint32_t(quads) - 1u) / uint32_t(quads);  // item / quads for item < 512
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
@@ -124,7 +125,13 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
       // stage the environment's live rows (cp.async, 4 bytes per lane per instruction: rows are 44 bytes, so nothing
       // wider stays aligned); the other warps of the SM cover the latency
       const int n_before = min(io.env_task_count[env], K);
-      for (int i = sub; i < n_before * kCols; i += G) cp_async_4(table + 4u * i, global_rows + i);
+      {
+        // 16-byte pieces while they lie inside the live rows (table bases are 16-byte aligned when K is a multiple of
+        // four), single words for the remaining one to three
+        const int words = n_before * kCols, quads_of_words = wide_rows ? words >> 2 : 0;
+        for (int i = sub; i < quads_of_words; i += G) cp_async_16(table + 16u * i, global_rows + 4 * i);
+        for (int i = 4 * quads_of_words + sub; i < words; i += G) cp_async_4(table + 4u * i, global_rows + i);
+      }
       cp_async_commit();
 
       int agent_y = 0, agent_x = 0;
@@ -458,8 +465,14 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
           reinterpret_cast<int4*>(io.self_obs)[agent_at] = make_int4(agent_y, agent_x, n_accepted, n_riding);
         }
         if (sub == 0) io.env_task_count[env] = n_rows;
-        if (admits)
-          for (int i = sub; i < n_rows * kCols; i += G) global_rows[i] = int(lds(table + 4u * i));
+        if (admits) {
+          const int words = n_rows * kCols, quads_of_words = wide_rows ? words >> 2 : 0;
+          for (int i = sub; i < quads_of_words; i += G) {
+            const uint4 piece = lds_v4(table + 16u * i);
+            reinterpret_cast<int4*>(global_rows)[i] = make_int4(int(piece.x), int(piece.y), int(piece.z), int(piece.w));
+          }
+          for (int i = 4 * quads_of_words + sub; i < words; i += G) global_rows[i] = int(lds(table + 4u * i));
+        }
       }
       __syncwarp();
     }
