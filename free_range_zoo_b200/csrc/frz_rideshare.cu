@@ -122,8 +122,7 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
       const bool valid = env0 + lane / G < B;  // groups past the end of the batch replay the last environment, storing nothing
       const uint32_t agent_at = uint32_t(env) * uint32_t(A) + uint32_t(sub);
       int* const global_rows = io.passengers + uint32_t(env) * uint32_t(K * kCols);
-      // stage the environment's live rows (cp.async, 4 bytes per lane per instruction: rows are 44 bytes, so nothing
-      // wider stays aligned); the other warps of the SM cover the latency
+      // stage the environment's live rows (cp.async); the other warps of the SM cover the latency
       const int n_before = min(io.env_task_count[env], K);
       {
         // 16-byte pieces while they lie inside the live rows (table bases are 16-byte aligned when K is a multiple of
