@@ -172,10 +172,20 @@ def library() -> C.CDLL:
                                   ('frz_cyber_step_host', CyberParams, CyberBuffers),
                                   ('frz_rideshare_step_host', RideshareParams, RideshareBuffers)):
         getattr(lib, name).argtypes = [C.POINTER(params), C.POINTER(buffers), C.c_int32, C.POINTER(HostStep), C.c_void_p]
+    lib.frz_host_slices.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     if lib.frz_version() != 2:
         raise RuntimeError(f'libfrz.so ABI version {lib.frz_version()} != 2; rebuild the library')
     _lib = lib
     return lib
+
+
+def host_slices(parallel_envs: int, chunks: int):
+    """Boundaries of the slices ``frz_<domain>_step_host`` cuts a batch into (include/frz.h: frz_host_slices)."""
+    bounds = (C.c_int32 * (MAX_CHUNKS + 1))()
+    count = library().frz_host_slices(parallel_envs, chunks, bounds)
+    if count < 0:
+        check(-count, 'frz_host_slices')
+    return list(bounds[:count + 1])
 
 
 def check(status: int, what: str = '') -> None:

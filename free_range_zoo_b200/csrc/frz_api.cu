@@ -3,6 +3,7 @@
 #include <cstdio>
 
 #include "frz_common.cuh"
+#include "frz_host.cuh"
 
 namespace frz {
 
@@ -94,6 +95,18 @@ extern "C" {
 int frz_version(void) { return FRZ_ABI_VERSION; }
 
 const char* frz_last_error(void) { return frz::g_error; }
+
+int frz_host_slices(int32_t parallel_envs, int32_t chunks, int32_t* bounds) {
+  if (bounds == nullptr) {
+    frz::set_error("frz_host_slices: bounds is NULL");
+    return -FRZ_ERR_NULL;
+  }
+  if (parallel_envs <= 0 || chunks < 1 || chunks > FRZ_MAX_CHUNKS) {
+    frz::set_error("frz_host_slices: parallel_envs=%d chunks=%d", parallel_envs, chunks);
+    return -FRZ_ERR_SHAPE;
+  }
+  return frz::slice_bounds(parallel_envs, chunks, bounds);
+}
 
 int frz_control_init(FrzControl* control, uint64_t seed, void* stream) {
   if (control == nullptr) {

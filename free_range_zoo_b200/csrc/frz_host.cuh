@@ -27,6 +27,21 @@ namespace frz {
 // cybersecurity step moves its tiles with bulk copies) and the slices' warps fully populated
 constexpr int kSliceAlignment = 1024;
 
+// Slice boundaries of a batch of B environments cut into at most `chunks` slices: bounds[0] = 0 < ... < bounds[n] = B,
+// every inner boundary a multiple of kSliceAlignment, the first slice half as long as the others.  Returns n.
+inline int slice_bounds(int B, int chunks, int* bounds) {
+  int slices = 0;
+  const long long halves = 2LL * chunks - 1;  // the batch in units of half a regular slice
+  bounds[0] = 0;
+  for (int i = 1; i <= chunks; ++i) {
+    long long end = (long long)B * (2LL * i - 1) / halves;
+    end = (end + kSliceAlignment - 1) / kSliceAlignment * kSliceAlignment;
+    if (end > B || i == chunks) end = B;
+    if (end > bounds[slices]) bounds[++slices] = int(end);
+  }
+  return slices;
+}
+
 struct HostArrays {  // device side of what the pipeline moves: [B, A, 2] actions in, [B, A] rewards and [B] flags out
   const int32_t* actions;
   const float* rewards;
@@ -55,20 +70,8 @@ int run_host_pipeline(const char* what, const FrzHostStep* host, const HostArray
   cudaEvent_t* const uploaded = events + 1;                   // [slice]
   cudaEvent_t* const finished = events + 1 + FRZ_MAX_CHUNKS;  // [slice]
 
-  // slice boundaries: the first slice is half as long as the others
   int bounds[FRZ_MAX_CHUNKS + 1];
-  int slices = 0;
-  {
-    const int chunks = host->chunks;
-    const long long halves = 2LL * chunks - 1;  // the batch in units of half a regular slice
-    bounds[0] = 0;
-    for (int i = 1; i <= chunks; ++i) {
-      long long end = (long long)B * (2LL * i - 1) / halves;
-      end = (end + kSliceAlignment - 1) / kSliceAlignment * kSliceAlignment;
-      if (end > B || i == chunks) end = B;
-      if (end > bounds[slices]) bounds[++slices] = int(end);
-    }
-  }
+  const int slices = slice_bounds(B, host->chunks, bounds);
   const size_t A = size_t(device.agents);
 
   if (slices == 1) {  // nothing to overlap: upload, step and download on the caller's stream, on the main control block

@@ -336,6 +336,10 @@ typedef struct {
 
 int frz_wildfire_step_host(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
                            const FrzHostStep* host, void* stream);
+/* How frz_<domain>_step_host cuts a batch: writes bounds[0] = 0 < ... < bounds[n] = parallel_envs (room for
+ * FRZ_MAX_CHUNKS + 1 entries) and returns n <= chunks, or -FrzStatus.  Inner boundaries are multiples of 1024
+ * environments; the first slice is half as long as the others (no kernel can start before it has been uploaded). */
+int frz_host_slices(int32_t parallel_envs, int32_t chunks, int32_t* bounds);
 int frz_cyber_step_host(const FrzCyberParams* params, const FrzCyberBuffers* io, int32_t parallel_envs,
                         const FrzHostStep* host, void* stream);
 int frz_rideshare_step_host(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,

@@ -31,7 +31,7 @@ def lib():
 
 def test_every_declared_symbol_is_exported(lib):
     declared = _lib.exported_symbols()
-    assert len(declared) == 18  # 3 library-wide + 5 per domain
+    assert len(declared) == 19  # 4 library-wide + 5 per domain
     missing = [name for name in declared if not hasattr(lib, name)]
     assert not missing, missing
     assert lib.frz_version() == 2
@@ -102,3 +102,24 @@ def test_product_code_never_imports_the_oracle():
                 if 'import oracle' in text or 'from oracle' in text:
                     offenders.append(os.path.join(folder, name))
     assert not offenders, offenders
+
+
+def test_host_step_slices(lib):
+    """frz_host_slices: what frz_<domain>_step_host does with a batch (pure host logic, no GPU)."""
+    assert _lib.host_slices(65536, 1) == [0, 65536]
+    assert _lib.host_slices(65536, 5) == [0, 8192, 22528, 36864, 51200, 65536]  # first slice half as long
+    assert _lib.host_slices(1000, 4) == [0, 1000]  # too small to cut: one slice
+    assert _lib.host_slices(3000, 2) == [0, 1024, 3000]
+    for B in (1, 1023, 1024, 1025, 4100, 70000, 524288, 4194304):
+        for chunks in range(1, _lib.MAX_CHUNKS + 1):
+            bounds = _lib.host_slices(B, chunks)
+            assert bounds[0] == 0 and bounds[-1] == B and len(bounds) - 1 <= chunks
+            assert all(a < b for a, b in zip(bounds, bounds[1:]))
+            assert all(b % 1024 == 0 for b in bounds[1:-1])
+            sizes = [b - a for a, b in zip(bounds, bounds[1:])]
+            if len(sizes) > 2:
+                assert sizes[0] <= max(sizes[1:-1])
+    with pytest.raises(RuntimeError):
+        _lib.host_slices(0, 2)
+    with pytest.raises(RuntimeError):
+        _lib.host_slices(100, _lib.MAX_CHUNKS + 1)
