@@ -133,9 +133,10 @@ def wildfire_actions(raw, gen):
     return acts
 
 
-def gen_wildfire(name, preset, B, steps, seed, **env_kwargs):
+def gen_wildfire(name, preset, B, steps, seed, preset_kwargs=None, **env_kwargs):
     torch.manual_seed(seed)
-    config = preset(ref_wf_conf)
+    preset_kwargs = preset_kwargs or {}
+    config = preset(ref_wf_conf, **preset_kwargs)
     env = wildfire_v0.parallel_env(parallel_envs=B, max_steps=steps, configuration=config, device=torch.device('cpu'),
                                    single_seeding=True, **env_kwargs)
     env.reset(seed=seed)
@@ -167,8 +168,8 @@ def gen_wildfire(name, preset, B, steps, seed, **env_kwargs):
     with torch.no_grad():
         lut = raw.fire_spread_transition.fire_spread_filter(patterns)[:, 0, 1, 1].numpy().copy()
 
-    meta = dict(domain='wildfire', preset=preset.__name__, B=B, steps=executed, max_steps=steps, seed=seed,
-                env_kwargs=env_kwargs)
+    meta = dict(domain='wildfire', preset=preset.__name__, preset_kwargs=preset_kwargs, B=B, steps=executed,
+                max_steps=steps, seed=seed, env_kwargs=env_kwargs)
     save(name, meta, traj, recorder, extra=dict(
         actions=np.stack(actions),
         spread_weights=raw.fire_spread_weights.numpy().copy(),
@@ -351,6 +352,12 @@ def main():
                  observe_other_power=True, observe_other_suppressant=True)
     gen_wildfire('wildfire_quirks_good', presets.wildfire_quirks, B=24, steps=30, seed=15, show_bad_actions=False,
                  observe_other_power=False, observe_other_suppressant=True)
+
+    # the other kernel geometries: half-warp groups with the cells in registers (7x8), one warp per environment (12x12)
+    gen_wildfire('wildfire_7x8', presets.wildfire_large, B=12, steps=25, seed=16,
+                 preset_kwargs=dict(height=7, width=8, num_agents=5, seed=5))
+    gen_wildfire('wildfire_12x12', presets.wildfire_large, B=6, steps=20, seed=17,
+                 preset_kwargs=dict(height=12, width=12, num_agents=20, seed=3))
 
     gen_rideshare('rideshare_profile', presets.rideshare_profile, B=8, steps=20, seed=21)
     gen_rideshare('rideshare_c2', presets.rideshare_c2, B=24, steps=100, seed=22)

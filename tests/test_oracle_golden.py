@@ -10,7 +10,7 @@ from tests import golden_util as G
 @pytest.mark.parametrize('name', G.fixtures('wildfire'))
 def test_wildfire_oracle_matches_reference(name):
     meta, gold = G.load(name)
-    config = getattr(presets, meta['preset'])()
+    config = getattr(presets, meta['preset'])(**meta.get('preset_kwargs', {}))
     oracle = WildfireOracle(config, meta['B'], meta['max_steps'], **meta['env_kwargs'])
     np.testing.assert_array_equal(oracle.spread_weights, gold['spread_weights'])
     np.testing.assert_array_equal(oracle.spread_lut, gold['spread_lut'])

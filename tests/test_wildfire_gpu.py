@@ -25,7 +25,8 @@ def make_env(config, B, max_steps, **kwargs):
 @pytest.mark.parametrize('name', G.fixtures('wildfire'))
 def test_matches_reference_trajectory(name):
     meta, gold = G.load(name)
-    env = make_env(getattr(presets, meta['preset'])(), meta['B'], meta['max_steps'], **meta['env_kwargs'])
+    env = make_env(getattr(presets, meta['preset'])(**meta.get('preset_kwargs', {})), meta['B'], meta['max_steps'],
+                   **meta['env_kwargs'])
     env.reset(seed=0)
     G.compare(wildfire_outputs(env), gold, 0, context=name)
     agents = env.agents
@@ -197,7 +198,8 @@ def test_action_mapping_wrapper_returns_the_reference_mappings():
     the mappings equal the reference's recorded ones on a golden trajectory."""
     from free_range_zoo_b200.wrappers import action_mapping_wrapper_v0
     meta, gold = G.load('wildfire_c4')
-    env = action_mapping_wrapper_v0(make_env(getattr(presets, meta['preset'])(), meta['B'], meta['max_steps'], **meta['env_kwargs']))
+    env = action_mapping_wrapper_v0(make_env(getattr(presets, meta['preset'])(**meta.get('preset_kwargs', {})), meta['B'],
+                                             meta['max_steps'], **meta['env_kwargs']))
     observations, _ = env.reset(seed=0)
     agents = env.agents
     for t in range(3):
