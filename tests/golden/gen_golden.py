@@ -316,8 +316,9 @@ def cyber_actions(raw, gen):
     return acts
 
 
-def gen_cyber(name, preset, B, steps, seed, **env_kwargs):
-    config = preset(ref_cy_conf)
+def gen_cyber(name, preset, B, steps, seed, preset_kwargs=None, **env_kwargs):
+    preset_kwargs = preset_kwargs or {}
+    config = preset(ref_cy_conf, **preset_kwargs)
     env = cybersecurity_v0.parallel_env(parallel_envs=B, max_steps=steps, configuration=config,
                                         device=torch.device('cpu'), single_seeding=True, **env_kwargs)
     env.reset(seed=seed)
@@ -338,8 +339,8 @@ def gen_cyber(name, preset, B, steps, seed, **env_kwargs):
         _, rewards, _, _, _ = env.step({a: torch.from_numpy(acts[:, i].copy()) for i, a in enumerate(raw.agents)})
         traj.add(**cyber_outputs(raw, rewards))
         executed += 1
-    meta = dict(domain='cybersecurity', preset=preset.__name__, B=B, steps=executed, max_steps=steps, seed=seed,
-                env_kwargs=env_kwargs, agents=list(raw.agents))
+    meta = dict(domain='cybersecurity', preset=preset.__name__, preset_kwargs=preset_kwargs, B=B, steps=executed,
+                max_steps=steps, seed=seed, env_kwargs=env_kwargs, agents=list(raw.agents))
     # tanh of every reachable danger score as computed by torch on CPU (pins the one transcendental on the path)
     save(name, meta, traj, recorder, extra=dict(actions=np.stack(actions)))
 
@@ -368,6 +369,12 @@ def main():
     gen_rideshare('rideshare_fast', presets.rideshare_quirks, B=16, steps=40, seed=25,
                   preset_kwargs=dict(parallel_envs=16, fast=True))
 
+    # the wider kernel geometries: 16 / 32 lanes per environment
+    gen_rideshare('rideshare_12drivers', presets.rideshare_synthetic, B=6, steps=25, seed=26,
+                  preset_kwargs=dict(drivers=12, rows=40))
+    gen_rideshare('rideshare_20drivers', presets.rideshare_synthetic, B=4, steps=25, seed=27,
+                  preset_kwargs=dict(drivers=20, rows=64))
+
     gen_cyber('cyber_profile', presets.cyber_profile, B=8, steps=20, seed=31)
     gen_cyber('cyber_c3', presets.cyber_c3, B=32, steps=60, seed=32, show_bad_actions=False, partially_observable=True)
     gen_cyber('cyber_quirks', presets.cyber_quirks, B=24, steps=50, seed=33, show_bad_actions=True,
@@ -376,6 +383,13 @@ def main():
     gen_cyber('cyber_quirks_open', presets.cyber_quirks, B=16, steps=30, seed=34, show_bad_actions=False,
               partially_observable=False, observe_other_location=True, observe_other_presence=False,
               observe_other_power=True)
+    # the other size classes of the tiled kernel: (8, 4, 4), (16, 8, 8), and a network beyond them (direct kernel)
+    gen_cyber('cyber_6nodes', presets.cyber_synthetic, B=12, steps=25, seed=35,
+              preset_kwargs=dict(nodes=6, attackers=3, defenders=3, seed=71), show_bad_actions=True)
+    gen_cyber('cyber_10nodes', presets.cyber_synthetic, B=8, steps=25, seed=36,
+              preset_kwargs=dict(nodes=10, attackers=5, defenders=4, seed=77), show_bad_actions=True)
+    gen_cyber('cyber_20nodes', presets.cyber_synthetic, B=6, steps=20, seed=37,
+              preset_kwargs=dict(nodes=20, attackers=10, defenders=9, seed=79), show_bad_actions=True)
 
 
 if __name__ == '__main__':

@@ -19,7 +19,7 @@ def make_env(config, B, max_steps, **kwargs):
 @pytest.mark.parametrize('name', G.fixtures('cyber'))
 def test_matches_reference_trajectory(name):
     meta, gold = G.load(name)
-    env = make_env(getattr(presets, meta['preset'])(), meta['B'], meta['max_steps'], **meta['env_kwargs'])
+    env = make_env(getattr(presets, meta['preset'])(**meta.get('preset_kwargs', {})), meta['B'], meta['max_steps'], **meta['env_kwargs'])
     env.reset(seed=0)
     assert list(env.agents) == meta['agents']
     G.compare(cyber_outputs(env), gold, 0, context=name)

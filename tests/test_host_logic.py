@@ -54,7 +54,7 @@ def test_wildfire_flattening_matches_reference_tables(name):
     """spread LUT == the reference conv2d outputs recorded in the fixture; range masks == the oracle's range test."""
     from oracle.wildfire import WildfireOracle
     meta, gold = G.load(name)
-    config = getattr(presets, meta['preset'])()
+    config = getattr(presets, meta['preset'])(**meta.get('preset_kwargs', {}))
     params, cell_reward, cell_ignition, range_mask = wf_env.flatten_configuration(config, 7, True, env_offset=5)
     np.testing.assert_array_equal(np.array(list(params.spread_lut), np.float32), gold['spread_lut'])
     assert params.max_steps == 7 and params.env_offset == 5 and params.flags & _lib.WF_SHOW_BAD_ACTIONS

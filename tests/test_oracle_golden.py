@@ -26,7 +26,7 @@ def test_wildfire_oracle_matches_reference(name):
 def test_cybersecurity_oracle_matches_reference(name):
     from oracle.cybersecurity import CybersecurityOracle
     meta, gold = G.load(name)
-    config = getattr(presets, meta['preset'])()
+    config = getattr(presets, meta['preset'])(**meta.get('preset_kwargs', {}))
     oracle = CybersecurityOracle(config, meta['B'], meta['max_steps'], **meta['env_kwargs'])
     oracle.reset()
     G.compare(oracle.outputs(meta['agents']), gold, 0, context=name)
