@@ -109,6 +109,9 @@ __device__ __forceinline__ void sts(uint32_t address, uint32_t value) {
 __device__ __forceinline__ void cp_async_4(uint32_t shared_dst, const void* global_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" : : "r"(shared_dst), "l"(global_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_8(uint32_t shared_dst, const void* global_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" : : "r"(shared_dst), "l"(global_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_16(uint32_t shared_dst, const void* global_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" : : "r"(shared_dst), "l"(global_src) : "memory");
 }

@@ -73,12 +73,22 @@ __device__ __forceinline__ uint32_t group_ballot(bool pred, int group_base, uint
 //   static again (sizes depend on the configuration, so they come last: every offset above is a constant)
 //     cell_agents[E][kCells]   bit a = agent a reaches cell c when its equipment is in state e
 //     range_mask[A][E][NW]     bit c = cell c is within agent a's reach in equipment state e
-//     (half-warp groups with more than 4 cells per lane only) fires, intensity, fuel [kCells each]: the cell state
-//     stays here instead of in registers, padded so that the two groups of a warp hit different banks
-__host__ __device__ constexpr bool cells_in_smem(int group, int cells_per_lane) { return group == 16 && cells_per_lane > 4; }
+//     (half-warp groups with more than 4 cells per lane only) 2 x { fires, intensity, fuel [kCells each] }: the cell
+//     state stays here instead of in registers, padded so that the two groups of a warp hit different banks.  Two
+//     buffers: when the rows are 16-byte multiples the state planes move with bulk async copies (cp.async.bulk,
+//     completion on an mbarrier) -- the next environment's planes are fetched while the current one is stepped, and
+//     the stepped planes are written back with three bulk stores instead of 3 * CPL per-lane stores
+#ifndef FRZ_WF_CELLS_IN_SMEM
+#define FRZ_WF_CELLS_IN_SMEM 1
+#endif
+__host__ __device__ constexpr bool split_geometry(int group, int cells_per_lane) { return group == 16 && cells_per_lane > 4; }
+__host__ __device__ constexpr bool cells_in_smem(int group, int cells_per_lane) {
+  return FRZ_WF_CELLS_IN_SMEM && split_geometry(group, cells_per_lane);
+}
 __host__ __device__ constexpr int group_smem_words(int group, int cells_per_lane) {
   const int cells = group * cells_per_lane;
-  const int words = cells_in_smem(group, cells_per_lane) ? 5 * cells : 2 * cells;
+  // (bulk path: + a one-deep staging area for the next environment's agent rows: suppressant, capacity, equipment, action pair)
+  const int words = cells_in_smem(group, cells_per_lane) ? 8 * cells + 5 * group : 2 * cells;
   return (group == 16 && words % 32 == 0) ? words + 16 : words;
 }
 __host__ __device__ inline int static_smem_words(int cells, int agents, int states) {
@@ -137,9 +147,14 @@ struct Derived {
   uint32_t west_ok[FRZ_MAX_CELLS / 32];  // bit c: cell c has a western neighbour (x > 0)
   uint32_t east_ok[FRZ_MAX_CELLS / 32];  // bit c: cell c has an eastern neighbour (x < W - 1)
   int32_t spare_lanes_feed_agents;       // Philox: the agents' four words come from lanes whose last cell is off-grid
+  // Philox mode compares the 24 random bits k of a draw (u = k * 2^-24) with integer thresholds: u < p  <=>  k < ceil(p * 2^24),
+  // u > c  <=>  k > floor(c * 2^24) -- the same outcome as the fp32 compare for every k, without the int -> float conversion
+  uint32_t t_increase, t_burnout, t_suppressant_decrease, t_repair, t_critical, t_degrade, t_refill, t_tank_switch;
+  int32_t t_capacity_cum[FRZ_MAX_CAPACITIES];
+  int32_t almost_state, burned_state;    // num_fire_states - 2 / - 1
 };
 
-template <int G, int CPL, int MODE, bool INJECTED>
+template <int G, int CPL, int MODE, bool INJECTED, bool BULK>
 __global__ void __launch_bounds__(kThreads, (G * CPL > 128) ? 1 : FRZ_WF_MIN_BLOCKS)
 wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_constant__ FrzWildfireBuffers io,
                      const __grid_constant__ Derived derived, const int B) {
@@ -198,7 +213,24 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   asm volatile("" : "+r"(s_attack));
   const uint32_t s_tasks = s_base + 4u * uint32_t(tasks_off);
   const uint32_t s_range = s_base + 4u * uint32_t(range_off);
-  uint32_t* const my_state = smem + tasks_off + kCells + sub;  // this lane's column of the group's state planes
+  uint32_t* my_state = smem + tasks_off + kCells + sub;  // this lane's column of the group's current state planes
+  // bulk-copy path of the state planes (kCellsInSmem geometries whose rows are 16-byte multiples): one mbarrier per
+  // (warp, buffer); lane 0 of the warp issues the copies of both groups -- every operand of a bulk copy is then
+  // warp-uniform (a per-group issuer makes the compiler serialise the copies lane by lane) -- and all lanes wait
+  // (the barriers sit behind the range masks in the dynamic region, so that their addresses derive from the same
+  // warp-uniform base as everything else)
+  constexpr bool bulk = BULK;
+  static_assert(!BULK || kCellsInSmem, "the bulk path moves the shared-memory state planes");
+  const uint32_t s_barriers = s_base + 4u * uint32_t((range_off + A * E * NW + 3) & ~3) + 16u * uint32_t(warp_in_cta);
+  const uint32_t s_planes = s_base + 4u * uint32_t(tasks_off + kCells);  // buffer 0 of this group's state planes
+  // the same for group g of this warp, from warp-uniform values only
+  const auto planes_of_group = [&](int g) {
+    return s_base + 4u * uint32_t(kRegionOff + (warp_in_cta * kGroupsPerWarp + g) * group_smem_words(G, CPL) + 2 * kCells);
+  };
+  constexpr uint32_t kBufferBytes = 4u * 3u * kCells;
+  // staging area of the next environment's agent rows (this lane's slots): [G] suppressant, [G] capacity, [G] equipment,
+  // [G] x 8 bytes action pair -- filled by cp.async one iteration ahead, so the decode does not wait for global memory
+  const uint32_t s_stage = s_planes + 2u * kBufferBytes + 4u * uint32_t(sub);
 
   for (int i = threadIdx.x; i < E * kCells; i += kThreads) {
     const int e = i / kCells, c = i - e * kCells;
@@ -218,6 +250,15 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   }
 #pragma unroll
   for (int i = 0; i < CPL; ++i) smem[attack_off + i * G + sub] = 0u;
+  if constexpr (kCellsInSmem) {
+    // (the cells past the end of the grid are never touched by the bulk copies: they stay zero = "no fire")
+#pragma unroll
+    for (int i = 0; i < 6 * CPL; ++i) my_state[i * G] = 0u;
+    if (bulk && lane == 0) {
+      mbarrier_init(s_barriers, 1);
+      mbarrier_init(s_barriers + 8u, 1);
+    }
+  }
   __syncthreads();
 
   FrzControl* const control = io.control;
@@ -233,14 +274,44 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   const float base_power = is_agent ? p.agent_power[sub] : 0.f;
   const float agent_yf = is_agent ? float(p.agent_y[sub]) : 0.f;
   const float agent_xf = is_agent ? float(p.agent_x[sub]) : 0.f;
-  const int burned_state = p.num_fire_states - 1, almost_state = p.num_fire_states - 2;
 
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
 
   if (!skip) {
     const int groups_per_cta = (kThreads / 32) * kGroupsPerWarp;
-    for (int env0 = (blockIdx.x * (kThreads / 32) + warp_in_cta) * kGroupsPerWarp; env0 < B;
-         env0 += gridDim.x * groups_per_cta) {
+    const int first_env0 = (blockIdx.x * (kThreads / 32) + warp_in_cta) * kGroupsPerWarp;
+    // bulk path: fetch the three state rows of environment `which` into buffer `buffer` of this group (lane 0 of the
+    // group only; the expected byte count arms the buffer's barrier)
+    const uint32_t row_bytes = 4u * uint32_t(HW);
+    const auto fetch_state = [&](int pair, uint32_t into) {  // pair = the warp's first environment of that iteration
+      // (broadcast from lane 0: the buffer index is the same in every lane, which the compiler cannot see)
+      const uint32_t buffer = __shfl_sync(kFullMask, into, 0);
+      if (lane == 0) {
+        const uint32_t barrier = s_barriers + 8u * buffer;
+        mbarrier_expect_bytes(barrier, uint32_t(kGroupsPerWarp) * 3u * row_bytes);
+#pragma unroll
+        for (int g = 0; g < kGroupsPerWarp; ++g) {
+          const size_t at = size_t(min(pair + g, B - 1)) * size_t(HW);
+          const uint32_t planes = planes_of_group(g) + kBufferBytes * buffer;
+          bulk_load(planes, io.fires + at, row_bytes, barrier);
+          bulk_load(planes + 4u * kCells, io.intensity + at, row_bytes, barrier);
+          bulk_load(planes + 8u * kCells, io.fuel + at, row_bytes, barrier);
+        }
+      }
+      if (is_agent) {  // (the staged values were consumed at the top of the current iteration)
+        const uint32_t at = uint32_t(min(pair + lane / G, B - 1)) * uint32_t(A) + uint32_t(sub);
+        cp_async_4(s_stage, io.suppressants + at);
+        cp_async_4(s_stage + 4u * G, io.capacity + at);
+        cp_async_4(s_stage + 8u * G, io.equipment + at);
+        if (mode == kStep) cp_async_8(s_stage + 12u * G + 4u * uint32_t(sub), io.actions + 2u * at);
+      }
+      cp_async_commit();
+    };
+    uint32_t buffer = 0u, parities = 0u;  // current state buffer; bit b = phase parity of buffer b's barrier
+    if constexpr (kCellsInSmem) {
+      if (bulk && first_env0 < B) fetch_state(first_env0, 0u);
+    }
+    for (int env0 = first_env0; env0 < B; env0 += gridDim.x * groups_per_cta) {
       const int env = env0 + lane / G;
       const bool valid = (G == 32) || env < B;  // sub-warp groups past the end stay for the warp-wide votes
       const int e = valid ? env : B - 1;
@@ -266,20 +337,40 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         else cell_regs[plane][i] = value;
       };
       uint32_t litw[NW], rows[CPL];
+      if constexpr (bulk) {
+        // the planes of this environment were requested one iteration ago (or in the prologue)
+        mbarrier_wait(s_barriers + 8u * buffer, (parities >> buffer) & 1u);
+        parities ^= 1u << buffer;
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) {
-        const int c = i * G + sub;
-        // pick_geometry() only chooses CPL cells per lane when the rows before the last one are full
-        const bool in_grid = i < kFullRows || c < HW;
-        const int f = in_grid ? fires_row[c] : 0;
-        set_cell(0, i, f);
-        set_cell(1, i, in_grid ? inten_row[c] : 0);
-        set_cell(2, i, in_grid ? fuel_row[c] : 0);
-        rows[i] = __ballot_sync(kFullMask, f > 0);
+        for (int i = 0; i < CPL; ++i) rows[i] = __ballot_sync(kFullMask, cell(0, i) > 0);
+      } else {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          const int c = i * G + sub;
+          // pick_geometry() only chooses CPL cells per lane when the rows before the last one are full
+          const bool in_grid = i < kFullRows || c < HW;
+          const int f = in_grid ? fires_row[c] : 0;
+          set_cell(0, i, f);
+          set_cell(1, i, in_grid ? inten_row[c] : 0);
+          set_cell(2, i, in_grid ? fuel_row[c] : 0);
+          rows[i] = __ballot_sync(kFullMask, f > 0);
+        }
       }
       float supp = 0.f, cap = 0.f;
       int equip = 0;
-      if (is_agent) {
+      int2 staged_action = make_int2(0, -1);
+      if constexpr (bulk) {
+        cp_async_wait_all();  // this lane's own copies: no other lane reads its staging slots
+        if (is_agent) {
+          supp = __uint_as_float(lds(s_stage));
+          cap = __uint_as_float(lds(s_stage + 4u * G));
+          equip = min(max(int(lds(s_stage + 8u * G)), 0), E - 1);
+          if (mode == kStep) {
+            staged_action.x = int(lds(s_stage + 12u * G + 4u * uint32_t(sub)));
+            staged_action.y = int(lds(s_stage + 12u * G + 4u * uint32_t(sub) + 4u));
+          }
+        }
+      } else if (is_agent) {
         supp = io.suppressants[agent_at];
         cap = io.capacity[agent_at];
         equip = min(max(io.equipment[agent_at], 0), E - 1);
@@ -295,11 +386,25 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       int moves = 0, total_burnouts = 0, n_burned = 0, n_putout = 0;
       bool terminated = false, truncated = false;
 
+      // bulk path: request the next environment's planes into the other buffer.  Every lane finished with that buffer
+      // at the end of the previous iteration; its write-back (the previous iteration's bulk stores, issued by the same
+      // lane) must have finished reading it.  Called a third of the way into the step so that wait is over already.
+      const auto prefetch_next = [&]() {
+        if constexpr (kCellsInSmem) {
+          const int next_env0 = env0 + gridDim.x * groups_per_cta;
+          if (bulk && next_env0 < B) {
+            if (lane == 0) bulk_wait_read();
+            fetch_state(next_env0, buffer ^ 1u);
+          }
+        }
+      };
+      if (mode != kStep) prefetch_next();
+
       if (mode == kStep) {
         // ---------------------------------------------------------------- action decode (wildfire.py:412-486)
         int act_k = 0, act_id = -1;
         if (is_agent) {
-          const int2 act = reinterpret_cast<const int2*>(io.actions)[agent_at];
+          const int2 act = bulk ? staged_action : reinterpret_cast<const int2*>(io.actions)[agent_at];
           act_k = act.x;
           act_id = act.y;
           cumulative = io.cumulative_rewards[agent_at];
@@ -374,11 +479,12 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         // after that loop, so its words are not alive across it -- feeds the spread; used by the geometries that keep
         // the cell state in shared memory (register-bound; measured 6 % slower on the others).  Otherwise the words of
         // cell i are 2i and 2i + 1 and every call is made up front.
-        constexpr bool kSplit = !INJECTED && kCellsInSmem && 2 * ((CPL + 3) / 4) == kCalls;
+        constexpr bool kSplit = !INJECTED && split_geometry(G, CPL) && 2 * ((CPL + 3) / 4) == kCalls;
         constexpr int kCallsA = kSplit ? kCalls / 2 : kCalls;
         const auto grow_word = [](int i) { return kSplit ? i : 2 * i; };
         const auto spread_word = [](int i) { return kSplit ? 4 * kCallsA + i : 2 * i + 1; };
         float ua[5], uf[INJECTED ? 3 * CPL : 1];  // uf[3*i + event]: injected / pre-converted uniforms (parity mode)
+        uint32_t ka[5];                           // Philox mode: the agents' draws as 24-bit integers
         uint32_t bits[4 * kCalls];
         const bool inject_agent = INJECTED && io.agent_uniforms != nullptr;
         const bool inject_field = INJECTED && io.field_uniforms != nullptr;
@@ -458,29 +564,41 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
               words[2] = r.z;
               words[3] = r.w;
             }
-            ua[0] = ua[2] = u01(words[0]);
-            ua[1] = u01(words[1]);
-            ua[3] = u01(words[2]);
-            ua[4] = u01(words[3]);
+            if constexpr (INJECTED) {
+              ua[0] = ua[2] = u01(words[0]);
+              ua[1] = u01(words[1]);
+              ua[3] = u01(words[2]);
+              ua[4] = u01(words[3]);
+            } else {
+              ka[0] = ka[2] = words[0] >> 8;
+              ka[1] = words[1] >> 8;
+              ka[3] = words[2] >> 8;
+              ka[4] = words[3] >> 8;
+            }
           }
+          // event `ev` happens with probability p: fp32 compare on injected uniforms, integer compare on Philox bits
+          const auto happens = [&](int ev, float p_event, uint32_t t_event) -> bool {
+            if constexpr (INJECTED) return ua[ev] < p_event;
+            else return ka[ev] < t_event;
+          };
 
           // agent transitions (the host folded the StochasticConfiguration switches into the thresholds: 2 = always, -1 = never)
           // suppressant_decrease.py:34-63
-          const bool decrease = user && ua[0] < p.p_suppressant_decrease;
+          const bool decrease = user && happens(0, p.p_suppressant_decrease, derived.t_suppressant_decrease);
           supp = fmaxf(decrease ? __fadd_rn(supp, -1.f) : supp, 0.f);
           // equipment.py:42-77 -- masks from the pre-update state, one uniform for all three tests
           {
             const bool pristine = equip == E - 1, damaged = equip == 0;
             const bool wearable = pristine || !damaged;  // pristine | intermediate
-            const bool repairs = damaged && ua[1] < p.p_repair;
-            const bool critical = pristine && ua[1] < p.p_critical;
-            const bool degrades = wearable && ua[1] < p.p_degrade && !critical;
+            const bool repairs = damaged && happens(1, p.p_repair, derived.t_repair);
+            const bool critical = pristine && happens(1, p.p_critical, derived.t_critical);
+            const bool degrades = wearable && happens(1, p.p_degrade, derived.t_degrade) && !critical;
             if (repairs) equip = E - 1;
             if (critical) equip = 0;
             if (degrades) equip -= 1;
           }
           // suppressant_refill.py:43-74 -- bonus of the equipment state AFTER its transition
-          const bool increased = refill && ua[2] < p.p_refill;
+          const bool increased = refill && happens(2, p.p_refill, derived.t_refill);
           if (increased) supp = __fadd_rn(cap, p.equipment_capacity_bonus[max(equip, 0)]);
           // capacity.py:39-66 -- bucketize(right=False): first i with r <= cum[i]
           if (__any_sync(kFullMask, increased)) {
@@ -488,9 +606,12 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             // entries with +inf), capped at the last capacity like the reference's default
             int pick = 0;
 #pragma unroll
-            for (int i = 0; i < FRZ_MAX_CAPACITIES; ++i) pick += ua[3] > p.capacity_cum[i] ? 1 : 0;
+            for (int i = 0; i < FRZ_MAX_CAPACITIES; ++i) {
+              if constexpr (INJECTED) pick += ua[3] > p.capacity_cum[i] ? 1 : 0;
+              else pick += int(ka[3]) > derived.t_capacity_cum[i] ? 1 : 0;
+            }
             pick = min(pick, p.num_capacities - 1);
-            const bool switches = increased && ua[4] < p.p_tank_switch;
+            const bool switches = increased && happens(4, p.p_tank_switch, derived.t_tank_switch);
             const float extra = __fadd_rn(supp, -cap);
             if (switches) {
               cap = p.capacity_value[pick];
@@ -513,11 +634,19 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           const bool burning = f > 0 && it > 0;
           const float diff = __fadd_rn(f > 0 ? float(f) : 0.f, -attack);
           const bool unmet = burning && diff > 0.f;
-          // (one Philox word serves both events of a cell: convert it once)
-          const float u_up = field_uniform(i, 0), u_down = INJECTED ? field_uniform(i, 1) : u_up;
-          const bool grow = unmet && u_up < (it == almost_state ? p.p_burnout : p.p_increase);
+          // (one Philox word serves both events of a cell)
+          bool grow;
+          float u_down;
+          if constexpr (INJECTED) {
+            u_down = field_uniform(i, 1);
+            grow = unmet && field_uniform(i, 0) < (it == derived.almost_state ? p.p_burnout : p.p_increase);
+          } else {
+            const uint32_t k24 = bits[grow_word(i)] >> 8;
+            u_down = float(k24) * 5.9604644775390625e-08f;
+            grow = unmet && (it == derived.almost_state ? k24 < derived.t_burnout : k24 < derived.t_increase);
+          }
           it += grow ? 1 : 0;
-          const bool burned = grow && it >= burned_state;
+          const bool burned = grow && it >= derived.burned_state;
           // fire_decrease.py:36-80 sees the post-increase state: a cell that just burned out is no longer lit, any other
           // burning cell kept its sign and a positive intensity, so `diff` is unchanged; the product and the sum are
           // rounded separately like the reference's two aten ops
@@ -542,6 +671,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
 
         // ---------------------------------------------------------------- fire spread (fire_spreads.py:33-59)
         if constexpr (kSplit) draw(kCallsA, kCalls);
+        prefetch_next();
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
           int f = cell(0, i), it = cell(1, i);
@@ -730,29 +860,19 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           const int q = first + quad_in_span;
           if (q < quads) {
             const uint4 m = lds_v4(s_tasks + 16u * uint32_t(q));
-            uint32_t planes[FRZ_MAX_AGENTS / 8];
-            planes[0] = __byte_perm(__byte_perm(m.x, m.y, 0x0040), __byte_perm(m.z, m.w, 0x0040), 0x5410);
-#pragma unroll
-            for (int k = 1; k < FRZ_MAX_AGENTS / 8; ++k) planes[k] = 0u;
-            if (A > 8) {
-#pragma unroll
-              for (int k = 1; k < FRZ_MAX_AGENTS / 8; ++k) {
-                if (k * 8 < A) {
-                  const uint32_t lo = __byte_perm(m.x, m.y, uint32_t(k | ((4 + k) << 4)));
-                  const uint32_t hi = __byte_perm(m.z, m.w, uint32_t(k | ((4 + k) << 4)));
-                  planes[k] = __byte_perm(lo, hi, 0x5410);
-                }
-              }
-            }
+            // a group of G lanes holds at most G agents: one byte plane per eight of them; the agents are visited
+            // plane by plane (the plane index is a compile-time constant inside each inner loop)
+            constexpr int kPlanes = G / 8;
             uint32_t at = mask_env + uint32_t(slot * mask_words_row + q);
             const uint32_t stride = uint32_t(slots * mask_words_row);
-            for (int a = slot; a < A; a += slots, at += stride) {
-              uint32_t plane = planes[0];
-              if (A > 8) {
+            int a = slot;
 #pragma unroll
-                for (int k = 1; k < FRZ_MAX_AGENTS / 8; ++k) plane = (a >> 3) == k ? planes[k] : plane;
-              }
-              mask_words[at] = (plane >> (a & 7)) & 0x01010101u;
+            for (int k = 0; k < kPlanes; ++k) {
+              if (k > 0 && 8 * k >= A) break;
+              const uint32_t selector = uint32_t(k | ((4 + k) << 4));
+              const uint32_t plane = __byte_perm(__byte_perm(m.x, m.y, selector), __byte_perm(m.z, m.w, selector), 0x5410);
+              const int end = min(A, 8 * k + 8);
+              for (; a < end; a += slots, at += stride) mask_words[at] = (plane >> (a & 7)) & 0x01010101u;
             }
           }
         }
@@ -765,13 +885,15 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         if (sub == 0) io.env_task_count[env] = n_lit;
 
         if (mode == kStep) {
+          if (!bulk) {
 #pragma unroll
-          for (int i = 0; i < CPL; ++i) {
-            const int c = i * G + sub;
-            if (i < kFullRows || c < HW) {
-              fires_row[c] = cell(0, i);
-              inten_row[c] = cell(1, i);
-              fuel_row[c] = cell(2, i);
+            for (int i = 0; i < CPL; ++i) {
+              const int c = i * G + sub;
+              if (i < kFullRows || c < HW) {
+                fires_row[c] = cell(0, i);
+                inten_row[c] = cell(1, i);
+                fuel_row[c] = cell(2, i);
+              }
             }
           }
           if (is_agent) {
@@ -791,7 +913,36 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           }
         }
       }
+      if constexpr (kCellsInSmem) {
+        if (bulk) {
+          if (mode == kStep) {
+            // write the stepped planes back: the lanes' shared-memory writes become visible to the async proxy, then
+            // lane 0 stores the three rows of both groups
+            fence_async_shared();
+            __syncwarp();
+            const uint32_t from = __shfl_sync(kFullMask, buffer, 0);
+            if (lane == 0) {
+#pragma unroll
+              for (int g = 0; g < kGroupsPerWarp; ++g) {
+                if (env0 + g < B) {
+                  const size_t at = size_t(env0 + g) * size_t(HW);
+                  const uint32_t planes = planes_of_group(g) + kBufferBytes * from;
+                  bulk_store(io.fires + at, planes, row_bytes);
+                  bulk_store(io.intensity + at, planes + 4u * kCells, row_bytes);
+                  bulk_store(io.fuel + at, planes + 8u * kCells, row_bytes);
+                }
+              }
+              bulk_commit();
+            }
+          }
+          buffer ^= 1u;
+          my_state = smem + tasks_off + kCells + sub + buffer * (3 * kCells);
+        }
+      }
       __syncwarp();
+    }
+    if constexpr (kCellsInSmem) {
+      if (bulk && lane == 0) bulk_wait_read();  // shared memory must outlive the last write-back
     }
   }
   finish_launch(control, alive_bits, faults, agent_bits,
@@ -910,6 +1061,26 @@ void fold_configuration(const FrzWildfireParams& in, int group, int cells_per_la
     if (x > 0) derived->west_ok[c >> 5] |= 1u << (c & 31);
     if (x < W - 1) derived->east_ok[c >> 5] |= 1u << (c & 31);
   }
+  {
+    const auto below = [](float probability) {  // u < p  <=>  k < ceil(p * 2^24)
+      const double scaled = std::ceil(double(probability) * 16777216.0);
+      return uint32_t(scaled < 0.0 ? 0.0 : (scaled > 16777216.0 ? 16777216.0 : scaled));
+    };
+    derived->t_increase = below(out->p_increase);
+    derived->t_burnout = below(out->p_burnout);
+    derived->t_suppressant_decrease = below(out->p_suppressant_decrease);
+    derived->t_repair = below(out->p_repair);
+    derived->t_critical = below(out->p_critical);
+    derived->t_degrade = below(out->p_degrade);
+    derived->t_refill = below(out->p_refill);
+    derived->t_tank_switch = below(out->p_tank_switch);
+    for (int i = 0; i < FRZ_MAX_CAPACITIES; ++i) {  // u > c  <=>  k > floor(c * 2^24)
+      const double scaled = std::floor(double(out->capacity_cum[i]) * 16777216.0);
+      derived->t_capacity_cum[i] = std::isnan(scaled) ? (1 << 24) : int32_t(scaled < -1.0 ? -1.0 : (scaled > 16777216.0 ? 16777216.0 : scaled));
+    }
+    derived->almost_state = in.num_fire_states - 2;
+    derived->burned_state = in.num_fire_states - 1;
+  }
   // Philox layout (see the kernel): lanes whose last cell is off-grid have two unused words; with an odd number of
   // cells per lane every lane has two more.  The agents' four words are taken from those when enough lanes qualify.
   derived->spare_lanes_feed_agents = 0;
@@ -922,7 +1093,7 @@ void fold_configuration(const FrzWildfireParams& in, int group, int cells_per_la
   }
 }
 
-template <int G, int CPL, int MODE, bool INJECTED>
+template <int G, int CPL, int MODE, bool INJECTED, bool BULK>
 int launch_variant(const FrzWildfireParams& caller_params, const FrzWildfireBuffers& io, int B, cudaStream_t stream) {
   FrzWildfireParams p;
   Derived derived;
@@ -931,8 +1102,9 @@ int launch_variant(const FrzWildfireParams& caller_params, const FrzWildfireBuff
   static size_t cached_smem = ~size_t(0);
   const int groups_per_cta = (kThreads / 32) * (32 / G);
   const size_t smem = (size_t(static_smem_words(G * CPL, p.num_agents, p.num_equipment_states)) +
-                       size_t(groups_per_cta) * group_smem_words(G, CPL)) * sizeof(uint32_t);
-  auto kernel = wildfire_step_kernel<G, CPL, MODE, INJECTED>;
+                       size_t(groups_per_cta) * group_smem_words(G, CPL)) * sizeof(uint32_t) +
+                      (BULK ? 16 + 16 * (kThreads / 32) : 0);  // bulk path: two mbarriers per warp
+  auto kernel = wildfire_step_kernel<G, CPL, MODE, INJECTED, BULK>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
       return check_launch("wildfire smem attribute");
@@ -954,11 +1126,23 @@ int launch_variant(const FrzWildfireParams& caller_params, const FrzWildfireBuff
   return check_launch("wildfire_step_kernel");
 }
 
+template <int G, int CPL, bool BULK>
+int launch_mode(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B, int mode, cudaStream_t stream) {
+  if (mode != kStep) return launch_variant<G, CPL, kRefresh, false, BULK>(p, io, B, stream);
+  if (io.field_uniforms != nullptr || io.agent_uniforms != nullptr) return launch_variant<G, CPL, kStep, true, BULK>(p, io, B, stream);
+  return launch_variant<G, CPL, kStep, false, BULK>(p, io, B, stream);
+}
+
 template <int G, int CPL>
 int launch_step(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B, int mode, cudaStream_t stream) {
-  if (mode != kStep) return launch_variant<G, CPL, kRefresh, false>(p, io, B, stream);
-  if (io.field_uniforms != nullptr || io.agent_uniforms != nullptr) return launch_variant<G, CPL, kStep, true>(p, io, B, stream);
-  return launch_variant<G, CPL, kStep, false>(p, io, B, stream);
+  if constexpr (cells_in_smem(G, CPL)) {
+    // the state planes move with bulk async copies when every row is a 16-byte multiple at a 16-byte aligned address
+    // (same results either way: the Philox layout only depends on the geometry)
+    const uintptr_t bases = reinterpret_cast<uintptr_t>(io.fires) | reinterpret_cast<uintptr_t>(io.intensity) |
+                            reinterpret_cast<uintptr_t>(io.fuel);
+    if ((p.height * p.width) % 4 == 0 && bases % 16 == 0) return launch_mode<G, CPL, true>(p, io, B, mode, stream);
+  }
+  return launch_mode<G, CPL, false>(p, io, B, mode, stream);
 }
 
 int dispatch(const FrzWildfireParams* p, const FrzWildfireBuffers* io, int B, int mode, void* stream) {
