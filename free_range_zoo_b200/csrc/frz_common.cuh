@@ -120,6 +120,20 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // ---------------------------------------------------------------------------------------------- bulk async copies
 
+// true in exactly one lane of a fully converged warp (the hardware's choice): the issuer of warp-uniform work such as
+// bulk copies -- the compiler emits them once, without the serialisation loop a `lane == 0` test makes it build
+__device__ __forceinline__ bool elect_one() {
+  uint32_t elected;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(elected));
+  return elected != 0u;
+}
+
 // 1-D bulk copies of the async proxy (the TMA unit; SASS UBLKCP): one elected thread moves a whole tile between global
 // and shared memory, completion of loads is signalled on an mbarrier, stores are tracked as bulk groups.  Addresses and
 // sizes must be multiples of 16 bytes.

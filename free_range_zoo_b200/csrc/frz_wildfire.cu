@@ -152,6 +152,7 @@ struct Derived {
   uint32_t t_increase, t_burnout, t_suppressant_decrease, t_repair, t_critical, t_degrade, t_refill, t_tank_switch;
   int32_t t_capacity_cum[FRZ_MAX_CAPACITIES];
   int32_t almost_state, burned_state;    // num_fire_states - 2 / - 1
+  int32_t cells;                         // height * width
 };
 
 template <int G, int CPL, int MODE, bool INJECTED, bool BULK>
@@ -188,7 +189,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
   // 16-lane groups, byte g for 8-lane groups
   const uint32_t half_selector = (G == 16) ? ((group_base & 16) ? 0x7632u : 0x5410u)
                                            : (uint32_t(group_base >> 3) | ((4u + uint32_t(group_base >> 3)) << 4));
-  const int H = p.height, W = p.width, HW = H * W;
+  const int W = p.width, HW = derived.cells;
   const int A = p.num_agents;
   const int E = p.num_equipment_states;
   const uint32_t flags = p.flags;
@@ -286,7 +287,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
     const auto fetch_state = [&](int pair, uint32_t into) {  // pair = the warp's first environment of that iteration
       // (broadcast from lane 0: the buffer index is the same in every lane, which the compiler cannot see)
       const uint32_t buffer = __shfl_sync(kFullMask, into, 0);
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t barrier = s_barriers + 8u * buffer;
         mbarrier_expect_bytes(barrier, uint32_t(kGroupsPerWarp) * 3u * row_bytes);
 #pragma unroll
@@ -655,9 +656,12 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           const bool shrink = met && u_down < prob_down;
           it -= shrink ? 1 : 0;
           const bool put = shrink && it <= 0;
-          if (burned) set_cell(2, i, max(cell(2, i) - 1, 0));  // burn-out clamps the fuel (fire_increase.py:90) ...
-          if (put) set_cell(2, i, cell(2, i) - 1);             // ... putting out does not (fire_decrease.py:75)
-          if (burned || put) f = -f;
+          if (burned || put) {
+            // burn-out clamps the fuel (fire_increase.py:90), putting out does not (fire_decrease.py:75)
+            const int fuel = cell(2, i) - 1;
+            set_cell(2, i, burned ? max(fuel, 0) : fuel);
+            f = -f;
+          }
           burned_bits |= uint32_t(burned) << i;
           putout_bits |= uint32_t(put) << i;
           if (!kCellsInSmem || burned || put) set_cell(0, i, f);
@@ -673,16 +677,25 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         if constexpr (kSplit) draw(kCallsA, kCalls);
         prefetch_next();
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-          int f = cell(0, i), it = cell(1, i);
-          const bool unlit = f < 0 && it == 0 && (!use_fuel || cell(2, i) > 0);
-          if (__any_sync(kFullMask, unlit)) {
+        for (int w = 0; w < NW; ++w) {  // word by word: the neighbour words are shared by the RPW rows of a word
+          int f[RPW], it[RPW];
+          bool unlit[RPW], any_unlit = false;
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) {
+            const int i = w * RPW + r;
+            unlit[r] = false;
+            if (i < CPL) {
+              f[r] = cell(0, i);
+              it[r] = cell(1, i);
+              unlit[r] = f[r] < 0 && it[r] == 0 && (!use_fuel || cell(2, i) > 0);
+              any_unlit = any_unlit || unlit[r];
+            }
+          }
+          if (__any_sync(kFullMask, any_unlit)) {
             // burning neighbours of cell c as bit c of four words: N = cell c-W, W = c-1, E = c+1, S = c+W
-            const int w = i / RPW;  // the word holding this row
             const uint32_t cur = burnw[w];
             const uint32_t prev = w > 0 ? burnw[w > 0 ? w - 1 : 0] : 0u;
             const uint32_t next = w + 1 < NW ? burnw[w + 1 < NW ? w + 1 : 0] : 0u;
-            const uint32_t my_bit = row_bit(i);
             uint32_t north, south;
             if (W < 32) {
               north = __funnelshift_l(prev, cur, W);
@@ -695,28 +708,41 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
             }
             const uint32_t west = __funnelshift_l(prev, cur, 1) & derived.west_ok[w];
             const uint32_t east = __funnelshift_r(cur, next, 1) & derived.east_ok[w];
-            // the conv sum in the reference's accumulation order N, W, E, S, starting from zero (spread_lut[1 << k] is
-            // the weight of direction k; see spread_lut() on the host for the order)
-            float prob = 0.f;
-            if (north & my_bit) prob = p.spread_lut[1];
-            if (west & my_bit) prob = __fadd_rn(prob, p.spread_lut[2]);
-            if (east & my_bit) prob = __fadd_rn(prob, p.spread_lut[4]);
-            if (south & my_bit) prob = __fadd_rn(prob, p.spread_lut[8]);
-            prob = __fadd_rn(prob, p.p_random_ignition);
-            if (unlit && field_uniform(i, 2) < prob) {
-              f = -f;
-              it = int(lds_const(s_cell + 4u * (kIgnitionOff + i * G)));
-              if (kCellsInSmem) {
-                set_cell(0, i, f);
-                set_cell(1, i, it);
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+              const int i = w * RPW + r;
+              if (i < CPL) {
+                const uint32_t my_bit = row_bit(i);
+                // the conv sum in the reference's accumulation order N, W, E, S, starting from zero (spread_lut[1 << k]
+                // is the weight of direction k; see spread_lut() on the host for the order)
+                float prob = 0.f;
+                if (north & my_bit) prob = p.spread_lut[1];
+                if (west & my_bit) prob = __fadd_rn(prob, p.spread_lut[2]);
+                if (east & my_bit) prob = __fadd_rn(prob, p.spread_lut[4]);
+                if (south & my_bit) prob = __fadd_rn(prob, p.spread_lut[8]);
+                prob = __fadd_rn(prob, p.p_random_ignition);
+                if (unlit[r] && field_uniform(i, 2) < prob) {
+                  f[r] = -f[r];
+                  it[r] = int(lds_const(s_cell + 4u * (kIgnitionOff + i * G)));
+                  if (kCellsInSmem) {
+                    set_cell(0, i, f[r]);
+                    set_cell(1, i, it[r]);
+                  }
+                }
               }
             }
           }
-          if (!kCellsInSmem) {
-            set_cell(0, i, f);
-            set_cell(1, i, it);
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) {
+            const int i = w * RPW + r;
+            if (i < CPL) {
+              if (!kCellsInSmem) {
+                set_cell(0, i, f[r]);
+                set_cell(1, i, it[r]);
+              }
+              rows[i] = __ballot_sync(kFullMask, f[r] > 0);
+            }
           }
-          rows[i] = __ballot_sync(kFullMask, f > 0);
         }
         assemble_words<G, CPL, NW>(rows, litw, group_base, group_mask, half_selector);
 
@@ -794,6 +820,13 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
       }
 
       // ------------------------------------------------------------------ update_actions / update_observations
+      if constexpr (G != 32) {
+        if (!valid) {  // a group past the end of the batch has no tasks to publish: no rows, no mask words below
+          n_before = 0;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) litw[w] = 0u;
+        }
+      }
       int n_lit = 0;
 #pragma unroll
       for (int w = 0; w < NW; ++w) n_lit += __popc(litw[w]);
@@ -826,8 +859,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
           if (word & my_bit) {
             const int t = rank + __popc(word & (my_bit - 1u));  // env-local task index = rank in row-major lit order
             sts(s_tasks + 4u * uint32_t(t), fighters[i]);
-            if (valid)
-              task_rows[cell_row + uint32_t(t)] = make_int4(int(lds_const(s_cell + 4u * (kYOff + i * G))), int(lds_const(s_cell + 4u * (kXOff + i * G))),
+            task_rows[cell_row + uint32_t(t)] = make_int4(int(lds_const(s_cell + 4u * (kYOff + i * G))), int(lds_const(s_cell + 4u * (kXOff + i * G))),
                                       cell(0, i), cell(1, i));
           }
         }
@@ -839,7 +871,7 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         const int t = first + sub;
         if (t < 4 * quads) {
           sts(s_tasks + 4u * uint32_t(t), 0u);
-          if (valid && t < n_before) task_rows[cell_row + uint32_t(t)] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
+          if (t < n_before) task_rows[cell_row + uint32_t(t)] = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
         }
       }
       __syncwarp();
@@ -880,7 +912,8 @@ wildfire_step_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
         if (is_agent) {
           io.agent_task_count[agent_at] = n_avail;
           if (n_avail > 0) agent_bits |= lane_bit;
-          reinterpret_cast<float4*>(io.self_obs)[agent_at] = make_float4(agent_yf, agent_xf, base_power, supp);
+          reinterpret_cast<float4*>(io.self_obs)[agent_at] =
+              make_float4(agent_yf, agent_xf, base_power, supp);
         }
         if (sub == 0) io.env_task_count[env] = n_lit;
 
@@ -1080,6 +1113,7 @@ void fold_configuration(const FrzWildfireParams& in, int group, int cells_per_la
     }
     derived->almost_state = in.num_fire_states - 2;
     derived->burned_state = in.num_fire_states - 1;
+    derived->cells = in.height * in.width;
   }
   // Philox layout (see the kernel): lanes whose last cell is off-grid have two unused words; with an odd number of
   // cells per lane every lane has two more.  The agents' four words are taken from those when enough lanes qualify.
