@@ -133,7 +133,12 @@ MAX_CHUNKS = 16
 class HostStep(C.Structure):
     """FrzHostStep: page-locked host buffers, per-slice control blocks (device) and streams of the pipelined host step."""
     _fields_ = [('actions', C.c_void_p), ('rewards', C.c_void_p), ('terminated', C.c_void_p), ('truncated', C.c_void_p),
-                ('chunk_controls', C.c_void_p), ('streams', C.POINTER(C.c_void_p)), ('chunks', C.c_int32)]
+                ('chunk_controls', C.c_void_p), ('streams', C.POINTER(C.c_void_p)), ('chunks', C.c_int32),
+                ('action_format', C.c_int32), ('packed_actions', C.c_void_p), ('pipeline', C.c_void_p)]
+
+
+HOST_ACTIONS_I32, HOST_ACTIONS_I16 = 0, 1
+ABI_VERSION = 3
 
 
 _lib = None
@@ -173,8 +178,15 @@ def library() -> C.CDLL:
                                   ('frz_rideshare_step_host', RideshareParams, RideshareBuffers)):
         getattr(lib, name).argtypes = [C.POINTER(params), C.POINTER(buffers), C.c_int32, C.POINTER(HostStep), C.c_void_p]
     lib.frz_host_slices.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
-    if lib.frz_version() != 2:
-        raise RuntimeError(f'libfrz.so ABI version {lib.frz_version()} != 2; rebuild the library')
+    if lib.frz_version() != ABI_VERSION:
+        raise RuntimeError(f'libfrz.so ABI version {lib.frz_version()} != {ABI_VERSION}; rebuild the library')
+    lib.frz_control_restore.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.frz_host_pipeline_create.argtypes = [C.POINTER(C.c_void_p)]
+    lib.frz_host_pipeline_destroy.argtypes = [C.c_void_p]
+    for name, params in (('frz_wildfire_buffer_bytes', WildfireParams), ('frz_cyber_buffer_bytes', CyberParams),
+                         ('frz_rideshare_buffer_bytes', RideshareParams)):
+        getattr(lib, name).argtypes = [C.POINTER(params), C.c_int32, C.c_char_p]
+        getattr(lib, name).restype = C.c_int64
     _lib = lib
     return lib
 

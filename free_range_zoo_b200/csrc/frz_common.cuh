@@ -4,20 +4,79 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "frz.h"
+
+// State of one caller's pipelined host step (include/frz.h): its events and, once the pipeline has run, the whole
+// multi-stream pipeline of one step as an instantiated CUDA graph -- later steps with the same buffers cost one
+// cudaGraphLaunch (plus one node update per slice when the caller hands in a different page-locked action buffer)
+// instead of ~40 stream API calls, which is what bounds a host-driven step once the copies overlap the kernels.
+struct FrzHostPipeline {
+  int device = -1;
+  cudaEvent_t events[1 + 2 * FRZ_MAX_CHUNKS] = {};
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::vector<unsigned char> signature;  // everything the captured work depends on except the host action pointer
+  struct ActionCopy {
+    cudaGraphNode_t node;
+    void* dst;
+    size_t offset, bytes;  // source = host action buffer + offset
+  };
+  std::vector<ActionCopy> action_copies;
+  const void* captured_actions = nullptr;
+};
 
 namespace frz {
 
 constexpr unsigned kFullMask = 0xffffffffu;
-constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs
+constexpr int kMaxDevices = 64;  // launch-geometry caches are kept per device ordinal
 
 // ---------------------------------------------------------------------------------------------- host side
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+inline int current_device() {
+  int device = 0;
+  cudaGetDevice(&device);
+  return device;
+}
+
+// SMs of the current device (B200: 148 = 2 dies x 74), queried once per device
+inline int sm_count() {
+  static int cache[kMaxDevices] = {};
+  const int device = current_device();
+  int count = (device >= 0 && device < kMaxDevices) ? cache[device] : 0;
+  if (count == 0) {
+    cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device);
+    if (count < 1) count = 1;
+    if (device >= 0 && device < kMaxDevices) cache[device] = count;
+  }
+  return count;
+}
+
+// resident CTAs per SM of `kernel` on the current device; cached per (instantiation, device), re-queried when the
+// dynamic shared-memory footprint changes
+template <class Kernel>
+int resident_ctas(Kernel kernel, int threads, size_t smem) {
+  static int ctas[kMaxDevices] = {};
+  static size_t smem_of[kMaxDevices] = {};
+  const int device = current_device();
+  const bool cacheable = device >= 0 && device < kMaxDevices;
+  if (cacheable && ctas[device] > 0 && smem_of[device] == smem) return ctas[device];
+  int count = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&count, kernel, threads, smem);
+  if (count < 1) count = 1;
+  if (cacheable) {
+    ctas[device] = count;
+    smem_of[device] = smem;
+  }
+  return count;
+}
+
 inline int persistent_grid(int work_ctas, int ctas_per_sm) {
-  const int cap = kSmCount * ctas_per_sm;
+  const int cap = sm_count() * ctas_per_sm;
   return work_ctas < cap ? (work_ctas < 1 ? 1 : work_ctas) : cap;
 }
 
@@ -26,7 +85,10 @@ inline int persistent_grid(int work_ctas, int ctas_per_sm) {
 // and FRZ_MAX_CHUNKS "slice i finished"
 int control_broadcast(FrzControl* main_block, FrzControl* chunk_blocks, int count, cudaStream_t stream);
 int control_merge(FrzControl* main_block, FrzControl* chunk_blocks, int count, cudaStream_t stream);
-cudaEvent_t* pipeline_events();
+// the events of `pipeline`, or (NULL) of the calling thread on the current device; nullptr + error string on failure
+cudaEvent_t* pipeline_events(FrzHostPipeline* pipeline);
+// int16 [count] -> int32 [count] on the device (FRZ_HOST_ACTIONS_I16)
+int widen_actions(const int16_t* packed, int32_t* actions, size_t count, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------- Philox4x32-10
 

@@ -594,7 +594,8 @@ int frz_cyber_step_host(const FrzCyberParams* params, const FrzCyberBuffers* io,
   }
   const size_t N = size_t(params->num_nodes), att = size_t(params->num_attackers), dfd = size_t(params->num_defenders);
   const size_t n = att + dfd;
-  const frz::HostArrays arrays{io->actions, io->rewards, io->terminated, io->truncated, io->control, int(n)};
+  const frz::HostArrays arrays{io->actions, io->rewards, io->terminated, io->truncated, io->control, int(n),
+                                 params, sizeof(FrzCyberParams), io, sizeof(FrzCyberBuffers)};
   return frz::run_host_pipeline(
       "frz_cyber_step_host", host, arrays, parallel_envs, static_cast<cudaStream_t>(stream),
       [&](int first, int count, FrzControl* control, cudaStream_t slice_stream) {

@@ -483,12 +483,15 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
 __global__ void rideshare_restore_kernel(const FrzRideshareParams p, const FrzRideshareBuffers io, const int B,
                                          const uint8_t* __restrict__ env_mask) {
   const int A = p.num_agents, K = p.capacity;
-  const int per_env = K * kCols;
+  // items per environment: table words, or driver coordinates when the table is shorter than those (a one-row
+  // schedule with many drivers) -- every driver and every reward must be reached
+  const int table_words = K * kCols;
+  const int per_env = table_words > 2 * A ? table_words : 2 * A;
   const size_t total = size_t(B) * per_env;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
     const int env = int(i / per_env), j = int(i % per_env);
     if (env_mask != nullptr && !env_mask[env]) continue;
-    io.passengers[i] = io.init_passengers[i];
+    if (j < table_words) io.passengers[size_t(env) * table_words + j] = io.init_passengers[size_t(env) * table_words + j];
     if (j < 2 * A) io.agents[size_t(env) * 2 * A + j] = io.init_agents[size_t(env) * 2 * A + j];
     if (j < A) {
       io.rewards[size_t(env) * A + j] = 0.f;
@@ -562,13 +565,7 @@ int rideshare_launch_geometry(const FrzRideshareParams* p, const FrzRideshareBuf
   auto kernel = rideshare_step_kernel<G, PPL, MODE>;
   if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
     return check_launch("rideshare shared memory");
-  static int ctas_per_sm = 0;  // per instantiation; re-queried when the table capacity (hence the footprint) changes
-  static size_t cached_smem = ~size_t(0);
-  if (smem != cached_smem) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kRsThreads, smem);
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    cached_smem = smem;
-  }
+  const int ctas_per_sm = resident_ctas(kernel, kRsThreads, smem);
   const int grid = persistent_grid((B + groups_per_cta - 1) / groups_per_cta, ctas_per_sm);
   kernel<<<grid, kRsThreads, smem, s>>>(*p, *io, B, entry_mask, batch_base);
   return check_launch("rideshare_step_kernel");
@@ -620,7 +617,8 @@ int frz_rideshare_step_host(const FrzRideshareParams* params, const FrzRideshare
     return FRZ_ERR_NULL;
   }
   const size_t A = size_t(params->num_agents), K = size_t(params->capacity);
-  const frz::HostArrays arrays{io->actions, io->rewards, io->terminated, io->truncated, io->control, params->num_agents};
+  const frz::HostArrays arrays{io->actions, io->rewards, io->terminated, io->truncated, io->control, params->num_agents,
+                                 params, sizeof(FrzRideshareParams), io, sizeof(FrzRideshareBuffers)};
   return frz::run_host_pipeline(
       "frz_rideshare_step_host", host, arrays, parallel_envs, static_cast<cudaStream_t>(stream),
       [&](int first, int count, FrzControl* control, cudaStream_t slice_stream) {

@@ -1132,8 +1132,6 @@ int launch_variant(const FrzWildfireParams& caller_params, const FrzWildfireBuff
   FrzWildfireParams p;
   Derived derived;
   fold_configuration(caller_params, G, CPL, &p, &derived);
-  static int ctas_per_sm = 0, sm_count = 0;
-  static size_t cached_smem = ~size_t(0);
   const int groups_per_cta = (kThreads / 32) * (32 / G);
   const size_t smem = (size_t(static_smem_words(G * CPL, p.num_agents, p.num_equipment_states)) +
                        size_t(groups_per_cta) * group_smem_words(G, CPL)) * sizeof(uint32_t) +
@@ -1143,19 +1141,7 @@ int launch_variant(const FrzWildfireParams& caller_params, const FrzWildfireBuff
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
       return check_launch("wildfire smem attribute");
   }
-  if (sm_count == 0) {
-    int device = 0;
-    cudaGetDevice(&device);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
-  }
-  if (smem != cached_smem) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kThreads, smem);
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    cached_smem = smem;
-  }
-  const int work = (B + groups_per_cta - 1) / groups_per_cta;
-  const int cap = sm_count * ctas_per_sm;
-  const int grid = work < cap ? work : cap;
+  const int grid = persistent_grid((B + groups_per_cta - 1) / groups_per_cta, resident_ctas(kernel, kThreads, smem));
   kernel<<<grid, kThreads, smem, stream>>>(p, io, derived, B);
   return check_launch("wildfire_step_kernel");
 }
@@ -1254,7 +1240,8 @@ int frz_wildfire_step_host(const FrzWildfireParams* params, const FrzWildfireBuf
     return FRZ_ERR_UNSUPPORTED;
   }
   const size_t HW = size_t(params->height) * params->width, A = size_t(params->num_agents);
-  const frz::HostArrays arrays{io->actions, io->rewards, io->terminated, io->truncated, io->control, params->num_agents};
+  const frz::HostArrays arrays{io->actions, io->rewards, io->terminated, io->truncated, io->control, params->num_agents,
+                                 params, sizeof(FrzWildfireParams), io, sizeof(FrzWildfireBuffers)};
   return frz::run_host_pipeline(
       "frz_wildfire_step_host", host, arrays, parallel_envs, static_cast<cudaStream_t>(stream),
       [&](int first, int count, FrzControl* control, cudaStream_t slice_stream) {
@@ -1304,7 +1291,7 @@ int frz_wildfire_reset(const FrzWildfireParams* params, const FrzWildfireBuffers
   }
   const int HW = params->height * params->width;
   const size_t total = size_t(parallel_envs) * (HW > params->num_agents ? HW : params->num_agents);
-  const int grid = int((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  const int grid = frz::persistent_grid(int((total + 255) / 256 < (1u << 20) ? (total + 255) / 256 : (1u << 20)), 16);
   frz::wildfire_restore_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*params, *io, parallel_envs, env_mask);
   const int status = frz::check_launch("wildfire_restore_kernel");
   if (status != FRZ_OK) return status;
@@ -1318,7 +1305,7 @@ int frz_wildfire_sample_actions(const FrzWildfireParams* params, const FrzWildfi
     return FRZ_ERR_NULL;
   }
   const int total = parallel_envs * params->num_agents;
-  const int grid = (total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8;
+  const int grid = frz::persistent_grid((total + 255) / 256, 8);
   frz::wildfire_sample_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*params, *io, parallel_envs, sampler_seed);
   return frz::check_launch("wildfire_sample_kernel");
 }

@@ -35,6 +35,27 @@ from free_range_zoo_b200.utils.selector import AgentSelector
 HOST_STEP_MAX_DEFAULT_CHUNKS = 5
 
 
+class _DeviceBound:
+    """libfrz entry points bound to one CUDA device: every call of the C ABI works on the CURRENT device
+    (include/frz.h), so calls made while another device is current switch to the environment's device for their
+    duration.  When it already is current (the normal case) the call goes straight through."""
+
+    def __init__(self, library, device: torch.device):
+        self._library, self._index = library, device.index
+
+    def __getattr__(self, name):
+        entry, index = getattr(self._library, name), self._index
+
+        def call(*args):
+            if torch.cuda.current_device() == index:
+                return entry(*args)
+            with torch.cuda.device(index):
+                return entry(*args)
+
+        self.__dict__[name] = call
+        return call
+
+
 def _seed_to_u64(seed) -> int:
     """Fold whatever ``reset(seed=...)`` received (None / int / list / tensor) into one 64-bit Philox key."""
     if seed is None:
@@ -113,11 +134,39 @@ class BatchedAECEnv(ABC):
                 if hasattr(value, 'validate') and not isinstance(value, torch.Tensor):
                     setattr(self, key, value)
 
-        self._lib = _lib.library()
+        self._lib = _DeviceBound(_lib.library(), self.device)
         self._tap = None  # asynchronous CSV logging (utils/logging_tap.py), created by the first reset
         self._control = torch.zeros(8, dtype=torch.int64, device=self.device)  # FrzControl, 64 bytes
         self._seed_value = None
         self._graph = None
+
+    def __del__(self):
+        handle = getattr(self, '_host_events', None)
+        if handle is not None:
+            try:
+                self._lib.frz_host_pipeline_destroy(handle)
+            except Exception:
+                pass
+            self._host_events = None
+
+    # ------------------------------------------------------------------------------------------ random stream
+
+    def generator_state_dict(self) -> Dict[str, int]:
+        """The whole random state of the engine (reference: ``RandomGenerator.state_dict``, one pickled
+        ``torch.Generator`` state per environment, utils/random_generator.py:148-162): every draw is
+        Philox(seed; global environment index, step, event), so ``seed`` and the step counter say it all.
+        Synchronises (reads the device control block)."""
+        block = self.control_block()
+        return {'seed': block['seed'], 'step': block['step'], 'env_offset': self.env_offset}
+
+    def load_generator_state_dict(self, state: Dict[str, int]) -> None:
+        """Continue the random stream of a checkpoint (reference: ``RandomGenerator.load_state_dict``,
+        utils/random_generator.py:164-176).  Restore the state tensors (``env.state().load(...)`` /
+        ``reset(options={'initial_state': ...})``) and call ``update_actions()`` to re-publish masks and flags."""
+        self._seed_value = int(state['seed'])
+        _lib.check(self._lib.frz_control_restore(self._control.data_ptr(), ctypes.c_uint64(int(state['seed'])),
+                                                 ctypes.c_uint64(int(state['step'])), self._stream()),
+                   'frz_control_restore')
 
     # ------------------------------------------------------------------------------------------ properties
 
@@ -291,7 +340,15 @@ class BatchedAECEnv(ABC):
             done=torch.stack([self._terminated, self._truncated]).cpu().pin_memory(),
             controls=torch.zeros((chunks, 8), dtype=torch.int64, device=self.device),
             streams=[torch.cuda.Stream(self.device) for _ in range(chunks)],
+            # the stream the pipeline is issued on: a capturable one (the legacy default stream is not), so that the
+            # library can replay the whole pipeline as one CUDA graph from the second call on
+            main=torch.cuda.Stream(self.device),
+            packed=torch.zeros((B, A, 2), dtype=torch.int16, device=self.device),  # staging of int16 action uploads
         )
+        if getattr(self, '_host_events', None) is None:  # this environment's own events (never shared, include/frz.h)
+            handle = ctypes.c_void_p()
+            _lib.check(self._lib.frz_host_pipeline_create(ctypes.byref(handle)), 'frz_host_pipeline_create')
+            self._host_events = handle
         handles = (ctypes.c_void_p * chunks)(*[stream.cuda_stream for stream in state['streams']])
         block = _lib.HostStep()
         block.rewards = state['rewards'].data_ptr()
@@ -300,6 +357,8 @@ class BatchedAECEnv(ABC):
         block.chunk_controls = state['controls'].data_ptr()
         block.streams = ctypes.cast(handles, ctypes.POINTER(ctypes.c_void_p))
         block.chunks = chunks
+        block.packed_actions = state['packed'].data_ptr()
+        block.pipeline = self._host_events
         done = state['done'].view(torch.bool)
         state.update(handles=handles, block=block, terminated=done[0], truncated=done[1])
         self._host_state = state
@@ -308,28 +367,35 @@ class BatchedAECEnv(ABC):
     @torch.no_grad()
     def step_host(self, host_actions: torch.Tensor, chunks: Optional[int] = None
                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """One environment step for callers that live on the host: ``host_actions`` is a page-locked int32
-        ``[B, A, 2]`` CPU tensor (agent order = ``env.agents``); returns page-locked CPU tensors ``(rewards f32 [B, A],
+        """One environment step for callers that live on the host: ``host_actions`` is a page-locked int32 -- or int16,
+        which halves the upload and is widened on the device -- ``[B, A, 2]`` CPU tensor (agent order = ``env.agents``);
+        returns page-locked CPU tensors ``(rewards f32 [B, A],
         terminated bool [B], truncated bool [B])`` that are valid when the call returns and are overwritten by the next
         ``step_host``.  Equivalent to copying the actions to the device, ``step_all`` and copying the results back,
         but the batch is cut into ``chunks`` slices whose uploads, step kernels and downloads overlap
         (``frz_<domain>_step_host``, include/frz.h); the results are bit-identical.  Observations, masks and counts stay
         on the device as usual."""
         B, A = self.parallel_envs, len(self.possible_agents)
-        if (host_actions.device.type != 'cpu' or host_actions.dtype != torch.int32 or not host_actions.is_contiguous()
-                or tuple(host_actions.shape) != (B, A, 2) or not host_actions.is_pinned()):
-            raise ValueError(f'step_host expects a page-locked contiguous int32 CPU tensor of shape {(B, A, 2)} '
+        if (host_actions.device.type != 'cpu' or host_actions.dtype not in (torch.int32, torch.int16)
+                or not host_actions.is_contiguous() or tuple(host_actions.shape) != (B, A, 2)
+                or not host_actions.is_pinned()):
+            raise ValueError(f'step_host expects a page-locked contiguous int32 / int16 CPU tensor of shape {(B, A, 2)} '
                              '(torch.empty(..., dtype=torch.int32).pin_memory())')
         state = self._host_pipeline(chunks)
         state['block'].actions = host_actions.data_ptr()
+        state['block'].action_format = (_lib.HOST_ACTIONS_I16 if host_actions.dtype == torch.int16
+                                        else _lib.HOST_ACTIONS_I32)
+        current, main = torch.cuda.current_stream(self.device), state['main']
+        main.wait_stream(current)
         _lib.check(self._host_entry()(ctypes.byref(self._params), ctypes.byref(self._io), B,
-                                      ctypes.byref(state['block']), self._stream()), 'step_host')
+                                      ctypes.byref(state['block']), ctypes.c_void_p(main.cuda_stream)), 'step_host')
+        current.wait_stream(main)  # later work on the caller's stream sees the stepped state
         # host-side bookkeeping while the device works; the views do not depend on the data
         self._mid_cycle = False
         self._rebind_outputs()
         if self.log_directory is not None:
             self._log_environment()
-        torch.cuda.current_stream(self.device).synchronize()
+        main.synchronize()
         return state['rewards'], state['terminated'], state['truncated']
 
     def _advance(self) -> None:
@@ -462,15 +528,27 @@ class BatchedAECEnv(ABC):
         """Capture ``steps`` x ``[sample_actions ->] step`` in a CUDA graph; ``replay()`` then costs one graph launch
         per ``steps`` environment steps (small batches are bound by launch latency: several steps per launch keep the
         kernels back to back).  Kernel arguments are pointer-stable and the step counter lives on the device, so the
-        graph needs no updates."""
+        graph needs no updates.  Capturing leaves the environment where it was (the warm-up launch is undone).  Replays
+        do not feed the logging tap, so a ``log_directory`` is refused."""
+        if self.log_directory is not None:
+            raise RuntimeError('graph replays bypass the logging tap; capture_graph needs log_directory=None')
         torch.cuda.synchronize(self.device)
+        # the warm-up launch outside capture (lazy module load, occupancy query) steps for real: every tensor the
+        # kernels write -- state, outputs, the control block with the Philox step counter -- is put back afterwards,
+        # so capturing does not advance the environment
+        saved = {name: tensor.clone() for name, tensor in self._bound.items()
+                 if tensor is not None and not name.startswith('init_')}
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):  # warm-up outside capture (lazy module load, occupancy query)
+        with torch.cuda.stream(side):
             if sample:
                 self.sample_actions(sampler_seed)
             self.step_environment()
         torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        for name, tensor in saved.items():
+            self._bound[name].copy_(tensor)
+        del saved
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -481,8 +559,11 @@ class BatchedAECEnv(ABC):
         self._graph = graph
 
     def replay(self) -> None:
+        """Launch the captured graph (``steps`` environment steps); outputs are re-bound like after ``step``."""
         self._graph.replay()
         self._mid_cycle = False
+        if self.detach_outputs:
+            self._rebind_outputs()
 
     def sample_actions(self, sampler_seed: int = 2026) -> torch.Tensor:
         """Uniform random legal actions for every agent, generated on the device into the staged action table

@@ -12,7 +12,11 @@
  * Conventions
  *  - Plain C, no torch types.  Every pointer inside a Frz*Buffers struct is a DEVICE pointer owned by the caller
  *    (a torch tensor's data_ptr()); the library allocates nothing, frees nothing and keeps no device state (the one
- *    exception: frz_<domain>_step_host creates a handful of timing-disabled CUDA events on first use).
+ *    exception: the timing-disabled CUDA events of frz_<domain>_step_host, owned by a FrzHostPipeline handle).
+ *  - Every call works on the CURRENT CUDA device (cudaSetDevice by the caller): buffers, stream and control block must
+ *    belong to it.  Launch geometry (SM count, resident CTAs) is queried per device.
+ *  - frz_<domain>_buffer_bytes() gives the size of every array of a Frz*Buffers struct, so a C caller can allocate
+ *    them without reading the Python host code.
  *  - Every call only enqueues work on the caller's cudaStream_t (passed as void*): no synchronisation, no
  *    allocation, no host read-back -> capturable in a CUDA graph.  The step counter / seed / done flags live in the
  *    device-side FrzControl block and are advanced by the kernels themselves, so graph replays need no new arguments.
@@ -32,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FRZ_ABI_VERSION 2
+#define FRZ_ABI_VERSION 3
 
 #define FRZ_MAX_AGENTS 32      /* agents per environment (one warp lane each) */
 #define FRZ_MAX_EQUIPMENT 8    /* wildfire equipment states */
@@ -324,14 +328,27 @@ int frz_rideshare_sample_actions(const FrzRideshareParams* params, const FrzRide
  * Injected uniforms (parity mode) are not supported on this path. */
 #define FRZ_MAX_CHUNKS 16
 
+/* Events of the pipelined host step: one handle per caller (environment object / host thread) and device, so that two
+ * environments -- or two devices in one process -- never share an event.  Created on the current device. */
+typedef struct FrzHostPipeline FrzHostPipeline;
+int frz_host_pipeline_create(FrzHostPipeline** out);
+int frz_host_pipeline_destroy(FrzHostPipeline* pipeline);
+
+#define FRZ_HOST_ACTIONS_I32 0  /* actions: int32 [B, A, 2], the device layout */
+#define FRZ_HOST_ACTIONS_I16 1  /* actions: int16 [B, A, 2] -- half the upload; widened on the device (every task index
+                                   and action id of the three domains fits: <= 256 tasks, ids in [-3, 2]) */
+
 typedef struct {
-  const int32_t* actions;      /* HOST, page-locked: [B, A, 2] */
+  const void* actions;         /* HOST, page-locked: [B, A, 2] in `action_format` */
   float* rewards;              /* HOST, page-locked: [B, A] */
   uint8_t* terminated;         /* HOST, page-locked: [B] */
   uint8_t* truncated;          /* HOST, page-locked: [B] */
   FrzControl* chunk_controls;  /* DEVICE scratch owned by the caller: `chunks` control blocks (64 bytes each) */
   void* const* streams;        /* `chunks` cudaStream_t of the caller, one per slice */
   int32_t chunks;              /* 1 .. FRZ_MAX_CHUNKS */
+  int32_t action_format;       /* FRZ_HOST_ACTIONS_* */
+  int16_t* packed_actions;     /* DEVICE scratch [B, A, 2] int16, required for FRZ_HOST_ACTIONS_I16 */
+  FrzHostPipeline* pipeline;   /* NULL = per-thread, per-device events kept by the library */
 } FrzHostStep;
 
 int frz_wildfire_step_host(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
@@ -351,6 +368,18 @@ int frz_version(void);
 const char* frz_last_error(void);
 /* (re)initialise a control block on the device: seed, step = 0, alive = 3, error_word = 0 */
 int frz_control_init(FrzControl* control, uint64_t seed, void* stream);
+/* Restore the random stream of a checkpoint: (seed, step) are all the generator state there is -- every draw is
+ * Philox(seed; global env, step, event) -- so this is the engine's load_state_dict (the reference pickles one
+ * torch.Generator state per environment: utils/random_generator.py:148-176).  The published flags (alive,
+ * agents_with_tasks) are recomputed by the frz_<domain>_refresh the caller runs after restoring the state arrays. */
+int frz_control_restore(FrzControl* control, uint64_t seed, uint64_t step, void* stream);
+
+/* Size in bytes of the array behind field `field` of Frz<Domain>Buffers (its name as spelled in the struct, e.g.
+ * "fires", "action_mask", "task_obs") for `parallel_envs` environments of this configuration; -1 for an unknown
+ * name.  (wildfire: mask_stride = H*W rounded up to a multiple of 4; rideshare: rows per table = params->capacity.) */
+int64_t frz_wildfire_buffer_bytes(const FrzWildfireParams* params, int32_t parallel_envs, const char* field);
+int64_t frz_cyber_buffer_bytes(const FrzCyberParams* params, int32_t parallel_envs, const char* field);
+int64_t frz_rideshare_buffer_bytes(const FrzRideshareParams* params, int32_t parallel_envs, const char* field);
 
 #ifdef __cplusplus
 }

@@ -44,25 +44,42 @@ def main():
         raw.step_all()
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream(device)
+    side = torch.cuda.Stream(device)
+    packed = host_actions.to(torch.int16).pin_memory()
     for chunks in [int(c) for c in args.slices.split(',')]:
         row = {'chunks': chunks}
-        for mode in ('abi_only', 'step_host'):
+        # direct: every stream call issued per step (no pipeline handle); graph: the library replays the captured
+        # pipeline (handle + capturable stream); *_i16: int16 actions
+        for mode in ('direct', 'graph', 'graph_i16', 'step_host', 'step_host_i16'):
             env.reset(seed=1)
             state = raw._host_pipeline(chunks)
-            times = []
+            block = state['block']
+            saved = block.pipeline
+            times, issue = [], []
             for t in range(steps + 5):
                 torch.cuda.synchronize()
                 begin = time.perf_counter()
-                if mode == 'abi_only':
-                    state['block'].actions = host_actions[t].data_ptr()
-                    _lib.check(raw._host_entry()(ctypes.byref(raw._params), ctypes.byref(raw._io), B,
-                                                 ctypes.byref(state['block']), raw._stream()))
-                    stream.synchronize()
+                if mode.startswith('step_host'):
+                    env.step_host(packed[t] if mode.endswith('i16') else host_actions[t], chunks)
+                    issued = begin
                 else:
-                    env.step_host(host_actions[t], chunks)
+                    source = packed if mode.endswith('i16') else host_actions
+                    block.actions = source[t].data_ptr()
+                    block.action_format = 1 if mode.endswith('i16') else 0
+                    block.pipeline = None if mode == 'direct' else saved
+                    on = stream if mode == 'direct' else side
+                    _lib.check(raw._host_entry()(ctypes.byref(raw._params), ctypes.byref(raw._io), B, ctypes.byref(block),
+                                                 ctypes.c_void_p(on.cuda_stream)))
+                    issued = time.perf_counter()
+                    on.synchronize()
                 times.append(time.perf_counter() - begin)
-            times = sorted(times[5:])
+                issue.append(issued - begin)
+            block.pipeline = saved
+            block.action_format = 0
+            times, issue = sorted(times[5:]), sorted(issue[5:])
             row[mode + '_us'] = round(1e6 * times[len(times) // 2], 1)
+            if not mode.startswith('step_host'):
+                row[mode + '_issue_us'] = round(1e6 * issue[len(issue) // 2], 1)
         print(json.dumps(row), flush=True)
     # the unpipelined sequence on one stream, for comparison
     env.reset(seed=1)

@@ -31,10 +31,10 @@ def lib():
 
 def test_every_declared_symbol_is_exported(lib):
     declared = _lib.exported_symbols()
-    assert len(declared) == 19  # 4 library-wide + 5 per domain
+    assert len(declared) == 25  # 7 library-wide + 6 per domain
     missing = [name for name in declared if not hasattr(lib, name)]
     assert not missing, missing
-    assert lib.frz_version() == 2
+    assert lib.frz_version() == _lib.ABI_VERSION == 3
 
 
 def test_ctypes_mirrors_match_the_c_layout(tmp_path):
@@ -123,3 +123,44 @@ def test_host_step_slices(lib):
         _lib.host_slices(0, 2)
     with pytest.raises(RuntimeError):
         _lib.host_slices(100, _lib.MAX_CHUNKS + 1)
+
+
+def test_buffer_bytes_matches_the_host_allocations(lib):
+    """frz_<domain>_buffer_bytes (pure host logic): the sizes a C caller needs equal what the Python host allocates --
+    checked against the shapes / dtypes documented in include/frz.h for one configuration per domain."""
+    import torch
+
+    from free_range_zoo_b200 import presets
+    from free_range_zoo_b200.envs.cybersecurity.env import cybersecurity
+    from free_range_zoo_b200.envs.rideshare.env import rideshare
+    from free_range_zoo_b200.envs.wildfire.env import wildfire
+    B = 37
+    params = wildfire.flatten_configuration(presets.wildfire_large(), 100, False)[0]
+    sizes = {name: lib.frz_wildfire_buffer_bytes(ctypes.byref(params), B, name.encode())
+             for name, _ in _lib.WildfireBuffers._fields_ if name not in ('mask_stride', 'mask_words')}
+    assert sizes['fires'] == sizes['intensity'] == sizes['init_fuel'] == 4 * B * 100
+    assert sizes['action_mask'] == B * 10 * 100 and sizes['task_obs'] == 16 * B * 100 and sizes['self_obs'] == 16 * B * 10
+    assert sizes['actions'] == 8 * B * 10 and sizes['terminated'] == B and sizes['control'] == 64
+    assert sizes['range_mask'] == 4 * 10 * 3 * 4 and sizes['cell_agents'] == 4 * 3 * 100
+    assert all(value > 0 for value in sizes.values()), sizes
+    assert lib.frz_wildfire_buffer_bytes(ctypes.byref(params), B, b'no_such_field') == -1
+    assert b'unknown buffer field' in lib.frz_last_error()
+    assert lib.frz_wildfire_buffer_bytes(None, B, b'fires') == -1
+
+    cy_params = cybersecurity.flatten_configuration(presets.cyber_c3(), 100, False)[0]
+    cy = {name: lib.frz_cyber_buffer_bytes(ctypes.byref(cy_params), B, name.encode()) for name, _ in _lib.CyberBuffers._fields_}
+    assert cy['network_state'] == 4 * B * 3 and cy['presence'] == B * 4 and cy['defender_self'] == 12 * B * 2
+    assert cy['task_obs'] == 8 * B * 3 and cy['score_lut'] == 4 * 16 and min(cy.values()) > 0
+
+    rs_params = rideshare.flatten_configuration(presets.rideshare_c2(), 100, 0)[0]
+    rs = {name: lib.frz_rideshare_buffer_bytes(ctypes.byref(rs_params), B, name.encode())
+          for name, _ in _lib.RideshareBuffers._fields_}
+    K = rs_params.capacity
+    assert rs['passengers'] == 4 * B * K * 11 and rs['task_mask'] == B * 4 * K and rs['task_obs'] == 32 * B * K
+    assert rs['schedule'] == 4 * 32 * 7 and min(rs.values()) > 0
+
+
+def test_host_pipeline_handle_argument_checks(lib):
+    assert lib.frz_host_pipeline_create(None) == 1  # FRZ_ERR_NULL
+    assert lib.frz_host_pipeline_destroy(None) == 0
+    assert lib.frz_control_restore(None, 1, 2, None) == 1

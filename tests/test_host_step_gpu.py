@@ -38,15 +38,16 @@ def device_arrays(raw):
             if tensor is not None and not name.startswith('init_') and name != 'control'}
 
 
+@pytest.mark.parametrize('dtype', [torch.int32, torch.int16], ids=['i32', 'i16'])
 @pytest.mark.parametrize('domain,preset,kwargs,B,chunks', CASES)
-def test_host_step_equals_device_step(domain, preset, kwargs, B, chunks):
+def test_host_step_equals_device_step(domain, preset, kwargs, B, chunks, dtype):
     steps = 12
     device_env, host_env = make(domain, preset, kwargs, B, 10), make(domain, preset, kwargs, B, 10)
     device_env.reset(seed=11)
     host_env.reset(seed=11)
     reference, raw = device_env.unwrapped, host_env.unwrapped
     A = len(raw.agents)
-    host_actions = torch.empty((B, A, 2), dtype=torch.int32).pin_memory()
+    host_actions = torch.empty((B, A, 2), dtype=dtype).pin_memory()  # int16 pairs are widened on the device
     for t in range(steps):  # runs past max_steps: the "every environment is done" early-out is covered too
         reference.sample_actions(5)
         host_actions.copy_(reference._actions)
@@ -107,3 +108,80 @@ def test_host_step_rejects_unpinned_or_misshaped_actions():
         raw.step_host(torch.zeros((64, A, 2), dtype=torch.int64).pin_memory())
     rewards, terminated, truncated = env.step_host(torch.full((64, A, 2), -1, dtype=torch.int32).pin_memory())
     assert rewards.shape == (64, A) and terminated.shape == (64, ) and not np.asarray(truncated).any()
+
+
+def test_two_environments_keep_their_own_pipeline_events():
+    """Each environment owns a FrzHostPipeline handle: host steps of two environments interleave without sharing events."""
+    a, b = make('wildfire', 'wildfire_large', {}, 26000, 50), make('wildfire', 'wildfire_large', {}, 26000, 50)
+    a.reset(seed=1)
+    b.reset(seed=1)
+    ra, rb = a.unwrapped, b.unwrapped
+    actions = torch.empty((26000, 10, 2), dtype=torch.int32).pin_memory()
+    for _ in range(4):
+        ra.sample_actions(3)
+        actions.copy_(ra._actions)
+        torch.cuda.synchronize()
+        first = [t.clone() for t in ra.step_host(actions, 3)]
+        second = rb.step_host(actions, 2)
+        for x, y in zip(first, second):
+            assert torch.equal(x, y)
+    assert ra._host_events.value != rb._host_events.value
+    assert torch.equal(ra.state().fires, rb.state().fires)
+
+
+@pytest.mark.parametrize('domain,preset,kwargs', [
+    ('wildfire', 'wildfire_large', {}),
+    ('cybersecurity', 'cyber_c3', dict(show_bad_actions=False, partially_observable=True)),
+])
+def test_generator_state_restores_a_checkpoint(domain, preset, kwargs):
+    """generator_state_dict / load_generator_state_dict (reference: RandomGenerator.state_dict / load_state_dict,
+    utils/random_generator.py:148-176): state tensors + (seed, step) continue a rollout bit for bit."""
+    B = 700
+    env = make(domain, preset, kwargs, B, 100)
+    env.reset(seed=77)
+    raw = env.unwrapped
+    for _ in range(6):
+        raw.sample_actions(8)
+        raw.step_all()
+    checkpoint = {name: tensor.clone() for name, tensor in device_arrays(raw).items()}
+    generator = raw.generator_state_dict()
+    assert generator['seed'] == 77 and generator['step'] == 6
+    for _ in range(5):
+        raw.sample_actions(8)
+        raw.step_all()
+    want = {name: tensor.clone() for name, tensor in device_arrays(raw).items()}
+
+    other = make(domain, preset, kwargs, B, 100)
+    other.reset(seed=123)  # a different stream, then the checkpoint is loaded over it
+    restored = other.unwrapped
+    for name, tensor in checkpoint.items():
+        restored._bound[name].copy_(tensor)
+    restored.load_generator_state_dict(generator)
+    restored.update_actions()
+    for _ in range(5):
+        restored.sample_actions(8)
+        restored.step_all()
+    for name, tensor in want.items():
+        assert torch.equal(restored._bound[name], tensor), name
+
+
+def test_capture_graph_does_not_advance_the_environment():
+    env = make('wildfire', 'wildfire_3x3', {}, 1500, 100)
+    env.reset(seed=5)
+    raw = env.unwrapped
+    for _ in range(3):
+        raw.sample_actions(2)
+        raw.step_all()
+    before = {name: tensor.clone() for name, tensor in raw._bound.items() if tensor is not None}
+    raw.capture_graph(sample=True, sampler_seed=2, steps=2)
+    for name, tensor in before.items():
+        assert torch.equal(raw._bound[name], tensor), name
+    twin = make('wildfire', 'wildfire_3x3', {}, 1500, 100)
+    twin.reset(seed=5)
+    for _ in range(5):
+        twin.unwrapped.sample_actions(2)
+        twin.unwrapped.step_all()
+    raw.replay()  # two more steps
+    torch.cuda.synchronize()
+    assert torch.equal(raw.state().fires, twin.unwrapped.state().fires)
+    assert torch.equal(raw._cumulative, twin.unwrapped._cumulative)

@@ -147,3 +147,30 @@ def test_flat_table_view_and_partial_reset():
     assert torch.equal(again[again[:, 0] == 7][:, 1:], first[first[:, 0] == 7][:, 1:])
     assert torch.equal(raw.state().passenger_table[0, :int(moved.passenger_count[0])],
                        moved.passenger_table[0, :int(moved.passenger_count[0])])
+
+
+def test_reset_reaches_every_driver_when_the_table_is_shorter_than_the_driver_list():
+    """A one-row schedule (11 table words per environment) with 12 drivers (24 coordinates): the restore kernel must
+    still put every driver back and zero every reward."""
+    config = presets.rideshare_synthetic(drivers=12, rows=1, horizon=3, height=6, width=7)
+    B = 300
+    env = make_env(config, B, 50)
+    env.reset(seed=0)
+    raw = env.unwrapped
+    start = raw.state().agents.clone()
+    for _ in range(6):
+        raw.sample_actions(4)
+        raw.step_all()
+    raw._cumulative.fill_(3.0)
+    raw.state().agents.add_(1)
+    picked = torch.arange(0, B, 3, device='cuda')
+    env.reset_batches(picked)
+    torch.cuda.synchronize()
+    assert torch.equal(raw.state().agents[picked], start[picked])
+    assert (raw._cumulative[picked] == 0).all() and (raw._rewards[picked] == 0).all()
+    keep = torch.ones(B, dtype=torch.bool, device='cuda')
+    keep[picked] = False
+    assert (raw._cumulative[keep] == 3.0).all()
+    env.reset(seed=0)
+    torch.cuda.synchronize()
+    assert torch.equal(raw.state().agents, start) and (raw._cumulative == 0).all()
