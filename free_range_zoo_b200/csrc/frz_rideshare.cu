@@ -20,6 +20,10 @@
 #include <climits>
 #include <math_constants.h>
 
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
 #include "frz_common.cuh"
 #include "frz_host.cuh"
 
@@ -480,6 +484,606 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
                 skip ? kPublishNothing : (MODE == kRsStep ? kPublishStep : kPublishRefresh));
 }
 
+// ------------------------------------------------------------------------------------------------ tiled kernel
+//
+// One THREAD per environment, a warp per tile of 32 consecutive environments (tables with a multiple of four rows and at
+// most eight drivers -- the named configurations; everything else takes the group kernel above).  The arithmetic of a
+// rideshare step is a few dozen decisions per environment, so a lane-per-row mapping spends its instructions on ballots
+// and on lanes without a row; here a thread walks its environment's rows serially (row sets are bit masks in registers)
+// and a warp instruction serves 32 environments instead of 4.
+//
+// What makes that possible is the staging: the live rows of an environment are one contiguous byte range of the table
+// (rows 0 .. count-1 of its slot), so they move global -> shared -> global as ONE 1-D bulk async copy per environment
+// (cp.async.bulk, the TMA unit; completion on the warp's mbarrier), never through registers or the LSU.  The warp's
+// buffer is carved up by a prefix sum over what its environments need this step (live rows + rows that may enter), so
+// shared memory is sized for the typical table fill, not for the capacity; a tile whose environments do not fit in one
+// go is stepped in several passes (each pass takes the longest prefix of the waiting environments that fits).
+constexpr int kTileThreads = 128;
+constexpr int kTileWarps = kTileThreads / 32;
+constexpr int kTileRowBudget = 8;   // rows per environment the warp buffers are sized for (32 * 8 rows per warp)
+
+constexpr int kTileIndexWords = 2048;      // longest schedule_index copied to shared memory
+constexpr int kTileMinimumBatch = 49152;   // environments from which the tiled kernel is used (measured cross-over)
+
+// Tuning knobs for kernel experiments (profiles/README.md), read once: FRZ_RIDESHARE_KERNEL=groups|tiles forces one of
+// the two kernels whatever the batch size, FRZ_RIDESHARE_TILE_ROWS=n sizes the warp buffers of the tiled kernel for n
+// rows per environment.
+inline int rideshare_kernel_choice() {  // 0 = by batch size, 1 = tiles, 2 = groups
+  static const int choice = [] {
+    const char* name = std::getenv("FRZ_RIDESHARE_KERNEL");
+    if (name == nullptr) return 0;
+    return std::strcmp(name, "tiles") == 0 ? 1 : (std::strcmp(name, "groups") == 0 ? 2 : 0);
+  }();
+  return choice;
+}
+inline int tile_row_budget() {
+  static const int rows = [] {
+    const char* choice = std::getenv("FRZ_RIDESHARE_TILE_ROWS");
+    const int value = choice != nullptr ? std::atoi(choice) : 0;
+    return value >= 1 && value <= FRZ_MAX_PASSENGERS ? value : kTileRowBudget;
+  }();
+  return rows;
+}
+
+__device__ __forceinline__ int mask_count(uint32_t m) { return __popc(m); }
+__device__ __forceinline__ int mask_count(uint64_t m) { return __popcll(m); }
+__device__ __forceinline__ int mask_first(uint32_t m) { return __ffs(int(m)) - 1; }
+__device__ __forceinline__ int mask_first(uint64_t m) { return __ffsll((long long)(m)) - 1; }
+__device__ __forceinline__ int mask_last(uint32_t m) { return 31 - __clz(int(m)); }
+__device__ __forceinline__ int mask_last(uint64_t m) { return 63 - __clzll((long long)(m)); }
+__device__ __forceinline__ int mask_select(uint32_t m, int k) { return select_bit(m, k); }
+__device__ __forceinline__ int mask_select(uint64_t m, int k) { return select_bit64(m, k); }
+
+template <int MAXA, bool WIDE, int MODE>
+__global__ void __launch_bounds__(kTileThreads, MAXA <= 4 ? 5 : 3)
+rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid_constant__ FrzRideshareBuffers io,
+                      const int B, const uint8_t* __restrict__ entry_mask, const int batch_base,
+                      const uint32_t warp_bytes, const int index_words, const uint32_t inverse_rows,
+                      const uint32_t inverse_agents) {
+  using Mask = typename std::conditional<WIDE, uint64_t, uint32_t>::type;
+  extern __shared__ __align__(16) int smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(kFullMask, int(threadIdx.x >> 5), 0);  // warp-uniform by construction
+  const int warps = blockDim.x >> 5;
+  const int K = p.capacity, A = p.num_agents, S = p.schedule_rows;
+  const uint32_t table_words = uint32_t(K * kCols);
+  const uint32_t buffer = shared_address(smem) + uint32_t(warp) * warp_bytes;
+  int* const buffer_words = smem + warp * int(warp_bytes >> 2);
+  // after the table buffers: per warp the 32 x A task lists of its tile as row sets, then the mbarriers, then
+  // schedule_index
+  constexpr int kSetWords = int(sizeof(Mask) / 4);
+  Mask* const members_of = reinterpret_cast<Mask*>(smem + warps * int(warp_bytes >> 2)) + warp * 32 * A;
+  int* const after_masks = smem + warps * int(warp_bytes >> 2) + warps * 32 * A * kSetWords;
+  const uint32_t barrier = shared_address(after_masks) + 8u * uint32_t(warp);
+  // schedule_index[0 .. index_words) copied next to the barriers (index_words = 0: the schedule is too long, read it
+  // from global memory): turns the dependent load "count -> step -> schedule rows entering now" into a shared-memory read
+  int* const index_copy = after_masks + 2 * warps;
+  for (int i = threadIdx.x; i < index_words; i += blockDim.x) index_copy[i] = io.schedule_index[i];
+  if (lane == 0) mbarrier_init(barrier, 1);
+  __syncthreads();
+  uint32_t phase = 0;
+
+  FrzControl* control = io.control;
+  const uint32_t alive_prev = control->alive;
+  const uint32_t agents_with_tasks = control->agents_with_tasks;
+  const bool skip = (MODE == kRsStep) && ((alive_prev & 3u) != 3u);  // utils/env.py:212
+  const bool fast = p.flags & FRZ_RS_FAST_TRAVEL, diagonal = p.flags & FRZ_RS_DIAGONAL_TRAVEL;
+  const int directions = diagonal ? 9 : 5;
+  const bool even_agents = (A & 1) == 0, quad_agents = (A & 3) == 0;
+  const uint32_t one_table = (table_words * 4u + 15u) & ~15u;
+  unsigned alive_bits = 0, faults = 0, agent_bits = 0;
+
+  if (!skip) {
+    const int tile_stride = gridDim.x * warps * 32;
+    int tile0 = (blockIdx.x * warps + warp) * 32;
+    // table fill and step of the tile's environments: loaded one tile ahead
+    int next_count = 0, next_moves = 0;
+    if (tile0 + lane < B) {
+      next_count = io.env_task_count[tile0 + lane];
+      next_moves = io.num_moves[tile0 + lane];
+    }
+    for (; tile0 < B; tile0 += tile_stride) {
+      const int env = tile0 + lane;
+      const bool valid = env < B;
+      const int n_before = valid ? min(next_count, K) : 0, t_now = valid ? next_moves : 0;
+      if (tile0 + tile_stride + lane < B) {
+        next_count = io.env_task_count[tile0 + tile_stride + lane];
+        next_moves = io.num_moves[tile0 + tile_stride + lane];
+      }
+      const bool admits =
+          valid && (MODE == kRsStep || (MODE == kRsEntryRefresh && (entry_mask == nullptr || entry_mask[env])));
+      const int t_entry = (MODE == kRsStep) ? t_now + 1 : t_now;  // rideshare.py:307 vs :212
+      // rows of the time-sorted schedule that enter at t_entry: [schedule_index[t], schedule_index[t + 1])
+      int lo = S, hi = S;
+      if (admits && t_entry >= 0 && t_entry <= p.schedule_horizon) {
+        if (index_words > 0) {
+          lo = index_copy[t_entry];
+          hi = index_copy[t_entry + 1];
+        } else {
+          lo = io.schedule_index[t_entry];
+          hi = io.schedule_index[t_entry + 1];
+        }
+      }
+      // shared memory this environment needs: its live rows and the rows that may enter, in whole 16-byte pieces
+      const uint32_t need = valid ? (uint32_t(min(K, n_before + (hi - lo)) * kCols * 4) + 15u) & ~15u : 0u;
+      const uint32_t bytes_in = (uint32_t(n_before * kCols * 4) + 15u) & ~15u;
+      int* const global_rows = io.passengers + size_t(tile0) * size_t(table_words);  // of the tile's first environment
+
+      // ------------------------------------------------------------------ drivers and their actions
+      // (requested before the tables are staged: these loads fly while the bulk copies do)
+      const uint32_t agent_at = uint32_t(env) * uint32_t(A);
+      int agent_y[MAXA], agent_x[MAXA], act_k[MAXA], act_id[MAXA];
+      float cumulative[MAXA];
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a) {
+        agent_y[a] = agent_x[a] = act_k[a] = 0;
+        act_id[a] = -100;
+        cumulative[a] = 0.f;
+      }
+      if (valid) {
+        if (even_agents) {  // two drivers per 16-byte load
+#pragma unroll
+          for (int j = 0; j < MAXA / 2; ++j) {
+            if (2 * j < A) {
+              const int4 at = reinterpret_cast<const int4*>(io.agents)[(agent_at >> 1) + j];
+              agent_y[2 * j] = at.x, agent_x[2 * j] = at.y, agent_y[2 * j + 1] = at.z, agent_x[2 * j + 1] = at.w;
+              if (MODE == kRsStep) {
+                const int4 act = reinterpret_cast<const int4*>(io.actions)[(agent_at >> 1) + j];
+                act_k[2 * j] = act.x, act_id[2 * j] = act.y, act_k[2 * j + 1] = act.z, act_id[2 * j + 1] = act.w;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int a = 0; a < MAXA; ++a) {
+            if (a < A) {
+              const int2 at = reinterpret_cast<const int2*>(io.agents)[agent_at + a];
+              agent_y[a] = at.x, agent_x[a] = at.y;
+              if (MODE == kRsStep) {
+                const int2 act = reinterpret_cast<const int2*>(io.actions)[agent_at + a];
+                act_k[a] = act.x, act_id[a] = act.y;
+              }
+            }
+          }
+        }
+        if (MODE == kRsStep) {
+          if (quad_agents) {
+#pragma unroll
+            for (int j = 0; j < MAXA / 4; ++j) {
+              if (4 * j < A) {
+                const float4 sum = reinterpret_cast<const float4*>(io.cumulative_rewards)[(agent_at >> 2) + j];
+                cumulative[4 * j] = sum.x, cumulative[4 * j + 1] = sum.y, cumulative[4 * j + 2] = sum.z, cumulative[4 * j + 3] = sum.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a)
+              if (a < A) cumulative[a] = io.cumulative_rewards[agent_at + a];
+          }
+        }
+      }
+
+      for (uint32_t pending = __ballot_sync(kFullMask, valid); pending != 0u;) {
+        // the environments of this pass: a prefix of the waiting ones whose rows fit in the warp's buffer (never empty:
+        // one table always fits); when the tile needs several passes they are cut into pieces of similar size
+        const bool waiting = (pending >> lane) & 1u;
+        const uint32_t mine = waiting ? need : 0u;
+        uint32_t scan = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t below = __shfl_up_sync(kFullMask, scan, d);
+          if (lane >= d) scan += below;
+        }
+        const uint32_t total = __shfl_sync(kFullMask, scan, 31);
+        uint32_t limit = warp_bytes;
+        if (total > warp_bytes) {
+          const uint32_t passes = (total + warp_bytes - 1u) / warp_bytes;
+          limit = min(warp_bytes, (total + passes - 1u) / passes + one_table);
+        }
+        const bool now = waiting && scan <= limit;
+        const uint32_t batch = __ballot_sync(kFullMask, now);
+        const uint32_t offset = scan - mine;  // of this environment's rows in the warp's buffer (a multiple of 16)
+        int* const rows = buffer_words + (offset >> 2);
+
+        // ---------------------------------------------------------------- stage the live rows (one bulk copy each)
+        const uint32_t load_bytes = now ? bytes_in : 0u;
+        const uint32_t total_in = __reduce_add_sync(kFullMask, load_bytes);
+        bulk_wait_read();  // the previous pass's write-back has left the buffer
+#ifndef FRZ_RS_ABLATE
+#define FRZ_RS_ABLATE 0  // profiling experiments (profiles/README.md): 1 = copies only, 2 = no copies, 3 = no observation stores
+#endif
+        if (total_in != 0u && FRZ_RS_ABLATE != 2) {
+          if (elect_one()) mbarrier_expect_bytes(barrier, total_in);
+          const uint32_t piece = (offset << 4) | (load_bytes >> 4);  // (offset / 16) << 8 | bytes / 16
+          const int* source = global_rows;
+#pragma unroll 4
+          for (int e = 0; e < 32; ++e, source += table_words) {
+            const uint32_t of = __shfl_sync(kFullMask, piece, e);
+            if ((of & 0xffu) != 0u) {
+              if (elect_one()) bulk_load(buffer + ((of >> 8) << 4), source, (of & 0xffu) << 4, barrier);
+            }
+          }
+          mbarrier_wait(barrier, phase);
+          phase ^= 1u;
+        }
+
+        int n_rows = n_before, obs_rows = 0;
+        Mask* const my_members = members_of + lane * A;  // this environment's task lists as row sets, one per driver
+        if (now && FRZ_RS_ABLATE != 1) {
+          int fare_won[MAXA];
+          float move_cost[MAXA];
+#pragma unroll
+          for (int a = 0; a < MAXA; ++a) fare_won[a] = 0, move_cost[a] = 0.f;
+
+          if (MODE == kRsStep) {
+            // ---------------------------------------------------------------- task lists (rideshare.py:374-386)
+            Mask unaccepted = 0, riding = 0, own[MAXA];
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a) own[a] = 0;
+            for (int r = 0; r < n_before; ++r) {
+              const int state = rows[r * kCols + cState], assoc = rows[r * kCols + cAssoc];
+              const Mask bit = Mask(1) << r;
+              if (state == 0) unaccepted |= bit;
+              if (state == 2) riding |= bit;
+#pragma unroll
+              for (int a = 0; a < MAXA; ++a)
+                if (assoc == a) own[a] |= bit;
+            }
+
+            // ---------------------------------------------------------------- decode + movement
+            // (rideshare.py:255-300, transitions/movement.py:57-116)
+            int target[MAXA], distance2[MAXA], move_y[MAXA], move_x[MAXA], fare_target[MAXA];
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a) {
+              target[a] = -1, distance2[a] = INT_MAX, move_y[a] = move_x[a] = 0, fare_target[a] = 0;
+              if (a < A) {
+                const bool noop = act_id[a] == -1, acts = act_id[a] == 0 || act_id[a] == 1 || act_id[a] == 2;
+                // the reference only resolves targets of agents that have a task in SOME environment (rideshare.py:276)
+                if (!noop && ((agents_with_tasks >> a) & 1u)) {
+                  const Mask list = unaccepted | own[a];
+                  if (act_k[a] >= 0 && act_k[a] < mask_count(list)) target[a] = mask_select(list, act_k[a]);
+                  else if (acts) faults |= FRZ_FAULT_BAD_TASK_INDEX;
+                }
+                if (target[a] >= 0 && acts) {
+                  const int* row = rows + target[a] * kCols;
+                  const bool drop = act_id[a] == 2;
+                  const int goal_y = drop ? row[cDestY] : row[cY], goal_x = drop ? row[cDestX] : row[cX];
+                  fare_target[a] = row[cFare];
+                  // squared distance agent -> goal before moving (passenger_state.py:48-49)
+                  distance2[a] = squared(agent_y[a] - goal_y, agent_x[a] - goal_x);
+                  if (fast) {
+                    move_y[a] = goal_y - agent_y[a];
+                    move_x[a] = goal_x - agent_x[a];
+                  } else {
+                    int best = INT_MAX;
+                    for (int d = 0; d < directions; ++d) {  // first argmin: strict <
+                      const int candidate = squared(agent_y[a] + kDirY[d] - goal_y, agent_x[a] + kDirX[d] - goal_x);
+                      if (candidate < best) {
+                        best = candidate;
+                        move_y[a] = kDirY[d];
+                        move_x[a] = kDirX[d];
+                      }
+                    }
+                  }
+                  move_cost[a] = diagonal ? __fsqrt_rn(float(squared(move_y[a], move_x[a])))
+                                          : float(abs(move_y[a]) + abs(move_x[a]));
+                }
+                agent_y[a] += move_y[a];
+                agent_x[a] += move_x[a];
+              }
+            }
+            // riding passengers travel with their driver; association -1 wraps to the last agent like the tensor index
+            for (Mask m = riding; m != 0; m &= m - 1) {
+              int* row = rows + mask_first(m) * kCols;
+              int driver = row[cAssoc];
+              driver = driver < 0 ? driver + A : driver;
+              int dy = 0, dx = 0;
+#pragma unroll
+              for (int a = 0; a < MAXA; ++a)
+                if (driver == a) dy = move_y[a], dx = move_x[a];
+              if ((dy | dx) != 0) {
+                row[cY] += dy;
+                row[cX] += dx;
+              }
+            }
+
+            // ---------------------------------------------------------------- accept conflicts (passenger_state.py:50-74)
+            int claim[MAXA];
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a) claim[a] = (act_id[a] == 0 && target[a] >= 0) ? target[a] : -1;
+            {
+              bool duplicated[MAXA], any = false;
+#pragma unroll
+              for (int a = 0; a < MAXA; ++a) {
+                duplicated[a] = false;
+#pragma unroll
+                for (int b = 0; b < MAXA; ++b)
+                  if (b != a && claim[a] >= 0 && claim[a] == claim[b]) duplicated[a] = true;
+                any |= duplicated[a];
+              }
+              if (any) {
+                // among ALL duplicated claims of the environment only the closest claimant (first on ties) survives
+                int closest = INT_MAX, keeper = -1;
+#pragma unroll
+                for (int a = 0; a < MAXA; ++a)
+                  if (duplicated[a] && distance2[a] < closest) closest = distance2[a], keeper = a;
+#pragma unroll
+                for (int a = 0; a < MAXA; ++a)
+                  if (duplicated[a] && a != keeper) claim[a] = -1;
+              }
+            }
+            // ---------------------------------------------------------------- apply: accepts, then picks, then exits
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a) {
+              if (claim[a] >= 0) {
+                int* row = rows + claim[a] * kCols;
+                row[cState] = 1;
+                row[cAccepted] = t_now;
+                row[cAssoc] = a;
+              }
+            }
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a) {
+              if (act_id[a] == 1 && target[a] >= 0 && distance2[a] == 0) {  // passenger_state.py:89-92 (< 1e-6)
+                int* row = rows + target[a] * kCols;
+                row[cState] = 2;
+                row[cPicked] = t_now;
+              }
+            }
+            bool exits = false;
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a) {
+              if (act_id[a] == 2 && target[a] >= 0 && distance2[a] == 0) {  // passenger_exit.py:40-45 (== 0)
+                fare_won[a] = fare_target[a];
+                rows[target[a] * kCols + cState] = kRemoved;
+                exits = true;
+              }
+            }
+            // ---------------------------------------------------------------- exit: order-preserving compaction
+            if (exits) {
+              int kept = 0;
+              for (int r = 0; r < n_before; ++r) {
+                if (rows[r * kCols + cState] != kRemoved) {
+                  if (kept != r) {
+#pragma unroll
+                    for (int c = 0; c < kCols; ++c) rows[kept * kCols + c] = rows[r * kCols + c];
+                  }
+                  ++kept;
+                }
+              }
+              n_rows = kept;
+            }
+          }
+
+          // ------------------------------------------------------------------ entry (passenger_entry.py:25-72)
+          {
+            const int64_t global_env = p.env_offset + env;
+            for (int r = lo; r < hi; ++r) {
+              const int* s = io.schedule + r * 7;
+              const int batch = s[1];
+              if (batch == -1 || batch == global_env) {
+                if (n_rows < K) {
+                  int* row = rows + n_rows * kCols;
+                  row[cBatch] = batch_base + env;  // index in the caller's batch (a slice starts at batch_base)
+                  row[cY] = s[2], row[cX] = s[3], row[cDestY] = s[4], row[cDestX] = s[5], row[cFare] = s[6];
+                  row[cState] = 0, row[cAssoc] = -1, row[cEntered] = t_entry, row[cAccepted] = -1, row[cPicked] = -1;
+                  ++n_rows;
+                } else {
+                  faults |= FRZ_FAULT_TABLE_FULL;
+                }
+              }
+            }
+          }
+
+          // ------------------------------------------------------------------ the new table: row sets by state / driver
+          Mask in_state[3] = {0, 0, 0}, own[MAXA];
+#pragma unroll
+          for (int a = 0; a < MAXA; ++a) own[a] = 0;
+          for (int r = 0; r < n_rows; ++r) {
+            const int state = rows[r * kCols + cState], assoc = rows[r * kCols + cAssoc];
+            const Mask bit = Mask(1) << r;
+#pragma unroll
+            for (int cls = 0; cls < 3; ++cls)
+              if (state == cls) in_state[cls] |= bit;
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a)
+              if (assoc == a) own[a] |= bit;
+          }
+          // rows of task_obs to (re)write: the table and the rows that just became free (every row on a refresh)
+          obs_rows = MODE == kRsStep ? max(n_rows, n_before) : K;
+
+          // ------------------------------------------------------------------ rewards shared by the drivers
+          float shared = 0.f;
+          if (MODE == kRsStep && (p.flags & FRZ_RS_WAITING_COSTS)) {
+            // `global[idx] += v` with duplicate indices keeps ONE write per statement: the last row of the class
+            int elapsed_unaccepted = 0;
+#pragma unroll
+            for (int cls = 0; cls < 3; ++cls) {
+              if (in_state[cls] != 0) {
+                const int when = rows[mask_last(in_state[cls]) * kCols + (cls == 0 ? cEntered : (cls == 1 ? cAccepted : cPicked))];
+                const int elapsed = t_now - when;
+                shared = __fadd_rn(shared, __fmul_rn(elapsed >= p.wait_limit[cls] ? 1.f : 0.f, p.general_wait_cost));
+                if (cls == 0) elapsed_unaccepted = elapsed;
+              }
+            }
+            if (in_state[0] != 0)
+              shared = __fadd_rn(shared, __fmul_rn(elapsed_unaccepted >= p.long_wait_time ? 1.f : 0.f, p.long_wait_cost));
+            const int free_slots = A * p.pool_limit - n_rows;
+            const float unserved = __fmul_rn(mask_count(in_state[0]) >= free_slots ? 1.f : 0.f, -0.5f);
+            shared = __fadd_rn(shared, __fmul_rn(unserved, float(free_slots)));
+          }
+
+          // ------------------------------------------------------------------ per driver: counts, task mask, rewards
+          int n_tasks[MAXA];
+          float reward[MAXA];
+          int4 self[MAXA];
+#pragma unroll
+          for (int a = 0; a < MAXA; ++a) {
+            n_tasks[a] = 0, reward[a] = 0.f, self[a] = make_int4(0, 0, 0, 0);
+            if (a < A) {
+              const int associated = mask_count(own[a]);
+              const Mask members = in_state[0] | own[a];
+              n_tasks[a] = mask_count(members);
+              if (n_tasks[a] > 0) agent_bits |= 1u << a;
+              self[a] = make_int4(agent_y[a], agent_x[a], mask_count(own[a] & in_state[1]), mask_count(own[a] & in_state[2]));
+              my_members[a] = members;  // expanded to the task-mask bytes by the whole warp below
+              if (MODE == kRsStep) {  // rideshare.py:309-363
+                float value = associated > p.pool_limit ? p.pool_limit_cost : 0.f;
+                value = __fadd_rn(value, __fmul_rn(act_id[a] == -1 ? 1.f : 0.f, p.noop_cost));
+                value = __fadd_rn(value, __fmul_rn(act_id[a] == 0 ? 1.f : 0.f, p.accept_cost));
+                value = __fadd_rn(value, fare_won[a] > 0 ? __fadd_rn(float(fare_won[a]), -p.drop_cost) : 0.f);
+                float move_reward = __fmul_rn(move_cost[a], p.move_cost);
+                if (p.flags & FRZ_RS_VARIABLE_MOVE_COST) move_reward = __fdiv_rn(move_reward, float(associated + 1));
+                value = __fadd_rn(value, move_reward);
+                reward[a] = __fadd_rn(value, shared);
+              }
+            }
+          }
+
+          // ------------------------------------------------------------------ publish
+          if (quad_agents) {  // four drivers per 16-byte store
+#pragma unroll
+            for (int j = 0; j < MAXA / 4; ++j) {
+              if (4 * j < A) {
+                reinterpret_cast<int4*>(io.agent_task_count)[(agent_at >> 2) + j] =
+                    make_int4(n_tasks[4 * j], n_tasks[4 * j + 1], n_tasks[4 * j + 2], n_tasks[4 * j + 3]);
+                if (MODE == kRsStep) {
+                  reinterpret_cast<float4*>(io.rewards)[(agent_at >> 2) + j] =
+                      make_float4(reward[4 * j], reward[4 * j + 1], reward[4 * j + 2], reward[4 * j + 3]);
+                  reinterpret_cast<float4*>(io.cumulative_rewards)[(agent_at >> 2) + j] =
+                      make_float4(__fadd_rn(cumulative[4 * j], reward[4 * j]), __fadd_rn(cumulative[4 * j + 1], reward[4 * j + 1]),
+                                  __fadd_rn(cumulative[4 * j + 2], reward[4 * j + 2]),
+                                  __fadd_rn(cumulative[4 * j + 3], reward[4 * j + 3]));
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a) {
+              if (a < A) {
+                io.agent_task_count[agent_at + a] = n_tasks[a];
+                if (MODE == kRsStep) {
+                  io.rewards[agent_at + a] = reward[a];
+                  io.cumulative_rewards[agent_at + a] = __fadd_rn(cumulative[a], reward[a]);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < MAXA; ++a)
+            if (a < A) reinterpret_cast<int4*>(io.self_obs)[agent_at + a] = self[a];
+          if (MODE == kRsStep) {
+            if (even_agents) {
+#pragma unroll
+              for (int j = 0; j < MAXA / 2; ++j)
+                if (2 * j < A)
+                  reinterpret_cast<int4*>(io.agents)[(agent_at >> 1) + j] =
+                      make_int4(agent_y[2 * j], agent_x[2 * j], agent_y[2 * j + 1], agent_x[2 * j + 1]);
+            } else {
+#pragma unroll
+              for (int a = 0; a < MAXA; ++a)
+                if (a < A) reinterpret_cast<int2*>(io.agents)[agent_at + a] = make_int2(agent_y[a], agent_x[a]);
+            }
+            const int moves = t_now + 1;
+            const bool truncated = moves >= p.max_steps;
+            io.num_moves[env] = moves;
+            io.truncated[env] = truncated;
+            alive_bits |= 1u | (truncated ? 0u : 2u);  // rideshare never terminates (rideshare.py:252)
+          }
+          io.env_task_count[env] = n_rows;
+          // the bulk store below moves whole 16-byte pieces: define the words between the last row and the boundary
+          if (admits)
+            for (int w = n_rows * kCols; (w & 3) != 0; ++w) rows[w] = 0;
+        }
+
+        // ------------------------------------------------------------------ observations: the warp writes them together
+        __syncwarp();
+        if (FRZ_RS_ABLATE != 3) {
+          // task observation rows (rideshare.py:398-416), built from the staged tables: a half-warp per environment,
+          // lane pair j of it writes the two 16-byte halves of row j (+ 8 per round), so every store instruction
+          // covers whole 32-byte sectors of two environments instead of 32 scattered half-sectors
+          const uint32_t info = now ? ((offset >> 4) | (uint32_t(n_rows) << 13) | (uint32_t(obs_rows) << 20)) : 0u;
+          const int most = __reduce_max_sync(kFullMask, now ? obs_rows : 0);
+          const int half = lane >> 4, slot = (lane & 15) >> 1, part = lane & 1;
+          int4* const tile_obs = reinterpret_cast<int4*>(io.task_obs) + size_t(tile0) * size_t(K) * 2u;
+#pragma unroll 2
+          for (int pair = 0; pair < 16; ++pair) {
+            const int e = 2 * pair + half;
+            const uint32_t of = __shfl_sync(kFullMask, info, e);
+            const int live = int((of >> 13) & 127u), written = int(of >> 20);
+            const int* const table_e = buffer_words + ((of & 8191u) << 2);
+            for (int base = 0; base < most; base += 8) {
+              const int r = base + slot;
+              if (r < written) {
+                int4 value = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
+                if (r < live) {
+                  const int* row = table_e + r * kCols;
+                  if (part == 0) {
+                    value = make_int4(row[cY], row[cX], row[cDestY], row[cDestX]);
+                  } else {
+                    const int state = row[cState], assoc = row[cAssoc];
+                    value = make_int4(state == 1 ? assoc : FRZ_PAD, state == 2 ? assoc : FRZ_PAD, row[cFare], row[cEntered]);
+                  }
+                }
+                tile_obs[(size_t(e) * size_t(K) + size_t(r)) * 2u + part] = value;
+              }
+            }
+          }
+          // task masks: the tile's [32, A, K] bytes are one contiguous range of task_mask -> a flat, coalesced sweep;
+          // every lane expands 16 (or 4) rows of one driver's row set into bytes: nibble x 0x204081 spreads four bits
+          // over four bytes.  Environments outside this pass are skipped.
+          __syncwarp();
+          const uint32_t lists = min(32u, uint32_t(B - tile0)) * uint32_t(A);  // (environment, driver) pairs of the tile
+          if ((K & 15) == 0) {
+            const uint32_t per_list = uint32_t(K) >> 4, total = lists * per_list;
+            uint4* const tile_masks = reinterpret_cast<uint4*>(io.task_mask + size_t(tile0) * size_t(A * K));
+            for (uint32_t i = lane; i < total; i += 32u) {
+              const uint32_t g = per_list == 1u ? i : __umulhi(i, inverse_rows), j = i - g * per_list;
+              const uint32_t e = A == 1 ? g : __umulhi(g, inverse_agents);
+              if ((batch >> e) & 1u) {
+                const uint32_t part = uint32_t(members_of[g] >> (16u * j));
+                tile_masks[i] = make_uint4(((part & 0xfu) * 0x00204081u) & 0x01010101u, (((part >> 4) & 0xfu) * 0x00204081u) & 0x01010101u,
+                                           (((part >> 8) & 0xfu) * 0x00204081u) & 0x01010101u,
+                                           (((part >> 12) & 0xfu) * 0x00204081u) & 0x01010101u);
+              }
+            }
+          } else {
+            const uint32_t per_list = uint32_t(K) >> 2, total = lists * per_list;
+            uint32_t* const tile_masks = reinterpret_cast<uint32_t*>(io.task_mask + size_t(tile0) * size_t(A * K));
+            for (uint32_t i = lane; i < total; i += 32u) {
+              const uint32_t g = per_list == 1u ? i : __umulhi(i, inverse_rows), j = i - g * per_list;
+              const uint32_t e = A == 1 ? g : __umulhi(g, inverse_agents);
+              if ((batch >> e) & 1u) tile_masks[i] = ((uint32_t(members_of[g] >> (4u * j)) & 0xfu) * 0x00204081u) & 0x01010101u;
+            }
+          }
+        }
+
+        // ------------------------------------------------------------------ write the tables back (one bulk copy each)
+        if (MODE != kRsRefresh && FRZ_RS_ABLATE != 2) {
+          const uint32_t store_bytes = (now && admits) ? (uint32_t(n_rows * kCols * 4) + 15u) & ~15u : 0u;
+          fence_async_shared();  // this lane's edits of its rows become visible to the async proxy
+          __syncwarp();
+          const uint32_t piece = (offset << 4) | (store_bytes >> 4);
+          int* target_rows = global_rows;
+#pragma unroll 4
+          for (int e = 0; e < 32; ++e, target_rows += table_words) {
+            const uint32_t of = __shfl_sync(kFullMask, piece, e);
+            if ((of & 0xffu) != 0u) {
+              if (elect_one()) bulk_store(target_rows, buffer + ((of >> 8) << 4), (of & 0xffu) << 4);
+            }
+          }
+          bulk_commit();  // waited for before the buffer is written again (next pass) and before the CTA exits
+        }
+        __syncwarp();
+        pending &= ~batch;
+      }
+    }
+    bulk_wait_read();
+  }
+  finish_launch(control, alive_bits, faults, agent_bits,
+                skip ? kPublishNothing : (MODE == kRsStep ? kPublishStep : kPublishRefresh));
+}
+
 __global__ void rideshare_restore_kernel(const FrzRideshareParams p, const FrzRideshareBuffers io, const int B,
                                          const uint8_t* __restrict__ env_mask) {
   const int A = p.num_agents, K = p.capacity;
@@ -571,10 +1175,49 @@ int rideshare_launch_geometry(const FrzRideshareParams* p, const FrzRideshareBuf
   return check_launch("rideshare_step_kernel");
 }
 
+// The tiled kernel: one thread per environment, 32 environments per warp, kTileWarps independent warps per CTA.
+template <int MAXA, bool WIDE, int MODE>
+int rideshare_launch_tiles(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, cudaStream_t s,
+                           const uint8_t* entry_mask, int batch_base) {
+  const int K = p->capacity;
+  const uint32_t one_table = (uint32_t(K * kCols * 4) + 15u) & ~15u;
+  const uint32_t typical = (uint32_t(32 * std::min(K, tile_row_budget()) * kCols * 4) + 15u) & ~15u;
+  const uint32_t warp_bytes = std::max(one_table, typical);
+  // schedule_index travels to shared memory when it is short enough (an entry per step of the schedule's horizon)
+  const int index_words = p->schedule_rows > 0 && p->schedule_horizon + 2 <= kTileIndexWords ? p->schedule_horizon + 2 : 0;
+  // i / n = umulhi(i, ceil(2^32 / n)) for the small i the task-mask sweep divides (n = 16- or 4-row pieces per task
+  // list, n = drivers)
+  const auto inverse = [](uint32_t n) { return n > 1u ? uint32_t(((1ull << 32) + n - 1u) / n) : 0u; };
+  const uint32_t inverse_rows = inverse((K & 15) == 0 ? uint32_t(K) >> 4 : uint32_t(K) >> 2);
+  const uint32_t inverse_agents = inverse(uint32_t(p->num_agents));
+  const size_t set_bytes = WIDE ? 8 : 4;
+  const size_t smem = size_t(kTileWarps) * (warp_bytes + 32 * p->num_agents * set_bytes) + 8 * kTileWarps + 4 * size_t(index_words);
+  auto kernel = rideshare_tile_kernel<MAXA, WIDE, MODE>;
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    return check_launch("rideshare shared memory");
+  const int ctas_per_sm = resident_ctas(kernel, kTileThreads, smem);
+  const int tiles = (B + 31) / 32;
+  const int grid = persistent_grid((tiles + kTileWarps - 1) / kTileWarps, ctas_per_sm);
+  kernel<<<grid, kTileThreads, smem, s>>>(*p, *io, B, entry_mask, batch_base, warp_bytes, index_words, inverse_rows,
+                                          inverse_agents);
+  return check_launch("rideshare_tile_kernel");
+}
+
 template <int MODE>
 int rideshare_launch_mode(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, cudaStream_t s,
                           const uint8_t* entry_mask, int batch_base) {
   const int K = p->capacity, A = p->num_agents;
+  // One thread per environment needs enough environments to fill the GPU with warps (a tile of 32 takes one warp
+  // through a long dependent chain); smaller batches keep a group of lanes per environment.  Bulk copies need 16-byte
+  // aligned tables.
+  const int choice = rideshare_kernel_choice();
+  const bool tiles = choice == 1 || (choice == 0 && B >= kTileMinimumBatch);
+  if (A <= 8 && (K & 3) == 0 && tiles) {
+    if (A <= 4) return K <= 32 ? rideshare_launch_tiles<4, false, MODE>(p, io, B, s, entry_mask, batch_base)
+                               : rideshare_launch_tiles<4, true, MODE>(p, io, B, s, entry_mask, batch_base);
+    return K <= 32 ? rideshare_launch_tiles<8, false, MODE>(p, io, B, s, entry_mask, batch_base)
+                   : rideshare_launch_tiles<8, true, MODE>(p, io, B, s, entry_mask, batch_base);
+  }
   if (A <= 8 && K <= 8) return rideshare_launch_geometry<8, 1, MODE>(p, io, B, s, entry_mask, batch_base);
   if (A <= 8 && K <= 16) return rideshare_launch_geometry<8, 2, MODE>(p, io, B, s, entry_mask, batch_base);
   if (A <= 8 && K <= 32) return rideshare_launch_geometry<8, 4, MODE>(p, io, B, s, entry_mask, batch_base);

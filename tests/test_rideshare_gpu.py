@@ -62,6 +62,12 @@ def policy_actions(oracle, rng, wild):
     ('rideshare_synthetic', dict(drivers=20, rows=64), 60, 30, 0.2),  # 32-lane groups: 20 drivers, a full 64-row table
     ('rideshare_synthetic', dict(drivers=12, rows=40), 80, 30, 0.2),  # 16-lane groups, 4 rows per lane
     ('rideshare_synthetic', dict(drivers=32, rows=24), 50, 30, 0.1),  # the engine's driver limit
+    # the tiled kernel (one thread per environment; tables with a multiple of four rows, at most eight drivers)
+    ('rideshare_synthetic', dict(drivers=7, rows=24), 200, 30, 0.2),  # eight-driver variant, odd driver count
+    ('rideshare_synthetic', dict(drivers=8, rows=40), 130, 30, 0.2),  # ... with 64-bit row sets, four drivers per store
+    ('rideshare_synthetic', dict(drivers=6, rows=16), 97, 30, 0.2),  # ... two drivers per load, a partial last tile
+    ('rideshare_synthetic', dict(drivers=2, rows=64), 70, 30, 0.1),  # four-driver variant, a full 64-row table
+    ('rideshare_c2', {}, 2100, 90, 0.1),  # more tiles than one CTA's warps, partial last tile
 ])
 def test_matches_oracle_on_random_rollouts(preset, preset_kwargs, B, steps, wild):
     from oracle.rideshare import RideshareOracle
