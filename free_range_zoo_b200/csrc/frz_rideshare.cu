@@ -534,12 +534,15 @@ __device__ __forceinline__ int mask_last(uint64_t m) { return 63 - __clzll((long
 __device__ __forceinline__ int mask_select(uint32_t m, int k) { return select_bit(m, k); }
 __device__ __forceinline__ int mask_select(uint64_t m, int k) { return select_bit64(m, k); }
 
+// bits 0 .. n-1 (n may equal the width of the set)
+__device__ __forceinline__ uint32_t mask_below(uint32_t, int n) { return n >= 32 ? 0xffffffffu : (1u << n) - 1u; }
+__device__ __forceinline__ uint64_t mask_below(uint64_t, int n) { return n >= 64 ? ~uint64_t(0) : (uint64_t(1) << n) - 1u; }
+
 template <int MAXA, bool WIDE, int MODE>
 __global__ void __launch_bounds__(kTileThreads, MAXA <= 4 ? 5 : 3)
 rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid_constant__ FrzRideshareBuffers io,
                       const int B, const uint8_t* __restrict__ entry_mask, const int batch_base,
-                      const uint32_t warp_bytes, const int index_words, const uint32_t inverse_rows,
-                      const uint32_t inverse_agents) {
+                      const uint32_t warp_bytes, const int index_words) {
   using Mask = typename std::conditional<WIDE, uint64_t, uint32_t>::type;
   extern __shared__ __align__(16) int smem[];
   const int lane = threadIdx.x & 31;
@@ -549,11 +552,8 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
   const uint32_t table_words = uint32_t(K * kCols);
   const uint32_t buffer = shared_address(smem) + uint32_t(warp) * warp_bytes;
   int* const buffer_words = smem + warp * int(warp_bytes >> 2);
-  // after the table buffers: per warp the 32 x A task lists of its tile as row sets, then the mbarriers, then
-  // schedule_index
-  constexpr int kSetWords = int(sizeof(Mask) / 4);
-  Mask* const members_of = reinterpret_cast<Mask*>(smem + warps * int(warp_bytes >> 2)) + warp * 32 * A;
-  int* const after_masks = smem + warps * int(warp_bytes >> 2) + warps * 32 * A * kSetWords;
+  // after the table buffers: the mbarriers, then schedule_index
+  int* const after_masks = smem + warps * int(warp_bytes >> 2);
   const uint32_t barrier = shared_address(after_masks) + 8u * uint32_t(warp);
   // schedule_index[0 .. index_words) copied next to the barriers (index_words = 0: the schedule is too long, read it
   // from global memory): turns the dependent load "count -> step -> schedule rows entering now" into a shared-memory read
@@ -568,7 +568,6 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
   const uint32_t agents_with_tasks = control->agents_with_tasks;
   const bool skip = (MODE == kRsStep) && ((alive_prev & 3u) != 3u);  // utils/env.py:212
   const bool fast = p.flags & FRZ_RS_FAST_TRAVEL, diagonal = p.flags & FRZ_RS_DIAGONAL_TRAVEL;
-  const int directions = diagonal ? 9 : 5;
   const bool even_agents = (A & 1) == 0, quad_agents = (A & 3) == 0;
   const uint32_t one_table = (table_words * 4u + 15u) & ~15u;
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
@@ -688,7 +687,6 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         // ---------------------------------------------------------------- stage the live rows (one bulk copy each)
         const uint32_t load_bytes = now ? bytes_in : 0u;
         const uint32_t total_in = __reduce_add_sync(kFullMask, load_bytes);
-        bulk_wait_read();  // the previous pass's write-back has left the buffer
 #ifndef FRZ_RS_ABLATE
 #define FRZ_RS_ABLATE 0  // profiling experiments (profiles/README.md): 1 = copies only, 2 = no copies, 3 = no observation stores
 #endif
@@ -707,28 +705,33 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
           phase ^= 1u;
         }
 
-        int n_rows = n_before, obs_rows = 0;
-        Mask* const my_members = members_of + lane * A;  // this environment's task lists as row sets, one per driver
+        int n_rows = n_before;
         if (now && FRZ_RS_ABLATE != 1) {
           int fare_won[MAXA];
           float move_cost[MAXA];
+          // what this step changes: `dirty` = rows of the NEW table whose contents differ from what global memory holds at
+          // that index (only those rows and their observation rows are written back); old_list = the drivers' task
+          // lists before the step = what task_mask holds
+          Mask dirty = 0, old_list[MAXA];
 #pragma unroll
-          for (int a = 0; a < MAXA; ++a) fare_won[a] = 0, move_cost[a] = 0.f;
+          for (int a = 0; a < MAXA; ++a) fare_won[a] = 0, move_cost[a] = 0.f, old_list[a] = 0;
+
+          // ------------------------------------------------------------------ row sets (rideshare.py:374-386)
+          // in_state[s] = rows whose passenger is unaccepted / accepted / riding, own[a] = rows associated with driver a;
+          // read from the table once, then kept up to date through every edit of the step
+          Mask in_state[3] = {0, 0, 0}, own[MAXA];
+#pragma unroll
+          for (int a = 0; a < MAXA; ++a) own[a] = 0;
+          for (int r = 0; r < n_before; ++r) {
+            const int state = rows[r * kCols + cState], assoc = rows[r * kCols + cAssoc];
+            const Mask bit = Mask(1) << r;
+#pragma unroll
+            for (int cls = 0; cls < 3; ++cls) in_state[cls] |= state == cls ? bit : Mask(0);
+#pragma unroll
+            for (int a = 0; a < MAXA; ++a) own[a] |= assoc == a ? bit : Mask(0);
+          }
 
           if (MODE == kRsStep) {
-            // ---------------------------------------------------------------- task lists (rideshare.py:374-386)
-            Mask unaccepted = 0, riding = 0, own[MAXA];
-#pragma unroll
-            for (int a = 0; a < MAXA; ++a) own[a] = 0;
-            for (int r = 0; r < n_before; ++r) {
-              const int state = rows[r * kCols + cState], assoc = rows[r * kCols + cAssoc];
-              const Mask bit = Mask(1) << r;
-              if (state == 0) unaccepted |= bit;
-              if (state == 2) riding |= bit;
-#pragma unroll
-              for (int a = 0; a < MAXA; ++a)
-                if (assoc == a) own[a] |= bit;
-            }
 
             // ---------------------------------------------------------------- decode + movement
             // (rideshare.py:255-300, transitions/movement.py:57-116)
@@ -739,8 +742,9 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
               if (a < A) {
                 const bool noop = act_id[a] == -1, acts = act_id[a] == 0 || act_id[a] == 1 || act_id[a] == 2;
                 // the reference only resolves targets of agents that have a task in SOME environment (rideshare.py:276)
+                old_list[a] = in_state[0] | own[a];  // what task_mask holds for this driver
                 if (!noop && ((agents_with_tasks >> a) & 1u)) {
-                  const Mask list = unaccepted | own[a];
+                  const Mask list = old_list[a];
                   if (act_k[a] >= 0 && act_k[a] < mask_count(list)) target[a] = mask_select(list, act_k[a]);
                   else if (acts) faults |= FRZ_FAULT_BAD_TASK_INDEX;
                 }
@@ -755,15 +759,16 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
                     move_y[a] = goal_y - agent_y[a];
                     move_x[a] = goal_x - agent_x[a];
                   } else {
-                    int best = INT_MAX;
-                    for (int d = 0; d < directions; ++d) {  // first argmin: strict <
-                      const int candidate = squared(agent_y[a] + kDirY[d] - goal_y, agent_x[a] + kDirX[d] - goal_x);
-                      if (candidate < best) {
-                        best = candidate;
-                        move_y[a] = kDirY[d];
-                        move_x[a] = kDirX[d];
-                      }
-                    }
+                    // first argmin over stay, N, E, S, W [, NW, NE, SE, SW] of the squared distance after the move,
+                    // written as its difference to staying: |v - m|^2 - |v|^2 = |m|^2 - 2 v.m with v = goal - agent
+                    const int vy = goal_y - agent_y[a], vx = goal_x - agent_x[a];
+                    int best = 0;
+                    const auto consider = [&](int dy, int dx) {  // strict <: earlier directions win ties
+                      const int change = dy * dy + dx * dx - 2 * (vy * dy + vx * dx);
+                      if (change < best) best = change, move_y[a] = dy, move_x[a] = dx;
+                    };
+                    consider(-1, 0), consider(0, 1), consider(1, 0), consider(0, -1);
+                    if (diagonal) consider(-1, -1), consider(-1, 1), consider(1, 1), consider(1, -1);
                   }
                   move_cost[a] = diagonal ? __fsqrt_rn(float(squared(move_y[a], move_x[a])))
                                           : float(abs(move_y[a]) + abs(move_x[a]));
@@ -773,7 +778,7 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
               }
             }
             // riding passengers travel with their driver; association -1 wraps to the last agent like the tensor index
-            for (Mask m = riding; m != 0; m &= m - 1) {
+            for (Mask m = in_state[2]; m != 0; m &= m - 1) {
               int* row = rows + mask_first(m) * kCols;
               int driver = row[cAssoc];
               driver = driver < 0 ? driver + A : driver;
@@ -784,6 +789,7 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
               if ((dy | dx) != 0) {
                 row[cY] += dy;
                 row[cX] += dx;
+                dirty |= m & (~m + 1);
               }
             }
 
@@ -820,6 +826,11 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
                 row[cState] = 1;
                 row[cAccepted] = t_now;
                 row[cAssoc] = a;
+                const Mask bit = Mask(1) << claim[a];
+                dirty |= bit;
+                in_state[0] &= ~bit, in_state[2] &= ~bit, in_state[1] |= bit;
+#pragma unroll
+                for (int b = 0; b < MAXA; ++b) own[b] = b == a ? (own[b] | bit) : (own[b] & ~bit);
               }
             }
 #pragma unroll
@@ -828,30 +839,43 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
                 int* row = rows + target[a] * kCols;
                 row[cState] = 2;
                 row[cPicked] = t_now;
+                const Mask bit = Mask(1) << target[a];
+                dirty |= bit;
+                in_state[0] &= ~bit, in_state[1] &= ~bit, in_state[2] |= bit;
               }
             }
-            bool exits = false;
+            Mask leaving = 0;
 #pragma unroll
             for (int a = 0; a < MAXA; ++a) {
               if (act_id[a] == 2 && target[a] >= 0 && distance2[a] == 0) {  // passenger_exit.py:40-45 (== 0)
                 fare_won[a] = fare_target[a];
-                rows[target[a] * kCols + cState] = kRemoved;
-                exits = true;
+                leaving |= Mask(1) << target[a];
               }
             }
             // ---------------------------------------------------------------- exit: order-preserving compaction
-            if (exits) {
-              int kept = 0;
-              for (int r = 0; r < n_before; ++r) {
-                if (rows[r * kCols + cState] != kRemoved) {
-                  if (kept != r) {
+            if (leaving != 0) {
+              const int first_gap = mask_first(leaving);
+              int kept = first_gap;
+              for (int r = first_gap + 1; r < n_before; ++r) {
+                if (!((leaving >> r) & 1u)) {
 #pragma unroll
-                    for (int c = 0; c < kCols; ++c) rows[kept * kCols + c] = rows[r * kCols + c];
-                  }
+                  for (int c = 0; c < kCols; ++c) rows[kept * kCols + c] = rows[r * kCols + c];
                   ++kept;
                 }
               }
               n_rows = kept;
+              // rows below the first gap stay where they were; everything from there on moved
+              dirty = (dirty & mask_below(Mask(0), first_gap)) | (mask_below(Mask(0), kept) & ~mask_below(Mask(0), first_gap));
+              // the row sets lose the leaving rows' positions (from the highest one down, so positions stay valid)
+              for (Mask gone = leaving; gone != 0;) {
+                const int at = mask_last(gone);
+                gone ^= Mask(1) << at;
+                const Mask low = mask_below(Mask(0), at);
+#pragma unroll
+                for (int cls = 0; cls < 3; ++cls) in_state[cls] = (in_state[cls] & low) | ((in_state[cls] >> 1) & ~low);
+#pragma unroll
+                for (int a = 0; a < MAXA; ++a) own[a] = (own[a] & low) | ((own[a] >> 1) & ~low);
+              }
             }
           }
 
@@ -867,6 +891,8 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
                   row[cBatch] = batch_base + env;  // index in the caller's batch (a slice starts at batch_base)
                   row[cY] = s[2], row[cX] = s[3], row[cDestY] = s[4], row[cDestX] = s[5], row[cFare] = s[6];
                   row[cState] = 0, row[cAssoc] = -1, row[cEntered] = t_entry, row[cAccepted] = -1, row[cPicked] = -1;
+                  dirty |= Mask(1) << n_rows;
+                  in_state[0] |= Mask(1) << n_rows;
                   ++n_rows;
                 } else {
                   faults |= FRZ_FAULT_TABLE_FULL;
@@ -875,22 +901,47 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
             }
           }
 
-          // ------------------------------------------------------------------ the new table: row sets by state / driver
-          Mask in_state[3] = {0, 0, 0}, own[MAXA];
-#pragma unroll
-          for (int a = 0; a < MAXA; ++a) own[a] = 0;
-          for (int r = 0; r < n_rows; ++r) {
-            const int state = rows[r * kCols + cState], assoc = rows[r * kCols + cAssoc];
-            const Mask bit = Mask(1) << r;
-#pragma unroll
-            for (int cls = 0; cls < 3; ++cls)
-              if (state == cls) in_state[cls] |= bit;
-#pragma unroll
-            for (int a = 0; a < MAXA; ++a)
-              if (assoc == a) own[a] |= bit;
+          // ------------------------------------------------------------------ write back what changed
+          // Only the rows this step touched go back to global memory, together with their task observation rows
+          // (rideshare.py:398-416): riding passengers that moved, accepted / picked passengers, rows that moved up behind
+          // an exit, rows that entered.  A refresh or reset writes every live row.  (The other rows of the table, of
+          // task_obs and of task_mask already hold these values: they are functions of the table alone.)
+          if (FRZ_RS_ABLATE != 3) {
+            int* const table_out = global_rows + size_t(lane) * size_t(table_words);
+            int4* const obs = reinterpret_cast<int4*>(io.task_obs) + size_t(env) * size_t(K) * 2u;
+            for (Mask m = MODE == kRsStep ? dirty : mask_below(Mask(0), n_rows); m != 0; m &= m - 1) {
+              const int r = mask_first(m);
+              const int* row = rows + r * kCols;
+              const int batch = row[cBatch], y = row[cY], x = row[cX], dest_y = row[cDestY], dest_x = row[cDestX], fare = row[cFare];
+              const int state = row[cState], assoc = row[cAssoc], entered = row[cEntered], accepted = row[cAccepted];
+              const int picked = row[cPicked];
+              obs[2 * r] = make_int4(y, x, dest_y, dest_x);
+              obs[2 * r + 1] = make_int4(state == 1 ? assoc : FRZ_PAD, state == 2 ? assoc : FRZ_PAD, fare, entered);
+              if (MODE == kRsStep || admits) {
+                // the 11 words of the row as five 8-byte stores and one word (rows start on alternating 8-byte phases)
+                int* out = table_out + r * kCols;
+                if (r & 1) {
+                  out[0] = batch;
+                  reinterpret_cast<int2*>(out + 1)[0] = make_int2(y, x);
+                  reinterpret_cast<int2*>(out + 1)[1] = make_int2(dest_y, dest_x);
+                  reinterpret_cast<int2*>(out + 1)[2] = make_int2(fare, state);
+                  reinterpret_cast<int2*>(out + 1)[3] = make_int2(assoc, entered);
+                  reinterpret_cast<int2*>(out + 1)[4] = make_int2(accepted, picked);
+                } else {
+                  reinterpret_cast<int2*>(out)[0] = make_int2(batch, y);
+                  reinterpret_cast<int2*>(out)[1] = make_int2(x, dest_y);
+                  reinterpret_cast<int2*>(out)[2] = make_int2(dest_x, fare);
+                  reinterpret_cast<int2*>(out)[3] = make_int2(state, assoc);
+                  reinterpret_cast<int2*>(out)[4] = make_int2(entered, accepted);
+                  out[10] = picked;
+                }
+              }
+            }
+            // padding of the observation rows that just became free (every row past the table on a refresh)
+            const int4 pad = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
+            const int pad_to = MODE == kRsStep ? n_before : K;
+            for (int r = n_rows; r < pad_to; ++r) obs[2 * r] = pad, obs[2 * r + 1] = pad;
           }
-          // rows of task_obs to (re)write: the table and the rows that just became free (every row on a refresh)
-          obs_rows = MODE == kRsStep ? max(n_rows, n_before) : K;
 
           // ------------------------------------------------------------------ rewards shared by the drivers
           float shared = 0.f;
@@ -926,14 +977,37 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
               n_tasks[a] = mask_count(members);
               if (n_tasks[a] > 0) agent_bits |= 1u << a;
               self[a] = make_int4(agent_y[a], agent_x[a], mask_count(own[a] & in_state[1]), mask_count(own[a] & in_state[2]));
-              my_members[a] = members;  // expanded to the task-mask bytes by the whole warp below
+              // task mask [A, K] bytes: the 16-row (4-row) pieces whose membership changed; nibble x 0x204081 spreads
+              // four bits over four bytes
+              const Mask changed = MODE == kRsStep ? (members ^ old_list[a]) : ~Mask(0);
+              if (changed != 0 && FRZ_RS_ABLATE != 3) {
+                uint32_t* const mask_row = reinterpret_cast<uint32_t*>(io.task_mask + (size_t(agent_at) + a) * size_t(K));
+                if ((K & 15) == 0) {
+#pragma unroll
+                  for (int q = 0; q < (WIDE ? 4 : 2); ++q) {
+                    if (16 * q < K && (uint32_t(changed >> (16 * q)) & 0xffffu) != 0u) {
+                      const uint32_t part = uint32_t(members >> (16 * q));
+                      reinterpret_cast<uint4*>(mask_row)[q] =
+                          make_uint4(((part & 0xfu) * 0x00204081u) & 0x01010101u, (((part >> 4) & 0xfu) * 0x00204081u) & 0x01010101u,
+                                     (((part >> 8) & 0xfu) * 0x00204081u) & 0x01010101u,
+                                     (((part >> 12) & 0xfu) * 0x00204081u) & 0x01010101u);
+                    }
+                  }
+                } else {
+                  for (int q = 0; 4 * q < K; ++q)
+                    if ((uint32_t(changed >> (4 * q)) & 0xfu) != 0u)
+                      mask_row[q] = ((uint32_t(members >> (4 * q)) & 0xfu) * 0x00204081u) & 0x01010101u;
+                }
+              }
               if (MODE == kRsStep) {  // rideshare.py:309-363
                 float value = associated > p.pool_limit ? p.pool_limit_cost : 0.f;
                 value = __fadd_rn(value, __fmul_rn(act_id[a] == -1 ? 1.f : 0.f, p.noop_cost));
                 value = __fadd_rn(value, __fmul_rn(act_id[a] == 0 ? 1.f : 0.f, p.accept_cost));
                 value = __fadd_rn(value, fare_won[a] > 0 ? __fadd_rn(float(fare_won[a]), -p.drop_cost) : 0.f);
                 float move_reward = __fmul_rn(move_cost[a], p.move_cost);
-                if (p.flags & FRZ_RS_VARIABLE_MOVE_COST) move_reward = __fdiv_rn(move_reward, float(associated + 1));
+                // (x / 1 = x and 0 / n = 0 exactly: the division runs only where it changes the value)
+                if ((p.flags & FRZ_RS_VARIABLE_MOVE_COST) && associated > 0 && move_cost[a] != 0.f)
+                  move_reward = __fdiv_rn(move_reward, float(associated + 1));
                 value = __fadd_rn(value, move_reward);
                 reward[a] = __fadd_rn(value, shared);
               }
@@ -991,94 +1065,14 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
             alive_bits |= 1u | (truncated ? 0u : 2u);  // rideshare never terminates (rideshare.py:252)
           }
           io.env_task_count[env] = n_rows;
-          // the bulk store below moves whole 16-byte pieces: define the words between the last row and the boundary
-          if (admits)
-            for (int w = n_rows * kCols; (w & 3) != 0; ++w) rows[w] = 0;
         }
 
-        // ------------------------------------------------------------------ observations: the warp writes them together
-        __syncwarp();
-        if (FRZ_RS_ABLATE != 3) {
-          // task observation rows (rideshare.py:398-416), built from the staged tables: a half-warp per environment,
-          // lane pair j of it writes the two 16-byte halves of row j (+ 8 per round), so every store instruction
-          // covers whole 32-byte sectors of two environments instead of 32 scattered half-sectors
-          const uint32_t info = now ? ((offset >> 4) | (uint32_t(n_rows) << 13) | (uint32_t(obs_rows) << 20)) : 0u;
-          const int most = __reduce_max_sync(kFullMask, now ? obs_rows : 0);
-          const int half = lane >> 4, slot = (lane & 15) >> 1, part = lane & 1;
-          int4* const tile_obs = reinterpret_cast<int4*>(io.task_obs) + size_t(tile0) * size_t(K) * 2u;
-#pragma unroll 2
-          for (int pair = 0; pair < 16; ++pair) {
-            const int e = 2 * pair + half;
-            const uint32_t of = __shfl_sync(kFullMask, info, e);
-            const int live = int((of >> 13) & 127u), written = int(of >> 20);
-            const int* const table_e = buffer_words + ((of & 8191u) << 2);
-            for (int base = 0; base < most; base += 8) {
-              const int r = base + slot;
-              if (r < written) {
-                int4 value = make_int4(FRZ_PAD, FRZ_PAD, FRZ_PAD, FRZ_PAD);
-                if (r < live) {
-                  const int* row = table_e + r * kCols;
-                  if (part == 0) {
-                    value = make_int4(row[cY], row[cX], row[cDestY], row[cDestX]);
-                  } else {
-                    const int state = row[cState], assoc = row[cAssoc];
-                    value = make_int4(state == 1 ? assoc : FRZ_PAD, state == 2 ? assoc : FRZ_PAD, row[cFare], row[cEntered]);
-                  }
-                }
-                tile_obs[(size_t(e) * size_t(K) + size_t(r)) * 2u + part] = value;
-              }
-            }
-          }
-          // task masks: the tile's [32, A, K] bytes are one contiguous range of task_mask -> a flat, coalesced sweep;
-          // every lane expands 16 (or 4) rows of one driver's row set into bytes: nibble x 0x204081 spreads four bits
-          // over four bytes.  Environments outside this pass are skipped.
-          __syncwarp();
-          const uint32_t lists = min(32u, uint32_t(B - tile0)) * uint32_t(A);  // (environment, driver) pairs of the tile
-          if ((K & 15) == 0) {
-            const uint32_t per_list = uint32_t(K) >> 4, total = lists * per_list;
-            uint4* const tile_masks = reinterpret_cast<uint4*>(io.task_mask + size_t(tile0) * size_t(A * K));
-            for (uint32_t i = lane; i < total; i += 32u) {
-              const uint32_t g = per_list == 1u ? i : __umulhi(i, inverse_rows), j = i - g * per_list;
-              const uint32_t e = A == 1 ? g : __umulhi(g, inverse_agents);
-              if ((batch >> e) & 1u) {
-                const uint32_t part = uint32_t(members_of[g] >> (16u * j));
-                tile_masks[i] = make_uint4(((part & 0xfu) * 0x00204081u) & 0x01010101u, (((part >> 4) & 0xfu) * 0x00204081u) & 0x01010101u,
-                                           (((part >> 8) & 0xfu) * 0x00204081u) & 0x01010101u,
-                                           (((part >> 12) & 0xfu) * 0x00204081u) & 0x01010101u);
-              }
-            }
-          } else {
-            const uint32_t per_list = uint32_t(K) >> 2, total = lists * per_list;
-            uint32_t* const tile_masks = reinterpret_cast<uint32_t*>(io.task_mask + size_t(tile0) * size_t(A * K));
-            for (uint32_t i = lane; i < total; i += 32u) {
-              const uint32_t g = per_list == 1u ? i : __umulhi(i, inverse_rows), j = i - g * per_list;
-              const uint32_t e = A == 1 ? g : __umulhi(g, inverse_agents);
-              if ((batch >> e) & 1u) tile_masks[i] = ((uint32_t(members_of[g] >> (4u * j)) & 0xfu) * 0x00204081u) & 0x01010101u;
-            }
-          }
-        }
-
-        // ------------------------------------------------------------------ write the tables back (one bulk copy each)
-        if (MODE != kRsRefresh && FRZ_RS_ABLATE != 2) {
-          const uint32_t store_bytes = (now && admits) ? (uint32_t(n_rows * kCols * 4) + 15u) & ~15u : 0u;
-          fence_async_shared();  // this lane's edits of its rows become visible to the async proxy
-          __syncwarp();
-          const uint32_t piece = (offset << 4) | (store_bytes >> 4);
-          int* target_rows = global_rows;
-#pragma unroll 4
-          for (int e = 0; e < 32; ++e, target_rows += table_words) {
-            const uint32_t of = __shfl_sync(kFullMask, piece, e);
-            if ((of & 0xffu) != 0u) {
-              if (elect_one()) bulk_store(target_rows, buffer + ((of >> 8) << 4), (of & 0xffu) << 4);
-            }
-          }
-          bulk_commit();  // waited for before the buffer is written again (next pass) and before the CTA exits
-        }
+        // this pass's generic accesses to the buffer are ordered before the next pass's bulk copies into it
+        fence_async_shared();
         __syncwarp();
         pending &= ~batch;
       }
     }
-    bulk_wait_read();
   }
   finish_launch(control, alive_bits, faults, agent_bits,
                 skip ? kPublishNothing : (MODE == kRsStep ? kPublishStep : kPublishRefresh));
@@ -1185,21 +1179,15 @@ int rideshare_launch_tiles(const FrzRideshareParams* p, const FrzRideshareBuffer
   const uint32_t warp_bytes = std::max(one_table, typical);
   // schedule_index travels to shared memory when it is short enough (an entry per step of the schedule's horizon)
   const int index_words = p->schedule_rows > 0 && p->schedule_horizon + 2 <= kTileIndexWords ? p->schedule_horizon + 2 : 0;
-  // i / n = umulhi(i, ceil(2^32 / n)) for the small i the task-mask sweep divides (n = 16- or 4-row pieces per task
-  // list, n = drivers)
-  const auto inverse = [](uint32_t n) { return n > 1u ? uint32_t(((1ull << 32) + n - 1u) / n) : 0u; };
-  const uint32_t inverse_rows = inverse((K & 15) == 0 ? uint32_t(K) >> 4 : uint32_t(K) >> 2);
-  const uint32_t inverse_agents = inverse(uint32_t(p->num_agents));
-  const size_t set_bytes = WIDE ? 8 : 4;
-  const size_t smem = size_t(kTileWarps) * (warp_bytes + 32 * p->num_agents * set_bytes) + 8 * kTileWarps + 4 * size_t(index_words);
+  const size_t smem = size_t(kTileWarps) * warp_bytes + 8 * kTileWarps + 4 * size_t(index_words);
   auto kernel = rideshare_tile_kernel<MAXA, WIDE, MODE>;
   if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
     return check_launch("rideshare shared memory");
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   const int ctas_per_sm = resident_ctas(kernel, kTileThreads, smem);
   const int tiles = (B + 31) / 32;
   const int grid = persistent_grid((tiles + kTileWarps - 1) / kTileWarps, ctas_per_sm);
-  kernel<<<grid, kTileThreads, smem, s>>>(*p, *io, B, entry_mask, batch_base, warp_bytes, index_words, inverse_rows,
-                                          inverse_agents);
+  kernel<<<grid, kTileThreads, smem, s>>>(*p, *io, B, entry_mask, batch_base, warp_bytes, index_words);
   return check_launch("rideshare_tile_kernel");
 }
 
