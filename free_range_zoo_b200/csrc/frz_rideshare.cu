@@ -498,7 +498,9 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
 // buffer is carved up by a prefix sum over what its environments need this step (live rows + rows that may enter), so
 // shared memory is sized for the typical table fill, not for the capacity; a tile whose environments do not fit in one
 // go is stepped in several passes (each pass takes the longest prefix of the waiting environments that fits).
-constexpr int kTileThreads = 128;
+// One warp per CTA: the tile index is then a function of blockIdx alone, which the compiler can prove warp-uniform -- the
+// addresses of the bulk copies stay in uniform registers -- and up to 20 such CTAs share an SM.
+constexpr int kTileThreads = 32;
 constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kTileRowBudget = 8;   // rows per environment the warp buffers are sized for (32 * 8 rows per warp)
 
@@ -539,19 +541,19 @@ __device__ __forceinline__ uint32_t mask_below(uint32_t, int n) { return n >= 32
 __device__ __forceinline__ uint64_t mask_below(uint64_t, int n) { return n >= 64 ? ~uint64_t(0) : (uint64_t(1) << n) - 1u; }
 
 template <int MAXA, bool WIDE, int MODE>
-__global__ void __launch_bounds__(kTileThreads, MAXA <= 4 ? 5 : 3)
+__global__ void __launch_bounds__(kTileThreads, MAXA <= 4 ? 20 : 12)
 rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid_constant__ FrzRideshareBuffers io,
                       const int B, const uint8_t* __restrict__ entry_mask, const int batch_base,
                       const uint32_t warp_bytes, const int index_words) {
   using Mask = typename std::conditional<WIDE, uint64_t, uint32_t>::type;
   extern __shared__ __align__(16) int smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp = __shfl_sync(kFullMask, int(threadIdx.x >> 5), 0);  // warp-uniform by construction
-  const int warps = blockDim.x >> 5;
+  static_assert(kTileWarps == 1, "the tile loop below assumes one warp per CTA");
+  const int lane = threadIdx.x;
+  constexpr int warp = 0, warps = 1;
   const int K = p.capacity, A = p.num_agents, S = p.schedule_rows;
   const uint32_t table_words = uint32_t(K * kCols);
-  const uint32_t buffer = shared_address(smem) + uint32_t(warp) * warp_bytes;
-  int* const buffer_words = smem + warp * int(warp_bytes >> 2);
+  const uint32_t buffer = shared_address(smem);
+  int* const buffer_words = smem;
   // after the table buffers: the mbarriers, then schedule_index
   int* const after_masks = smem + warps * int(warp_bytes >> 2);
   const uint32_t barrier = shared_address(after_masks) + 8u * uint32_t(warp);
@@ -573,8 +575,8 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
   unsigned alive_bits = 0, faults = 0, agent_bits = 0;
 
   if (!skip) {
-    const int tile_stride = gridDim.x * warps * 32;
-    int tile0 = (blockIdx.x * warps + warp) * 32;
+    const int tile_stride = gridDim.x * 32;
+    int tile0 = blockIdx.x * 32;
     // table fill and step of the tile's environments: loaded one tile ahead
     int next_count = 0, next_moves = 0;
     if (tile0 + lane < B) {
@@ -604,8 +606,9 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         }
       }
       // shared memory this environment needs: its live rows and the rows that may enter, in whole 16-byte pieces
-      const uint32_t need = valid ? (uint32_t(min(K, n_before + (hi - lo)) * kCols * 4) + 15u) & ~15u : 0u;
-      const uint32_t bytes_in = (uint32_t(n_before * kCols * 4) + 15u) & ~15u;
+      // (at least one piece, so that every environment of a pass has a copy to issue)
+      const uint32_t need = valid ? max(16u, (uint32_t(min(K, n_before + (hi - lo)) * kCols * 4) + 15u) & ~15u) : 0u;
+      const uint32_t bytes_in = max(16u, (uint32_t(n_before * kCols * 4) + 15u) & ~15u);
       int* const global_rows = io.passengers + size_t(tile0) * size_t(table_words);  // of the tile's first environment
 
       // ------------------------------------------------------------------ drivers and their actions
@@ -690,16 +693,16 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
 #ifndef FRZ_RS_ABLATE
 #define FRZ_RS_ABLATE 0  // profiling experiments (profiles/README.md): 1 = copies only, 2 = no copies, 3 = no observation stores
 #endif
-        if (total_in != 0u && FRZ_RS_ABLATE != 2) {
+        if (FRZ_RS_ABLATE != 2) {
           if (elect_one()) mbarrier_expect_bytes(barrier, total_in);
-          const uint32_t piece = (offset << 4) | (load_bytes >> 4);  // (offset / 16) << 8 | bytes / 16
-          const int* source = global_rows;
+          // the pass's environments are consecutive lanes; everything but the two shuffled words is warp-uniform
+          const int first = __ffs(int(batch)) - 1, last = first + __popc(batch);
+          const uint32_t table_at = buffer + offset;
+          const char* const tile_rows = reinterpret_cast<const char*>(global_rows);
 #pragma unroll 4
-          for (int e = 0; e < 32; ++e, source += table_words) {
-            const uint32_t of = __shfl_sync(kFullMask, piece, e);
-            if ((of & 0xffu) != 0u) {
-              if (elect_one()) bulk_load(buffer + ((of >> 8) << 4), source, (of & 0xffu) << 4, barrier);
-            }
+          for (int e = first; e < last; ++e) {
+            const uint32_t to = __shfl_sync(kFullMask, table_at, e), bytes = __shfl_sync(kFullMask, load_bytes, e);
+            if (elect_one()) bulk_load(to, tile_rows + uint32_t(e) * (table_words * 4u), bytes, barrier);
           }
           mbarrier_wait(barrier, phase);
           phase ^= 1u;
@@ -1169,7 +1172,7 @@ int rideshare_launch_geometry(const FrzRideshareParams* p, const FrzRideshareBuf
   return check_launch("rideshare_step_kernel");
 }
 
-// The tiled kernel: one thread per environment, 32 environments per warp, kTileWarps independent warps per CTA.
+// The tiled kernel: one thread per environment, a one-warp CTA per tile of 32 environments (persistent grid).
 template <int MAXA, bool WIDE, int MODE>
 int rideshare_launch_tiles(const FrzRideshareParams* p, const FrzRideshareBuffers* io, int B, cudaStream_t s,
                            const uint8_t* entry_mask, int batch_base) {
@@ -1185,8 +1188,12 @@ int rideshare_launch_tiles(const FrzRideshareParams* p, const FrzRideshareBuffer
     return check_launch("rideshare shared memory");
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   const int ctas_per_sm = resident_ctas(kernel, kTileThreads, smem);
+  // every CTA steps the same number of tiles (+-1): the fewest rounds the resident CTAs need, then as many CTAs as
+  // those rounds take
   const int tiles = (B + 31) / 32;
-  const int grid = persistent_grid((tiles + kTileWarps - 1) / kTileWarps, ctas_per_sm);
+  const int resident = sm_count() * ctas_per_sm;
+  const int rounds = (tiles + resident - 1) / resident;
+  const int grid = (tiles + rounds - 1) / rounds;
   kernel<<<grid, kTileThreads, smem, s>>>(*p, *io, B, entry_mask, batch_base, warp_bytes, index_words);
   return check_launch("rideshare_tile_kernel");
 }
