@@ -46,6 +46,9 @@ WORKLOADS = {
     'wildfire_c4': dict(domain='wildfire', preset='wildfire_large', envs=65536, kwargs={}, saturating=262144),
     'wildfire_c1': dict(domain='wildfire', preset='wildfire_3x3', envs=1024, kwargs={}, saturating=524288),
     'rideshare_c2': dict(domain='rideshare', preset='rideshare_c2', envs=16384, kwargs={}, saturating=524288),
+    # the two rideshare step kernels at any batch size (kernel tuning: the dispatcher picks by batch size otherwise)
+    'rideshare_c2_tiles': dict(domain='rideshare', preset='rideshare_c2', envs=16384, kwargs={}, engine_kwargs=dict(step_kernel='tiles')),
+    'rideshare_c2_groups': dict(domain='rideshare', preset='rideshare_c2', envs=16384, kwargs={}, engine_kwargs=dict(step_kernel='groups')),
     # extra wildfire geometries (kernel tuning; not named by BASELINE.json)
     'wildfire_5x6': dict(domain='wildfire', preset='wildfire_large', envs=262144, kwargs={},
                          preset_kwargs=dict(height=5, width=6, num_agents=6, seed=21)),
@@ -54,7 +57,7 @@ WORKLOADS = {
     'cyber_c3': dict(domain='cybersecurity', preset='cyber_c3', envs=16384,
                      kwargs=dict(show_bad_actions=False, partially_observable=True), saturating=4194304),
 }
-KERNELS = {'wildfire': 'wildfire_step_kernel', 'rideshare': 'rideshare_step_kernel',
+KERNELS = {'wildfire': 'wildfire_step_kernel', 'rideshare': 'rideshare_tile_kernel / rideshare_step_kernel (by batch size)',
            'cybersecurity': 'cyber_step_tiled_kernel'}
 SEED, SAMPLER = 2026, 2026
 
@@ -254,12 +257,15 @@ def _reference_rollout(job):
                          warmup=warmup)
 
 
-def _run_workers(worker, jobs):
+def _run_workers(worker, jobs, timeout: float = 900.0):
+    """One forked process per job.  Only ever called BEFORE this process touches CUDA (a forked child of a process with
+    a CUDA context dies when it collects the inherited CUDA objects, and a dead pool worker hangs ``map``); the
+    timeout turns any other stall into an error instead of a hang."""
     import multiprocessing as mp
     if len(jobs) == 1:
         return [worker(jobs[0])]
     with mp.get_context('fork').Pool(len(jobs)) as pool:
-        return pool.map(worker, jobs)
+        return pool.map_async(worker, jobs).get(timeout=timeout)
 
 
 def cpu_throughput(kind: str, workload: str, processes: int, envs_per_process: int, steps: int, warmup: int = 1):
@@ -328,6 +334,26 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def measure_cpu_baseline(workload: str):
+    """The ``cpu_baseline`` object of the engine's line: the UNMODIFIED reference (oracle/_ref) on all host cores on a
+    bounded sample of the workload, the numpy oracle port beside it (or alone when the reference copy is absent)."""
+    domain = WORKLOADS[workload]['domain']
+    host_cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    envs_per_process, cpu_steps = cpu_sample_size(workload)
+    port_value, _ = cpu_throughput('port', workload, host_cores, min(envs_per_process, 1024), cpu_steps)
+    if reference_available():
+        cpu_value, _ = cpu_throughput('reference', workload, host_cores, envs_per_process, cpu_steps)
+        return {'value': cpu_value, 'unit': 'env-steps/s', 'cores': host_cores, 'kind': 'reference',
+                'sample': f'{host_cores} single-threaded processes x {envs_per_process} envs x {cpu_steps} steps of '
+                          f'{workload}: the UNMODIFIED reference (oracle/_ref) on CPU, env.step() only, action '
+                          'sampling excluded',
+                'port_value': port_value,
+                'port': f'numpy oracle port (oracle/{domain}.py), same processes x steps, step() only'}
+    return {'value': port_value, 'unit': 'env-steps/s', 'cores': host_cores, 'kind': 'port',
+            'sample': f'{host_cores} processes x {min(envs_per_process, 1024)} envs x {cpu_steps} steps of '
+                      f'{workload}, numpy oracle port (oracle/{domain}.py); oracle/_ref is absent'}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 
 
@@ -348,7 +374,7 @@ class Harness:
         config = getattr(presets, spec['preset'])(**spec.get('preset_kwargs', {}))
         module = importlib.import_module(f'free_range_zoo_b200.envs.{spec["domain"]}_v0')
         self.env = module.parallel_env(parallel_envs=B, max_steps=1 << 30, configuration=config, device=device,
-                                       env_offset=rank * B, **spec['kwargs'])
+                                       env_offset=rank * B, **spec['kwargs'], **spec.get('engine_kwargs', {}))
         self.raw = self.env.unwrapped
         self.agents = len(self.raw.agents)
         self.start = torch.cuda.Event(enable_timing=True)
@@ -546,6 +572,8 @@ def run_engine(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    # the CPU arm runs first, while this process has no CUDA context yet (its workers are forked)
+    cpu_baseline = measure_cpu_baseline(args.workload) if world == 1 else None
     cores = pin_to_local_cores(local_rank, world)
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
@@ -631,23 +659,7 @@ def run_engine(args):
         del h, raw, recorded, packed
         torch.cuda.empty_cache()
         if world == 1:
-            host_cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
-            envs_per_process, cpu_steps = cpu_sample_size(args.workload)
-            port_value, _ = cpu_throughput('port', args.workload, host_cores, min(envs_per_process, 1024), cpu_steps)
-            if reference_available():
-                cpu_value, _ = cpu_throughput('reference', args.workload, host_cores, envs_per_process, cpu_steps)
-                line['cpu_baseline'] = {
-                    'value': cpu_value, 'unit': 'env-steps/s', 'cores': host_cores, 'kind': 'reference',
-                    'sample': f'{host_cores} single-threaded processes x {envs_per_process} envs x {cpu_steps} steps of '
-                              f'{args.workload}: the UNMODIFIED reference (oracle/_ref) on CPU, env.step() only, action '
-                              'sampling excluded',
-                    'port_value': port_value,
-                    'port': f'numpy oracle port (oracle/{domain}.py), same processes x steps, step() only'}
-            else:
-                line['cpu_baseline'] = {
-                    'value': port_value, 'unit': 'env-steps/s', 'cores': host_cores, 'kind': 'port',
-                    'sample': f'{host_cores} processes x {min(envs_per_process, 1024)} envs x {cpu_steps} steps of '
-                              f'{args.workload}, numpy oracle port (oracle/{domain}.py); oracle/_ref is absent'}
+            line['cpu_baseline'] = cpu_baseline
             if not args.skip_other_workloads:
                 others = {}
                 for name in ('wildfire_c1', 'rideshare_c2', 'cyber_c3', 'wildfire_c4'):

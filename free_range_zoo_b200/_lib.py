@@ -103,6 +103,7 @@ RS_FAST_TRAVEL = 0x1
 RS_DIAGONAL_TRAVEL = 0x2
 RS_VARIABLE_MOVE_COST = 0x4
 RS_WAITING_COSTS = 0x8
+RS_KERNEL_TILES, RS_KERNEL_GROUPS = 0x100, 0x200
 RS_PASSENGER_COLUMNS = 11
 RS_TASK_COLUMNS = 8
 
@@ -137,8 +138,14 @@ class HostStep(C.Structure):
                 ('action_format', C.c_int32), ('packed_actions', C.c_void_p), ('pipeline', C.c_void_p)]
 
 
+class GatherArray(C.Structure):
+    """FrzGatherArray: one padded [B, groups, capacity, row_bytes] array and where its live rows are packed to."""
+    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('row_bytes', C.c_int32), ('capacity', C.c_int32),
+                ('groups', C.c_int32), ('reserved', C.c_int32)]
+
+
 HOST_ACTIONS_I32, HOST_ACTIONS_I16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 _lib = None
@@ -178,6 +185,8 @@ def library() -> C.CDLL:
                                   ('frz_rideshare_step_host', RideshareParams, RideshareBuffers)):
         getattr(lib, name).argtypes = [C.POINTER(params), C.POINTER(buffers), C.c_int32, C.POINTER(HostStep), C.c_void_p]
     lib.frz_host_slices.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    lib.frz_gather_live_rows.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(GatherArray), C.c_int32,
+                                         C.c_void_p]
     if lib.frz_version() != ABI_VERSION:
         raise RuntimeError(f'libfrz.so ABI version {lib.frz_version()} != {ABI_VERSION}; rebuild the library')
     lib.frz_control_restore.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]

@@ -20,8 +20,6 @@
 #include <climits>
 #include <math_constants.h>
 
-#include <cstdlib>
-#include <cstring>
 #include <type_traits>
 
 #include "frz_common.cuh"
@@ -505,28 +503,10 @@ constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kTileRowBudget = 8;   // rows per environment the warp buffers are sized for (32 * 8 rows per warp)
 
 constexpr int kTileIndexWords = 2048;      // longest schedule_index copied to shared memory
-constexpr int kTileMinimumBatch = 49152;   // environments from which the tiled kernel is used (measured cross-over)
+constexpr int kTileMinimumBatch = 24576;   // environments from which the tiled kernel is used (measured cross-over:
+                                           // 16 384 envs 10.9 us with groups / 12.3 with tiles, 32 768: 18.9 / 13.4)
 
-// Tuning knobs for kernel experiments (profiles/README.md), read once: FRZ_RIDESHARE_KERNEL=groups|tiles forces one of
-// the two kernels whatever the batch size, FRZ_RIDESHARE_TILE_ROWS=n sizes the warp buffers of the tiled kernel for n
-// rows per environment.
-inline int rideshare_kernel_choice() {  // 0 = by batch size, 1 = tiles, 2 = groups
-  static const int choice = [] {
-    const char* name = std::getenv("FRZ_RIDESHARE_KERNEL");
-    if (name == nullptr) return 0;
-    return std::strcmp(name, "tiles") == 0 ? 1 : (std::strcmp(name, "groups") == 0 ? 2 : 0);
-  }();
-  return choice;
-}
-inline int tile_row_budget() {
-  static const int rows = [] {
-    const char* choice = std::getenv("FRZ_RIDESHARE_TILE_ROWS");
-    const int value = choice != nullptr ? std::atoi(choice) : 0;
-    return value >= 1 && value <= FRZ_MAX_PASSENGERS ? value : kTileRowBudget;
-  }();
-  return rows;
-}
-
+// row sets of an environment: bit r = table row r (32 or 64 rows)
 __device__ __forceinline__ int mask_count(uint32_t m) { return __popc(m); }
 __device__ __forceinline__ int mask_count(uint64_t m) { return __popcll(m); }
 __device__ __forceinline__ int mask_first(uint32_t m) { return __ffs(int(m)) - 1; }
@@ -535,7 +515,6 @@ __device__ __forceinline__ int mask_last(uint32_t m) { return 31 - __clz(int(m))
 __device__ __forceinline__ int mask_last(uint64_t m) { return 63 - __clzll((long long)(m)); }
 __device__ __forceinline__ int mask_select(uint32_t m, int k) { return select_bit(m, k); }
 __device__ __forceinline__ int mask_select(uint64_t m, int k) { return select_bit64(m, k); }
-
 // bits 0 .. n-1 (n may equal the width of the set)
 __device__ __forceinline__ uint32_t mask_below(uint32_t, int n) { return n >= 32 ? 0xffffffffu : (1u << n) - 1u; }
 __device__ __forceinline__ uint64_t mask_below(uint64_t, int n) { return n >= 64 ? ~uint64_t(0) : (uint64_t(1) << n) - 1u; }
@@ -1178,7 +1157,7 @@ int rideshare_launch_tiles(const FrzRideshareParams* p, const FrzRideshareBuffer
                            const uint8_t* entry_mask, int batch_base) {
   const int K = p->capacity;
   const uint32_t one_table = (uint32_t(K * kCols * 4) + 15u) & ~15u;
-  const uint32_t typical = (uint32_t(32 * std::min(K, tile_row_budget()) * kCols * 4) + 15u) & ~15u;
+  const uint32_t typical = (uint32_t(32 * std::min(K, kTileRowBudget) * kCols * 4) + 15u) & ~15u;
   const uint32_t warp_bytes = std::max(one_table, typical);
   // schedule_index travels to shared memory when it is short enough (an entry per step of the schedule's horizon)
   const int index_words = p->schedule_rows > 0 && p->schedule_horizon + 2 <= kTileIndexWords ? p->schedule_horizon + 2 : 0;
@@ -1205,8 +1184,7 @@ int rideshare_launch_mode(const FrzRideshareParams* p, const FrzRideshareBuffers
   // One thread per environment needs enough environments to fill the GPU with warps (a tile of 32 takes one warp
   // through a long dependent chain); smaller batches keep a group of lanes per environment.  Bulk copies need 16-byte
   // aligned tables.
-  const int choice = rideshare_kernel_choice();
-  const bool tiles = choice == 1 || (choice == 0 && B >= kTileMinimumBatch);
+  const bool tiles = (p->flags & FRZ_RS_KERNEL_TILES) || (!(p->flags & FRZ_RS_KERNEL_GROUPS) && B >= kTileMinimumBatch);
   if (A <= 8 && (K & 3) == 0 && tiles) {
     if (A <= 4) return K <= 32 ? rideshare_launch_tiles<4, false, MODE>(p, io, B, s, entry_mask, batch_base)
                                : rideshare_launch_tiles<4, true, MODE>(p, io, B, s, entry_mask, batch_base);

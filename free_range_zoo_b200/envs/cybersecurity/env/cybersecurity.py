@@ -241,6 +241,14 @@ class raw_env(BatchedAECEnv):
         _lib.check(self._lib.frz_cyber_refresh(ctypes.byref(self._params), ctypes.byref(self._io), self.parallel_envs,
                                                self._stream()), 'frz_cyber_refresh')
 
+
+    def _observation_download(self):
+        """Host-side observation download (``gather_observations``): every environment always has all N subnetworks as
+        tasks, so everything is dense."""
+        dense = dict(attacker_self=self._attacker_self, defender_self=self._defender_self, task_obs=self._task_obs,
+                     monitored=self._monitored, agent_task_count=self._agent_task_count)
+        return dense, {}
+
     def update_actions(self) -> None:
         """Recompute task counts from the current state (cybersecurity.py:414-457); only needed after manual edits."""
         self._refresh()

@@ -85,8 +85,12 @@ class raw_env(BatchedAECEnv):
                 "render_fps": 2}
 
     @torch.no_grad()
-    def __init__(self, *args, **kwargs):
+    def __init__(self, *args, step_kernel: str = 'auto', **kwargs):
+        """``step_kernel`` ('auto' | 'tiles' | 'groups') picks the step kernel: by batch size, or one of the two
+        whatever the batch size (identical results; for tests and kernel timing -- include/frz.h FRZ_RS_KERNEL_*)."""
         super().__init__(*args, **kwargs)
+        if step_kernel not in ('auto', 'tiles', 'groups'):
+            raise ValueError(f"step_kernel must be 'auto', 'tiles' or 'groups', not {step_kernel!r}")
         A = int(self.agent_config.start_positions.shape[0])
         self.possible_agents = tuple(f'driver_{i}' for i in range(1, A + 1))
         self.agents = self.possible_agents
@@ -97,6 +101,7 @@ class raw_env(BatchedAECEnv):
         self.passenger_observation_bounds = (self.max_y, self.max_x, self.max_y, self.max_x, A, A, self.config.max_fare,
                                              self.max_steps)
         self._params, schedule = flatten_configuration(self.config, self.max_steps, self.parallel_envs, self.env_offset)
+        self._params.flags |= {'auto': 0, 'tiles': _lib.RS_KERNEL_TILES, 'groups': _lib.RS_KERNEL_GROUPS}[step_kernel]
         B, K, dev = self.parallel_envs, self._params.capacity, self.device
         self._capacity = K
         self._allocate_runtime(A)
@@ -187,6 +192,14 @@ class raw_env(BatchedAECEnv):
     def _refresh(self) -> None:
         _lib.check(self._lib.frz_rideshare_refresh(ctypes.byref(self._params), ctypes.byref(self._io),
                                                    self.parallel_envs, self._stream()), 'frz_rideshare_refresh')
+
+
+    def _observation_download(self):
+        """Host-side observation download (``gather_observations``): self observations and per-driver task counts whole,
+        the live rows of the task observations and of every driver's task-mask row packed."""
+        dense = dict(self_obs=self._self_obs, agent_task_count=self._agent_task_count)
+        ragged = dict(task_obs=(self._task_obs, 1), task_mask=(self._task_mask, len(self.possible_agents)))
+        return dense, ragged
 
     def update_actions(self) -> None:
         """Recompute task lists from the current table (rideshare.py:368-395); only needed after manual edits."""

@@ -281,6 +281,14 @@ class raw_env(BatchedAECEnv):
         _lib.check(self._lib.frz_wildfire_refresh(ctypes.byref(self._params), ctypes.byref(self._io),
                                                   self.parallel_envs, self._stream()), 'frz_wildfire_refresh')
 
+
+    def _observation_download(self):
+        """Host-side observation download (``gather_observations``): self observations and per-agent task counts whole,
+        the live rows of the task observations and of every agent's action-mask row packed."""
+        dense = dict(self_obs=self._self_obs, agent_task_count=self._agent_task_count)
+        ragged = dict(task_obs=(self._task_obs, 1), action_mask=(self._action_mask, len(self.possible_agents)))
+        return dense, ragged
+
     def update_actions(self) -> None:
         """Recompute task counts / masks from the current state (wildfire.py:587-666). The fused step already does
         this; call it only after editing ``env.state()`` by hand."""

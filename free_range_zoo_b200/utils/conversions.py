@@ -67,12 +67,13 @@ class batched_aec_to_batched_parallel_wrapper:
         self.agents = env.agents
         return self.observe(), env.rewards, env.terminations, env.truncations, env.infos
 
-    def step_host(self, host_actions: torch.Tensor, chunks=None):
+    def step_host(self, host_actions: torch.Tensor, chunks=None, observations: bool = False):
         """Parallel step with HOST buffers: page-locked int32 ``[B, A, 2]`` actions in, page-locked ``(rewards [B, A],
         terminated [B], truncated [B])`` out; upload, step and download are pipelined over slices of the batch
-        (``BatchedAECEnv.step_host``).  Observations stay on the device: ``observe()``."""
+        (``BatchedAECEnv.step_host``).  Observations stay on the device (``observe()``) unless ``observations=True``:
+        then a fourth element carries them in host memory, packed (``BatchedAECEnv.gather_observations``)."""
         env = self.aec_env.unwrapped
-        results = env.step_host(host_actions, chunks)
+        results = env.step_host(host_actions, chunks, observations)
         self.agents = env.agents
         return results
 

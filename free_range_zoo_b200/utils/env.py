@@ -20,6 +20,7 @@ NOTE on aliasing: because buffers are updated in place, tensors returned by ``st
 from __future__ import annotations
 
 import ctypes
+import math
 from abc import ABC, abstractmethod
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -364,9 +365,94 @@ class BatchedAECEnv(ABC):
         self._host_state = state
         return state
 
+    # ------------------------------------------------------------------------------------------ observations on the host
+
+    def _observation_download(self) -> Tuple[Dict[str, torch.Tensor], Dict[str, Tuple[torch.Tensor, int]]]:
+        """What a policy on the host reads after a step: ``(dense, ragged)``.  ``dense`` arrays leave the device whole;
+        ``ragged`` maps a name to ``(padded array [B, groups, capacity, ...] or [B, capacity, ...], groups)`` of which
+        only the first ``environment_task_count[b]`` rows per environment (and row block) are live.  Domain hook."""
+        raise NotImplementedError
+
+    def _gather_state(self):
+        state = getattr(self, '_gather', None)
+        if state is not None:
+            return state
+        B, dev = self.parallel_envs, self.device
+        dense, ragged = self._observation_download()
+        arrays = (_lib.GatherArray * max(1, len(ragged)))()
+        packed, layout = {}, {}
+        for at, (name, (tensor, groups)) in enumerate(ragged.items()):
+            capacity = tensor.shape[2] if tensor.dim() >= 3 and groups > 1 else tensor.shape[1]
+            row_shape = tuple(tensor.shape[3:] if groups > 1 else tensor.shape[2:])
+            row_bytes = tensor.element_size() * math.prod(row_shape)
+            packed[name] = torch.empty(tensor.numel(), dtype=tensor.dtype, device=dev)
+            arrays[at].src, arrays[at].dst = tensor.data_ptr(), packed[name].data_ptr()
+            arrays[at].row_bytes, arrays[at].capacity, arrays[at].groups = row_bytes, capacity, groups
+            layout[name] = (groups, row_shape, row_bytes // tensor.element_size())
+        state = dict(
+            dense=dense, ragged=ragged, arrays=arrays, packed=packed, layout=layout,
+            offsets=torch.zeros(B + 1, dtype=torch.int32, device=dev),
+            scratch=torch.zeros((B + 1023) // 1024 + 1, dtype=torch.int32, device=dev),
+            host_counts=torch.zeros(B, dtype=torch.int32).pin_memory(),
+            host_offsets=torch.zeros(B + 1, dtype=torch.int32).pin_memory(),
+            host_dense={name: torch.empty(tensor.shape, dtype=tensor.dtype).pin_memory() for name, tensor in dense.items()},
+            host_packed={name: torch.empty(tensor.numel(), dtype=tensor.dtype).pin_memory() for name, tensor in packed.items()},
+        )
+        self._gather = state
+        return state
+
+    def _enqueue_gather(self, state) -> None:
+        """Compaction kernels + the downloads whose size is known up front (counts, offsets, dense arrays), on the
+        current stream of the device."""
+        _lib.check(self._lib.frz_gather_live_rows(self.environment_task_count.data_ptr(), self.parallel_envs,
+                                                  state['offsets'].data_ptr(), state['scratch'].data_ptr(), state['arrays'],
+                                                  len(state['ragged']), self._stream()), 'frz_gather_live_rows')
+        state['host_counts'].copy_(self.environment_task_count, non_blocking=True)
+        state['host_offsets'].copy_(state['offsets'], non_blocking=True)
+        for name, tensor in state['dense'].items():
+            state['host_dense'][name].copy_(tensor, non_blocking=True)
+
+    def _finish_gather(self, state) -> Dict[str, Any]:
+        """Second half, after the stream has been synchronised once: the packed rows, exactly as many bytes as are live
+        (one copy per array), then the host views."""
+        B = self.parallel_envs
+        total = int(state['host_offsets'][B])
+        moved = state['host_counts'].numel() * 4 + state['host_offsets'].numel() * 4
+        moved += sum(t.numel() * t.element_size() for t in state['host_dense'].values())
+        out: Dict[str, Any] = {'counts': state['host_counts'], 'offsets': state['host_offsets'], 'total': total}
+        out.update(state['host_dense'])
+        for name, device_rows in state['packed'].items():
+            groups, row_shape, row_elements = state['layout'][name]
+            live = total * groups * row_elements
+            host_rows = state['host_packed'][name][:live]
+            if live:
+                host_rows.copy_(device_rows[:live], non_blocking=True)
+            moved += live * device_rows.element_size()
+            # environment b's block g = rows [offsets[b] * groups + g * counts[b], ... + counts[b])
+            out[name] = host_rows.view((total * groups, ) + row_shape) if row_shape else host_rows
+        torch.cuda.current_stream(self.device).synchronize()
+        out['bytes'] = moved
+        return out
+
     @torch.no_grad()
-    def step_host(self, host_actions: torch.Tensor, chunks: Optional[int] = None
-                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    def gather_observations(self) -> Dict[str, Any]:
+        """The observations of the current state in page-locked HOST memory, packed like the reference's jagged nested
+        tensors (a value buffer + offsets; wildfire.py:669-717, rideshare.py:398-467): ``counts`` int32 [B] live tasks
+        per environment, ``offsets`` int32 [B + 1] their exclusive prefix sum, the dense arrays (``self_obs``,
+        ``agent_task_count``, ...) whole, and for every padded array its live rows only -- environment b's row block
+        g of array ``name`` is ``out[name][offsets[b] * groups + g * counts[b] :][:counts[b]]`` (groups = 1 for task
+        observations, = agents for the action / task masks).  The live rows are compacted on the device
+        (``frz_gather_live_rows``) so that each array crosses PCIe in one copy of exactly its live bytes.  The
+        returned tensors are overwritten by the next call.  ``out['bytes']`` = bytes copied device -> host."""
+        with torch.cuda.device(self.device):
+            state = self._gather_state()
+            self._enqueue_gather(state)
+            torch.cuda.current_stream(self.device).synchronize()
+            return self._finish_gather(state)
+
+    @torch.no_grad()
+    def step_host(self, host_actions: torch.Tensor, chunks: Optional[int] = None, observations: bool = False
+                  ) -> Tuple[torch.Tensor, ...]:
         """One environment step for callers that live on the host: ``host_actions`` is a page-locked int32 -- or int16,
         which halves the upload and is widened on the device -- ``[B, A, 2]`` CPU tensor (agent order = ``env.agents``);
         returns page-locked CPU tensors ``(rewards f32 [B, A],
@@ -374,7 +460,9 @@ class BatchedAECEnv(ABC):
         ``step_host``.  Equivalent to copying the actions to the device, ``step_all`` and copying the results back,
         but the batch is cut into ``chunks`` slices whose uploads, step kernels and downloads overlap
         (``frz_<domain>_step_host``, include/frz.h); the results are bit-identical.  Observations, masks and counts stay
-        on the device as usual."""
+        on the device as usual -- unless ``observations=True``: then the call also returns, as a fourth element, what
+        ``gather_observations()`` returns (the next observations in host memory, packed), which is what a policy that
+        runs on the CPU needs for its next decision."""
         B, A = self.parallel_envs, len(self.possible_agents)
         if (host_actions.device.type != 'cpu' or host_actions.dtype not in (torch.int32, torch.int16)
                 or not host_actions.is_contiguous() or tuple(host_actions.shape) != (B, A, 2)
@@ -395,8 +483,15 @@ class BatchedAECEnv(ABC):
         self._rebind_outputs()
         if self.log_directory is not None:
             self._log_environment()
-        main.synchronize()
-        return state['rewards'], state['terminated'], state['truncated']
+        if not observations:
+            main.synchronize()
+            return state['rewards'], state['terminated'], state['truncated']
+        with torch.cuda.stream(main):  # compaction + fixed-size downloads ride on the same synchronisation
+            gather = self._gather_state()
+            self._enqueue_gather(gather)
+            main.synchronize()
+            packed = self._finish_gather(gather)
+        return state['rewards'], state['terminated'], state['truncated'], packed
 
     def _advance(self) -> None:
         _, _, infos = self.step_environment()

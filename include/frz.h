@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FRZ_ABI_VERSION 3
+#define FRZ_ABI_VERSION 4
 
 #define FRZ_MAX_AGENTS 32      /* agents per environment (one warp lane each) */
 #define FRZ_MAX_EQUIPMENT 8    /* wildfire equipment states */
@@ -254,6 +254,12 @@ int frz_cyber_sample_actions(const FrzCyberParams* params, const FrzCyberBuffers
 #define FRZ_RS_DIAGONAL_TRAVEL 0x2u      /* AgentConfiguration.use_diagonal_travel */
 #define FRZ_RS_VARIABLE_MOVE_COST 0x4u   /* RewardConfiguration.use_variable_move_cost */
 #define FRZ_RS_WAITING_COSTS 0x8u        /* RewardConfiguration.use_waiting_costs */
+/* Which of the two step kernels runs is normally decided by the batch size (one thread per environment from 24 576
+ * environments up, a group of lanes per environment below).  These two bits force one of them -- results are identical;
+ * they exist so that both kernels can be tested and timed at any batch size.  The tiled kernel serves tables with a
+ * multiple of four rows and at most eight drivers; other shapes always take the group kernel. */
+#define FRZ_RS_KERNEL_TILES 0x100u
+#define FRZ_RS_KERNEL_GROUPS 0x200u
 #define FRZ_RS_PASSENGER_COLUMNS 11      /* (batch, y, x, dest_y, dest_x, fare, state, assoc, entered, accepted, picked) */
 #define FRZ_RS_TASK_COLUMNS 8            /* (y, x, dest_y, dest_x, accepted_by, riding_by, fare, entered) */
 
@@ -361,6 +367,29 @@ int frz_cyber_step_host(const FrzCyberParams* params, const FrzCyberBuffers* io,
                         const FrzHostStep* host, void* stream);
 int frz_rideshare_step_host(const FrzRideshareParams* params, const FrzRideshareBuffers* io, int32_t parallel_envs,
                             const FrzHostStep* host, void* stream);
+
+/* ----------------------------------------------------------------------------------------------- observation download */
+
+/* The step publishes observations as padded arrays -- task_obs [B, capacity, columns], action / task masks
+ * [B, agents, capacity] -- of which only the first counts[b] rows per environment are live; the reference hands the
+ * same data to a policy as jagged nested tensors, i.e. a packed value buffer + offsets (wildfire.py:669-717,
+ * rideshare.py:398-467, `obs['tasks']`, `agent_action_mapping`).  A caller that reads observations on the HOST wants
+ * that packed buffer: the PCIe link is the slowest hop of a host-driven step, so the live rows are compacted on the
+ * device and each array then leaves with ONE cudaMemcpyAsync of exactly offsets[B] * groups * row_bytes bytes.
+ *
+ * One padded array: src = [B, groups, capacity] rows of row_bytes bytes, environment b owns rows 0 .. counts[b]-1 of
+ * each of its `groups` row blocks; in dst environment b's block g starts at row offsets[b] * groups + g * counts[b]. */
+typedef struct {
+  const void* src;      /* device */
+  void* dst;            /* device, room for parallel_envs * groups * capacity rows */
+  int32_t row_bytes, capacity, groups;
+  int32_t reserved;
+} FrzGatherArray;
+
+/* offsets[0 .. B] <- exclusive prefix sum of counts (offsets[B] = all live rows), then every array is compacted.
+ * scratch = device int32 [(B + 1023) / 1024 + 1].  Only enqueues work on `stream`; allocates nothing. */
+int frz_gather_live_rows(const int32_t* counts, int32_t parallel_envs, int32_t* offsets, int32_t* scratch,
+                         const FrzGatherArray* arrays, int32_t array_count, void* stream);
 
 /* ----------------------------------------------------------------------------------------------- common */
 

@@ -3,7 +3,7 @@ cd "$(dirname "$0")/.."
 O=gpurun_out/rs
 mkdir -p $O; rm -f $O/*.json
 ( FRZ_RIDESHARE_KERNEL=tiles timeout 900 python -m pytest tests/test_rideshare_gpu.py tests/test_host_step_gpu.py -x -q ) > $O/pytest.log 2>&1; tail -5 $O/pytest.log
-for rows in 7 8; do
+for rows in 8; do
   FRZ_RIDESHARE_KERNEL=tiles FRZ_RIDESHARE_TILE_ROWS=$rows timeout 300 python bench.py --workload rideshare_c2 --parallel-envs 524288 --skip-other-workloads --windows 3 > $O/tiles_r$rows.json 2> $O/tiles_r$rows.err || tail -3 $O/tiles_r$rows.err
 done
 for b in $RS_SWEEP; do

@@ -28,7 +28,7 @@ def child(args):
     device = torch.device('cuda', 0)
     module = importlib.import_module(f'free_range_zoo_b200.envs.{spec["domain"]}_v0')
     env = module.parallel_env(parallel_envs=B, max_steps=1 << 30, configuration=getattr(presets, spec['preset'])(**spec.get('preset_kwargs', {})),
-                              device=device, **spec['kwargs'])
+                              device=device, **spec['kwargs'], **spec.get('engine_kwargs', {}))
     raw = env.unwrapped
     env.reset(seed=2026)
     for _ in range(args.warmup):

@@ -18,6 +18,7 @@ STRUCTS = {
     'FrzRideshareParams': _lib.RideshareParams,
     'FrzRideshareBuffers': _lib.RideshareBuffers,
     'FrzHostStep': _lib.HostStep,
+    'FrzGatherArray': _lib.GatherArray,
 }
 
 
@@ -31,10 +32,10 @@ def lib():
 
 def test_every_declared_symbol_is_exported(lib):
     declared = _lib.exported_symbols()
-    assert len(declared) == 25  # 7 library-wide + 6 per domain
+    assert len(declared) == 26  # 8 library-wide + 6 per domain
     missing = [name for name in declared if not hasattr(lib, name)]
     assert not missing, missing
-    assert lib.frz_version() == _lib.ABI_VERSION == 3
+    assert lib.frz_version() == _lib.ABI_VERSION == 4
 
 
 def test_ctypes_mirrors_match_the_c_layout(tmp_path):

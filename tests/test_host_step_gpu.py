@@ -185,3 +185,72 @@ def test_capture_graph_does_not_advance_the_environment():
     torch.cuda.synchronize()
     assert torch.equal(raw.state().fires, twin.unwrapped.state().fires)
     assert torch.equal(raw._cumulative, twin.unwrapped._cumulative)
+
+
+def expected_packing(raw):
+    """The packed observation download rebuilt with plain torch indexing from the padded device arrays."""
+    B = raw.parallel_envs
+    counts = raw.environment_task_count.cpu().numpy()
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    dense, ragged = raw._observation_download()
+    want = {name: tensor.cpu() for name, tensor in dense.items()}
+    for name, (tensor, groups) in ragged.items():
+        host = tensor.cpu()
+        pieces = []
+        for b in range(B):
+            blocks = host[b] if groups > 1 else host[b][None]
+            for g in range(groups):
+                pieces.append(blocks[g][:counts[b]])
+        want[name] = torch.cat(pieces) if pieces else host.new_zeros((0, ) + tuple(host.shape[2:]))
+    return counts, offsets, want
+
+
+@pytest.mark.parametrize('domain,preset,kwargs,B', [
+    ('wildfire', 'wildfire_large', {}, 1500),
+    ('wildfire', 'wildfire_3x3', {}, 2049),
+    ('rideshare', 'rideshare_c2', {}, 1300),
+    ('cybersecurity', 'cyber_c3', dict(show_bad_actions=False, partially_observable=True), 3000),
+])
+def test_gather_observations_packs_the_live_rows(domain, preset, kwargs, B):
+    """frz_gather_live_rows: counts, offsets, dense arrays and packed live rows in host memory == the padded device
+    arrays, bit for bit, at several points of a rollout (ragged, empty and full environments included)."""
+    env = make(domain, preset, kwargs, B, 50)
+    env.reset(seed=4)
+    raw = env.unwrapped
+    for t in range(10):
+        raw.sample_actions(9)
+        raw.step_all()
+        if t % 3:
+            continue
+        got = raw.gather_observations()
+        counts, offsets, want = expected_packing(raw)
+        assert np.array_equal(got['counts'].numpy(), counts) and np.array_equal(got['offsets'].numpy(), offsets)
+        assert got['total'] == int(offsets[-1])
+        moved = got['counts'].numel() * 4 + got['offsets'].numel() * 4
+        for name, tensor in want.items():
+            assert got[name].is_pinned()
+            assert torch.equal(got[name].reshape(tensor.shape), tensor), (name, t)
+            moved += tensor.numel() * tensor.element_size()
+        assert got['bytes'] == moved  # exactly the live bytes crossed the link
+
+
+def test_step_host_returns_the_next_observations():
+    """step_host(observations=True): the fourth element is the packed observation download of the stepped state."""
+    B = 4100
+    device_env, host_env = make('wildfire', 'wildfire_large', {}, B, 20), make('wildfire', 'wildfire_large', {}, B, 20)
+    device_env.reset(seed=2)
+    host_env.reset(seed=2)
+    reference, raw = device_env.unwrapped, host_env.unwrapped
+    host_actions = torch.empty((B, len(raw.agents), 2), dtype=torch.int32).pin_memory()
+    for t in range(6):
+        reference.sample_actions(3)
+        host_actions.copy_(reference._actions)
+        torch.cuda.synchronize()
+        reference.step_all()
+        rewards, terminated, truncated, observations = host_env.step_host(host_actions, 3, observations=True)
+        assert torch.equal(rewards, reference._rewards.cpu())
+        counts, offsets, want = expected_packing(reference)
+        assert np.array_equal(observations['counts'].numpy(), counts)
+        assert np.array_equal(observations['offsets'].numpy(), offsets)
+        for name, tensor in want.items():
+            assert torch.equal(observations[name].reshape(tensor.shape), tensor), (name, t)

@@ -16,11 +16,15 @@ def make_env(config, B, max_steps, **kwargs):
                                      device=torch.device('cuda'), **kwargs)
 
 
+KERNELS = ['groups', 'tiles']  # a group of lanes per environment / one thread per environment (include/frz.h)
+
+
+@pytest.mark.parametrize('kernel', KERNELS)
 @pytest.mark.parametrize('name', G.fixtures('rideshare'))
-def test_matches_reference_trajectory(name):
+def test_matches_reference_trajectory(name, kernel):
     meta, gold = G.load(name)
     config = getattr(presets, meta['preset'])(**meta['preset_kwargs'])
-    env = make_env(config, meta['B'], meta['max_steps'])
+    env = make_env(config, meta['B'], meta['max_steps'], step_kernel=kernel)
     env.reset(seed=0)
     width = gold['passengers'].shape[2]
     G.compare(rideshare_outputs(env, width), gold, 0, context=name)
@@ -62,19 +66,20 @@ def policy_actions(oracle, rng, wild):
     ('rideshare_synthetic', dict(drivers=20, rows=64), 60, 30, 0.2),  # 32-lane groups: 20 drivers, a full 64-row table
     ('rideshare_synthetic', dict(drivers=12, rows=40), 80, 30, 0.2),  # 16-lane groups, 4 rows per lane
     ('rideshare_synthetic', dict(drivers=32, rows=24), 50, 30, 0.1),  # the engine's driver limit
-    # the tiled kernel (one thread per environment; tables with a multiple of four rows, at most eight drivers)
+    # shapes the tiled kernel serves (tables with a multiple of four rows, at most eight drivers)
     ('rideshare_synthetic', dict(drivers=7, rows=24), 200, 30, 0.2),  # eight-driver variant, odd driver count
     ('rideshare_synthetic', dict(drivers=8, rows=40), 130, 30, 0.2),  # ... with 64-bit row sets, four drivers per store
     ('rideshare_synthetic', dict(drivers=6, rows=16), 97, 30, 0.2),  # ... two drivers per load, a partial last tile
     ('rideshare_synthetic', dict(drivers=2, rows=64), 70, 30, 0.1),  # four-driver variant, a full 64-row table
     ('rideshare_c2', {}, 2100, 90, 0.1),  # more tiles than one CTA's warps, partial last tile
 ])
-def test_matches_oracle_on_random_rollouts(preset, preset_kwargs, B, steps, wild):
+@pytest.mark.parametrize('kernel', KERNELS)
+def test_matches_oracle_on_random_rollouts(preset, preset_kwargs, B, steps, wild, kernel):
     from oracle.rideshare import RideshareOracle
     config = getattr(presets, preset)(**preset_kwargs)
     oracle = RideshareOracle(config, B, steps)
     oracle.reset()
-    env = make_env(config, B, steps)
+    env = make_env(config, B, steps, step_kernel=kernel)
     env.reset(seed=1)
     rng = np.random.default_rng(17)
     width = oracle.K
@@ -87,10 +92,32 @@ def test_matches_oracle_on_random_rollouts(preset, preset_kwargs, B, steps, wild
     env.unwrapped.check_errors()
 
 
-def test_full_size_sampler_rollout_properties():
+@pytest.mark.parametrize('B,steps', [(16384, 6), (32768, 4)], ids=['c2_named_size_groups', 'tiles_by_batch_size'])
+def test_full_size_oracle_parity(B, steps):
+    """C2 at its named batch size (16 384 environments, the group kernel) and at a size the dispatcher gives to the
+    tiled kernel: every output bit-exact against the oracle, actions sampled on the device."""
+    from oracle.rideshare import RideshareOracle
+    config = presets.rideshare_c2()
+    oracle = RideshareOracle(config, B, 100)
+    oracle.reset()
+    env = make_env(config, B, 100)
+    env.reset(seed=8)
+    raw = env.unwrapped
+    for t in range(steps):
+        raw.sample_actions(23)
+        actions = raw._actions.cpu().numpy().copy()
+        assert oracle.step(actions)
+        raw.step_all()
+        want = {key: value[None] for key, value in oracle.outputs().items()}
+        G.compare(rideshare_outputs(env, oracle.K), want, 0, context=f'B={B} t={t}')
+    raw.check_errors()
+
+
+@pytest.mark.parametrize('kernel', KERNELS)
+def test_full_size_sampler_rollout_properties(kernel):
     """C2 at its full size (16,384 envs): invariants of any legal rollout, driven by the on-device sampler."""
     B = 16384
-    env = make_env(presets.rideshare_c2(), B, 100)
+    env = make_env(presets.rideshare_c2(), B, 100, step_kernel=kernel)
     env.reset(seed=3)
     raw = env.unwrapped
     total = torch.zeros((B, 4), device='cuda')
