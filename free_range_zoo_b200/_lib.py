@@ -44,6 +44,7 @@ WF_FLAGS = dict(suppressant_decrease=0x0001, suppressant_refill=0x0002, tank_swi
 WF_BURNOUT_SCALED = 0x0400
 WF_LOCALIZE_PUTOUTS = 0x0800
 WF_SHOW_BAD_ACTIONS = 0x1000
+WF_KERNEL_TILES, WF_KERNEL_GROUPS = 0x2000, 0x4000
 
 
 class WildfireParams(C.Structure):

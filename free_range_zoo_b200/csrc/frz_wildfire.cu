@@ -1127,6 +1127,38 @@ void fold_configuration(const FrzWildfireParams& in, int group, int cells_per_la
   }
 }
 
+#include "frz_wildfire_tile.cuh"
+
+// The tiled kernel for small grids: a one-warp CTA per tile of 32 environments, persistent grid in whole rounds.
+template <int MAXA, int MODE, bool INJECTED>
+int launch_tiles(const FrzWildfireParams& caller_params, const FrzWildfireBuffers& io, int B, const Geometry& g,
+                 cudaStream_t stream) {
+  FrzWildfireParams p;
+  Derived derived;
+  fold_configuration(caller_params, g.group, g.cells_per_lane, &p, &derived);
+  const SmallRandomLayout layout = small_random_layout(p.height * p.width, p.num_agents, g.group, g.cells_per_lane,
+                                                       derived.spare_lanes_feed_agents != 0);
+  const size_t smem = size_t(small_tile(p.height * p.width, p.num_agents).total) * sizeof(uint32_t);
+  auto kernel = wildfire_tile_kernel<MAXA, MODE, INJECTED>;
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    return check_launch("wildfire tile shared memory");
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  const int tiles = (B + 31) / 32;
+  const int resident = sm_count() * resident_ctas(kernel, 32, smem);
+  const int rounds = (tiles + resident - 1) / resident;
+  const int grid = (tiles + rounds - 1) / rounds;
+  kernel<<<grid, 32, smem, stream>>>(p, io, derived, layout, B);
+  return check_launch("wildfire_tile_kernel");
+}
+
+template <int MAXA>
+int launch_tiles_mode(const FrzWildfireParams& p, const FrzWildfireBuffers& io, int B, int mode, const Geometry& g,
+                      cudaStream_t stream) {
+  if (mode != kStep) return launch_tiles<MAXA, kRefresh, false>(p, io, B, g, stream);
+  if (io.field_uniforms != nullptr || io.agent_uniforms != nullptr) return launch_tiles<MAXA, kStep, true>(p, io, B, g, stream);
+  return launch_tiles<MAXA, kStep, false>(p, io, B, g, stream);
+}
+
 template <int G, int CPL, int MODE, bool INJECTED, bool BULK>
 int launch_variant(const FrzWildfireParams& caller_params, const FrzWildfireBuffers& io, int B, cudaStream_t stream) {
   FrzWildfireParams p;
@@ -1188,6 +1220,11 @@ int dispatch(const FrzWildfireParams* p, const FrzWildfireBuffers* io, int B, in
     }
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // small grids: one thread per environment once the batch fills the GPU with tiles (same random streams either way)
+  if (small_grid(*p) && g.group == 8 &&
+      ((p->flags & FRZ_WF_KERNEL_TILES) || (!(p->flags & FRZ_WF_KERNEL_GROUPS) && B >= kSmallTileMinimumBatch))) {
+    return p->num_agents <= 4 ? launch_tiles_mode<4>(*p, *io, B, mode, g, s) : launch_tiles_mode<8>(*p, *io, B, mode, g, s);
+  }
   if (g.group == 8) {
     switch (g.cells_per_lane) {
       case 1: return launch_step<8, 1>(*p, *io, B, mode, s);

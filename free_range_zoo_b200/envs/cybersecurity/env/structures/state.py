@@ -6,7 +6,7 @@ import torch
 from free_range_zoo_b200.utils.state import State
 
 
-@dataclass
+@dataclass(eq=False)
 class CybersecurityState(State):
     """
     network_state: int32 [B, N]       exploitation state of each subnetwork (higher = worse)

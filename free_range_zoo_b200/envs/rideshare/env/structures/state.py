@@ -11,7 +11,7 @@ import torch
 from free_range_zoo_b200.utils.state import State
 
 
-@dataclass
+@dataclass(eq=False)
 class RideshareState(State):
     """
     agents:          int32 [B, A, 2] (y, x)

@@ -6,7 +6,7 @@ import torch
 from free_range_zoo_b200.utils.state import State
 
 
-@dataclass
+@dataclass(eq=False)
 class WildfireState(State):
     """
     fires:        int32 [B, H, W]  sign = lit (>0) / unlit or out (<0) / no fire possible (0); |value| = power needed

@@ -151,8 +151,15 @@ class raw_env(BatchedAECEnv):
 
     @torch.no_grad()
     def __init__(self, *args, observe_other_suppressant: bool = False, observe_other_power: bool = False,
-                 show_bad_actions: bool = False, **kwargs) -> None:
+                 show_bad_actions: bool = False, step_kernel: str = 'auto', **kwargs) -> None:
+        """``step_kernel`` ('auto' | 'tiles' | 'groups'): grids of at most 32 cells with at most 8 agents have two step
+        kernels (one thread per environment for large batches, eight lanes per environment otherwise) with identical
+        results and random streams; 'auto' picks by batch size, the other two force one (tests, kernel timing --
+        include/frz.h FRZ_WF_KERNEL_*).  Larger grids ignore it."""
         super().__init__(*args, **kwargs)
+        if step_kernel not in ('auto', 'tiles', 'groups'):
+            raise ValueError(f"step_kernel must be 'auto', 'tiles' or 'groups', not {step_kernel!r}")
+        self._step_kernel = step_kernel
         self.observe_other_suppressant = observe_other_suppressant
         self.observe_other_power = observe_other_power
         self.show_bad_actions = show_bad_actions
@@ -176,6 +183,7 @@ class raw_env(BatchedAECEnv):
 
         self._params, cell_reward, cell_ignition, range_mask = flatten_configuration(
             self.config, self.max_steps, show_bad_actions, self.env_offset)
+        self._params.flags |= {'auto': 0, 'tiles': _lib.WF_KERNEL_TILES, 'groups': _lib.WF_KERNEL_GROUPS}[step_kernel]
         B, HW, dev = self.parallel_envs, self.max_y * self.max_x, self.device
         self._allocate_runtime(A)
         self._mask_stride = (HW + 3) // 4 * 4

@@ -1,7 +1,8 @@
 """Environment state container.
 
 Same surface as the reference base class (free_range_zoo/utils/state.py:12-128): a dataclass of batched tensors with
-``to / clone / save_initial / restore_initial / save_checkpoint / restore_from_checkpoint / load_state``.  In this
+``to / clone / save_initial / restore_initial / save_checkpoint / restore_from_checkpoint / load_state / stack / cat /
+unwrap / to_dataframe`` plus ``__len__ / __getitem__ / __hash__``.  In this
 engine the fields are *views of the buffers the kernels update in place*, so ``env.state()`` is always current and
 assigning into a field (``state.fires[3] = ...``) edits the live device state.
 """
@@ -14,7 +15,7 @@ from typing import List, Optional
 import torch
 
 
-@dataclasses.dataclass
+@dataclasses.dataclass(eq=False)  # identity equality, content hash (below) -- like the reference's plain class
 class State:
     """Base class for the per-domain states; subclasses list their tensors as dataclass fields."""
 
@@ -99,3 +100,30 @@ class State:
     @staticmethod
     def cat(states: List['State'], *args, **kwargs) -> 'State':
         return State._combine(states, torch.cat, *args, **kwargs)
+
+    # -- per-environment access (reference state.py:180-238)
+    def unwrap(self) -> List['State']:
+        """One single-environment state per batch entry (``self[i]`` for every i)."""
+        return [self[index] for index in range(len(self))]
+
+    def __getitem__(self, indices) -> 'State':
+        shared = self.metadata.get('shared', ())
+        return type(self)(**{f.name: getattr(self, f.name) if f.name in shared else getattr(self, f.name)[indices]
+                             for f in dataclasses.fields(self)})
+
+    def to_dataframe(self):
+        """One row per environment, every field as the string of its nested list; shared fields repeated on every
+        row (reference state.py:180-191 -- the CSV logging format)."""
+        import pandas as pd
+        shared = self.metadata.get('shared', ())
+        data = {name: [str(row.tolist()) for row in getattr(self, name)] for name in self._tensor_fields()}
+        frame = pd.DataFrame(data)
+        for name in shared:
+            frame[name] = str(getattr(self, name).tolist())
+        return frame
+
+    def __hash__(self) -> int:
+        """Hash of the field contents (the reference hashes every tensor with xxhash, utils/caching.py:17-32; here the
+        raw bytes are hashed -- equal states hash equal, which is all the contract asks for)."""
+        return hash(tuple(getattr(self, f.name).detach().cpu().contiguous().numpy().tobytes()
+                          for f in dataclasses.fields(self)))

@@ -93,6 +93,11 @@ typedef struct {
 #define FRZ_WF_BURNOUT_SCALED 0x0400u
 #define FRZ_WF_LOCALIZE_PUTOUTS 0x0800u
 #define FRZ_WF_SHOW_BAD_ACTIONS 0x1000u
+/* Grids of at most 32 cells with at most 8 agents have two step kernels -- a group of eight lanes per environment, and
+ * (from 49 152 environments up) one thread per environment -- with identical results and identical random streams.
+ * These two bits force one of them whatever the batch size (tests, kernel timing). */
+#define FRZ_WF_KERNEL_TILES 0x2000u
+#define FRZ_WF_KERNEL_GROUPS 0x4000u
 
 /* WildfireConfiguration flattened once at construction (passed by value to the kernel). */
 typedef struct {

@@ -115,3 +115,60 @@ def test_full_size_philox_rollout_properties():
         assert torch.equal(raw._rewards[:, 0], -raw._rewards[:, 2])
         assert (raw.num_moves == 60).all() and not raw.terminated.any()
         raw.check_errors()
+
+
+def test_action_mapping_wrapper_returns_the_reference_mappings():
+    """wrappers/action_task.py on cybersecurity: every observation comes back with the agent's action -> task mapping
+    (all N subnetworks while the agent is present, nothing while it is away: cybersecurity.py:414-446); equal to the
+    reference's recorded mappings on a golden trajectory with presence openness."""
+    from free_range_zoo_b200.wrappers import action_mapping_wrapper_v0
+    meta, gold = G.load('cyber_c3')
+    env = action_mapping_wrapper_v0(make_env(getattr(presets, meta['preset'])(**meta.get('preset_kwargs', {})), meta['B'],
+                                             meta['max_steps'], **meta['env_kwargs']))
+    observations, _ = env.reset(seed=0)
+    agents = env.agents
+    for t in range(15):
+        for agent in agents:
+            observation, extra = observations[agent]
+            mapping = extra['agent_action_mapping'].to_padded_tensor(-100).cpu().numpy()
+            want = gold[f'action_map__{agent}'][t]
+            assert np.array_equal(mapping, want[:, :mapping.shape[1]]) and (want[:, mapping.shape[1]:] == -100).all(), (t, agent)
+        env.unwrapped.inject_uniforms(torch.from_numpy(gold['u_network'][t]), torch.from_numpy(gold['u_agent'][t]))
+        actions = torch.from_numpy(gold['actions'][t]).cuda()
+        observations, _, _, _, _ = env.step({a: actions[:, i] for i, a in enumerate(agents)})
+
+
+def test_sampled_actions_are_uniform_over_the_legal_choices():
+    """cyber_sample_kernel: chi-square of the sampled choice index over 262 144 environments, per agent and per number
+    of legal choices (attackers: N nodes + noop; defenders: N moves + noop + monitor [+ patch when not at home])."""
+    from scipy.stats import chi2
+    B = 262144
+    env = make_env(presets.cyber_c3(), B, 100, show_bad_actions=False, partially_observable=True)
+    env.reset(seed=5)
+    raw = env.unwrapped
+    for _ in range(4):
+        raw.sample_actions(11)
+        raw.step_all()
+    raw.sample_actions(12)
+    actions = raw._actions.cpu().numpy()
+    present = raw.state().presence.cpu().numpy().astype(bool)
+    location = raw.state().location.cpu().numpy()
+    n_att, N = raw._n_att, raw._n_nodes
+    for a in range(actions.shape[1]):
+        ident, k = actions[:, a, 1], actions[:, a, 0]
+        assert (ident[~present[:, a]] == -1).all()  # an absent agent can only pass
+        groups = [present[:, a]]
+        if a >= n_att:  # defenders at home cannot patch
+            home = location[:, a - n_att] == -1
+            groups = [present[:, a] & home, present[:, a] & ~home]
+        for members in groups:
+            if members.sum() < 1000:
+                continue
+            # the choice as one category: node 0 .. N-1, then the task-agnostic ids
+            category = np.where(ident[members] == 0, k[members], N - 1 - ident[members])
+            observed = np.bincount(category)
+            observed = observed[observed > 0]
+            expected = members.sum() / len(observed)
+            statistic = ((observed - expected)**2 / expected).sum()
+            assert statistic < chi2.ppf(1 - 1e-6, df=len(observed) - 1), (a, observed)
+            assert len(observed) >= N + 1

@@ -206,3 +206,33 @@ def test_seed_folding_is_deterministic():
     assert _seed_to_u64(7) == 7
     assert _seed_to_u64([1, 2, 3]) == _seed_to_u64(torch.tensor([1, 2, 3])) != _seed_to_u64([3, 2, 1])
     assert 0 <= _seed_to_u64(None) < 2**64
+
+
+def test_state_per_environment_access_and_hash():
+    """State.unwrap / __getitem__ / to_dataframe / __hash__ (reference utils/state.py:180-238)."""
+    import torch
+
+    from free_range_zoo_b200.envs.cybersecurity.env.structures.state import CybersecurityState
+    from free_range_zoo_b200.envs.rideshare.env.structures.state import RideshareState
+    from free_range_zoo_b200.envs.wildfire.env.structures.state import WildfireState
+    i32 = torch.int32
+    wildfire = WildfireState(fires=torch.arange(12, dtype=i32).view(3, 2, 2), intensity=torch.zeros(3, 2, 2, dtype=i32),
+                             fuel=torch.ones(3, 2, 2, dtype=i32), agents=torch.tensor([[0, 1], [1, 1]], dtype=i32),
+                             suppressants=torch.ones(3, 2), capacity=torch.ones(3, 2), equipment=torch.zeros(3, 2, dtype=i32))
+    singles = wildfire.unwrap()
+    assert len(wildfire) == 3 and len(singles) == 3
+    assert torch.equal(singles[2].fires, wildfire.fires[2]) and singles[2].agents is wildfire.agents  # shared field
+    frame = wildfire.to_dataframe()
+    assert list(frame.columns) == ['fires', 'intensity', 'fuel', 'suppressants', 'capacity', 'equipment', 'agents']
+    assert frame.shape == (3, 7) and frame['fires'][1] == '[[4, 5], [6, 7]]' and frame['agents'][2] == '[[0, 1], [1, 1]]'
+    assert hash(wildfire) == hash(wildfire.clone()) and hash(wildfire) != hash(wildfire[torch.tensor([0, 0, 0])])
+    assert wildfire == wildfire and wildfire != wildfire.clone()  # identity, not element-wise tensor comparison
+
+    rideshare = RideshareState(agents=torch.zeros(2, 4, 2, dtype=i32), passenger_table=torch.ones(2, 3, 11, dtype=i32),
+                               passenger_count=torch.tensor([1, 2], dtype=i32))
+    assert [int(s.passenger_count) for s in rideshare.unwrap()] == [1, 2]
+    assert rideshare.passengers.shape == (3, 11) and rideshare.passengers[:, 0].tolist() == [0, 1, 1]
+    cyber = CybersecurityState(network_state=torch.zeros(4, 3, dtype=i32), location=torch.zeros(4, 2, dtype=i32),
+                               presence=torch.ones(4, 4, dtype=torch.bool))
+    assert len(cyber.unwrap()) == 4 and cyber.to_dataframe().shape == (4, 3)
+    assert isinstance(hash(cyber), int)

@@ -207,3 +207,54 @@ def test_reset_reaches_every_driver_when_the_table_is_shorter_than_the_driver_li
     env.reset(seed=0)
     torch.cuda.synchronize()
     assert torch.equal(raw.state().agents, start) and (raw._cumulative == 0).all()
+
+
+def test_action_mapping_wrapper_returns_the_reference_mappings():
+    """wrappers/action_task.py on rideshare: every observation comes back with the driver's action -> task mapping
+    (jagged environment-local passenger indices); equal to the reference's recorded mappings on a golden trajectory."""
+    from free_range_zoo_b200.wrappers import action_mapping_wrapper_v0
+    meta, gold = G.load('rideshare_c2')
+    env = action_mapping_wrapper_v0(make_env(getattr(presets, meta['preset'])(**meta['preset_kwargs']), meta['B'],
+                                             meta['max_steps']))
+    observations, _ = env.reset(seed=0)
+    agents = env.agents
+    for t in range(12):
+        for i, agent in enumerate(agents):
+            observation, extra = observations[agent]
+            mapping = extra['agent_action_mapping'].to_padded_tensor(-100).cpu().numpy()
+            want = gold['action_map'][t][i]
+            assert np.array_equal(mapping, want[:, :mapping.shape[1]]) and (want[:, mapping.shape[1]:] == -100).all(), (t, agent)
+            assert observation['self'].shape == (meta['B'], 4)
+        actions = torch.from_numpy(gold['actions'][t]).cuda()
+        observations, _, _, _, _ = env.step({a: actions[:, i] for i, a in enumerate(agents)})
+
+
+def test_sampled_actions_are_uniform_over_the_legal_choices():
+    """rideshare_sample_kernel: a driver with n tasks picks each of its n + 1 choices (the tasks, then noop) with equal
+    probability -- chi-square over 131 072 environments in one state, and every task action carries the passenger's
+    state as its id (spaces/actions.py:10-50)."""
+    from scipy.stats import chi2
+    B = 131072
+    env = make_env(presets.rideshare_c2(), B, 100)
+    env.reset(seed=1)
+    raw = env.unwrapped
+    for _ in range(6):  # a state with several passengers, identical in every environment (wildcard schedule)
+        raw.sample_actions(3)
+        raw.step_all()
+    # the environments have diverged: test within groups of equal task count
+    raw.sample_actions(77)
+    actions, counts = raw._actions.cpu().numpy(), raw._agent_task_count.cpu().numpy()
+    checked = 0
+    for a in range(actions.shape[1]):
+        for n in np.unique(counts[:, a]):
+            picks = actions[counts[:, a] == n, a, 0]
+            if len(picks) < 20 * (n + 1):
+                continue
+            assert picks.min() >= 0 and picks.max() <= n
+            observed = np.bincount(picks, minlength=n + 1)
+            statistic = ((observed - len(picks) / (n + 1))**2 / (len(picks) / (n + 1))).sum()
+            assert statistic < chi2.ppf(1 - 1e-6, df=max(n, 1)), (a, n, observed)
+            checked += 1
+    assert checked >= 8
+    noop = actions[..., 0] == counts
+    assert (actions[..., 1][noop] == -1).all() and (actions[..., 1][~noop] >= 0).all()

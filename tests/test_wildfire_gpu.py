@@ -22,11 +22,23 @@ def make_env(config, B, max_steps, **kwargs):
                                     device=torch.device('cuda'), **kwargs)
 
 
+def tiled_kernel_serves(config) -> bool:
+    """Grids the one-thread-per-environment kernel steps (csrc/frz_wildfire_tile.cuh); others ignore step_kernel."""
+    return config.grid_height * config.grid_width <= 32 and config.agent_config.agents.shape[0] <= 8
+
+
+# 'groups': lanes per environment (every grid); 'tiles': one thread per environment (small grids, forced at any batch size)
+KERNELS = ['groups', 'tiles']
+
+
+@pytest.mark.parametrize('kernel', KERNELS)
 @pytest.mark.parametrize('name', G.fixtures('wildfire'))
-def test_matches_reference_trajectory(name):
+def test_matches_reference_trajectory(name, kernel):
     meta, gold = G.load(name)
-    env = make_env(getattr(presets, meta['preset'])(**meta.get('preset_kwargs', {})), meta['B'], meta['max_steps'],
-                   **meta['env_kwargs'])
+    config = getattr(presets, meta['preset'])(**meta.get('preset_kwargs', {}))
+    if kernel == 'tiles' and not tiled_kernel_serves(config):
+        pytest.skip('grid too large for the tiled kernel')
+    env = make_env(config, meta['B'], meta['max_steps'], step_kernel=kernel, **meta['env_kwargs'])
     env.reset(seed=0)
     G.compare(wildfire_outputs(env), gold, 0, context=name)
     agents = env.agents
@@ -46,6 +58,12 @@ def test_matches_reference_trajectory(name):
     ('wildfire_profile', 1000, 15, {}),
     ('wildfire_large', 1, 10, {}),  # a single environment
     ('wildfire_3x3', 3, 12, {}),  # fewer environments than one warp holds
+    # small grids (both kernels): all four cells-per-lane classes of the 8-lane layout, 8 agents, bad actions shown
+    (('wildfire_large', dict(height=2, width=4, num_agents=3, seed=41)), 333, 20, {}),
+    (('wildfire_large', dict(height=4, width=5, num_agents=4, seed=32)), 450, 20, dict(show_bad_actions=True)),
+    (('wildfire_large', dict(height=5, width=6, num_agents=6, seed=21)), 300, 20, {}),
+    (('wildfire_large', dict(height=4, width=8, num_agents=8, seed=33)), 257, 20, {}),
+    (('wildfire_large', dict(height=1, width=32, num_agents=5, seed=42)), 200, 15, {}),  # one row of 32 cells
     # the kernel's other geometries: 2 and 8 cells per lane, rows of >= 32 cells (word-crossing neighbours), 20 agents
     (('wildfire_large', dict(height=7, width=8, num_agents=5, seed=5)), 700, 20, {}),
     (('wildfire_large', dict(height=12, width=16, num_agents=12, seed=6)), 300, 20, {}),
@@ -56,12 +74,15 @@ def test_matches_reference_trajectory(name):
     (('wildfire_large', dict(height=5, width=9, num_agents=16, seed=11)), 300, 20, {}),  # half-warp groups, 16 agents
     (('wildfire_large', dict(height=16, width=16, num_agents=32, seed=12)), 100, 12, {}),  # the engine's size limits
 ])
-def test_matches_oracle_on_random_rollouts(preset, B, steps, kwargs):
+@pytest.mark.parametrize('kernel', KERNELS)
+def test_matches_oracle_on_random_rollouts(preset, B, steps, kwargs, kernel):
     from oracle.wildfire import WildfireOracle
     config = getattr(presets, preset)() if isinstance(preset, str) else getattr(presets, preset[0])(**preset[1])
+    if kernel == 'tiles' and not tiled_kernel_serves(config):
+        pytest.skip('grid too large for the tiled kernel')
     oracle = WildfireOracle(config, B, steps, **kwargs)
     oracle.reset()
-    env = make_env(config, B, steps, **kwargs)
+    env = make_env(config, B, steps, step_kernel=kernel, **kwargs)
     env.reset(seed=1)
     rng = np.random.default_rng(7)
     H, W, A = oracle.H, oracle.W, oracle.A
@@ -247,3 +268,57 @@ def test_burnt_out_and_live_environments_share_a_warp():
         want = {key: value[None] for key, value in oracle.outputs().items()}
         G.compare({k_: v for k_, v in wildfire_outputs(env).items() if k_ in ('fires', 'intensity', 'fuel', 'rewards', 'terminated', 'env_task_count', 'agent_task_count')},
                   want, 0, context=f'mixed t={t}')
+
+
+def test_sampled_actions_are_uniform_over_the_legal_choices():
+    """wildfire_sample_kernel: an agent with n reachable fires picks each of its n + 1 choices (the fires, then the
+    task-agnostic noop / refill slot) with equal probability -- chi-square over 262 144 environments that share one
+    state (same initial grid, no step taken), per agent."""
+    from scipy.stats import chi2
+    B = 262144
+    env = make_env(presets.wildfire_large(), B, 100)
+    env.reset(seed=9)
+    raw = env.unwrapped
+    raw.sample_actions(31)
+    actions, counts = raw._actions.cpu().numpy(), raw._agent_task_count.cpu().numpy()
+    assert (counts == counts[0]).all()  # identical environments
+    for a, n in enumerate(counts[0]):
+        picks = actions[:, a, 0]
+        assert picks.min() >= 0 and picks.max() <= n
+        observed = np.bincount(picks, minlength=n + 1)
+        statistic = ((observed - B / (n + 1))**2 / (B / (n + 1))).sum()
+        assert statistic < chi2.ppf(1 - 1e-6, df=max(int(n), 1)), (a, n, observed)
+        assert (actions[picks == n, a, 1] == -1).all() and (actions[picks < n, a, 1] == 0).all()
+
+
+@pytest.mark.parametrize('spec,B,kwargs', [
+    ('wildfire_3x3', 50000, {}),  # more than one round of tiles per CTA, partial last tile
+    (dict(height=5, width=6, num_agents=6, seed=21), 3000, dict(show_bad_actions=True)),
+    (dict(height=2, width=3, num_agents=3, seed=31), 1111, {}),
+])
+def test_tiled_and_group_kernels_draw_the_same_trajectories(spec, B, kwargs):
+    """In production (Philox) mode the two step kernels of a small grid are interchangeable: same random streams, so
+    the same trajectory bit for bit -- the batch size (and with it how a batch is sharded over GPUs) only selects
+    which one runs."""
+    config = presets.wildfire_3x3() if spec == 'wildfire_3x3' else presets.wildfire_large(**spec)
+    envs = {kernel: make_env(config, B, 25, step_kernel=kernel, **kwargs) for kernel in KERNELS}
+    for env in envs.values():
+        env.reset(seed=77)
+    groups, tiles = envs['groups'].unwrapped, envs['tiles'].unwrapped
+    names = ('fires', 'intensity', 'fuel', 'suppressants', 'capacity', 'equipment')
+    for t in range(30):  # runs past max_steps: the early-out of a finished batch included
+        groups.sample_actions(13)
+        tiles.sample_actions(13)
+        assert torch.equal(groups._actions, tiles._actions), t
+        groups.step_all()
+        tiles.step_all()
+        for name in names:
+            assert torch.equal(getattr(groups.state(), name), getattr(tiles.state(), name)), (name, t)
+        for name in ('_rewards', '_cumulative', '_task_obs', '_self_obs', '_agent_task_count', '_action_mask', '_burnouts',
+                     '_putouts', 'num_moves', 'num_burnouts', 'environment_task_count', '_terminated', '_truncated'):
+            assert torch.equal(getattr(groups, name), getattr(tiles, name)), (name, t)
+        mine, theirs = groups.control_block(), tiles.control_block()
+        for field in ('seed', 'step', 'alive', 'agents_with_tasks', 'error_word'):
+            assert mine[field] == theirs[field], (field, t)
+    groups.check_errors()
+    tiles.check_errors()
