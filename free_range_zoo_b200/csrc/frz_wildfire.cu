@@ -1222,7 +1222,8 @@ int dispatch(const FrzWildfireParams* p, const FrzWildfireBuffers* io, int B, in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // small grids: one thread per environment once the batch fills the GPU with tiles (same random streams either way)
   if (small_grid(*p) && g.group == 8 &&
-      ((p->flags & FRZ_WF_KERNEL_TILES) || (!(p->flags & FRZ_WF_KERNEL_GROUPS) && B >= kSmallTileMinimumBatch))) {
+      ((p->flags & FRZ_WF_KERNEL_TILES) ||
+       (!(p->flags & FRZ_WF_KERNEL_GROUPS) && tiny_grid(*p) && B >= kSmallTileMinimumBatch))) {
     return p->num_agents <= 4 ? launch_tiles_mode<4>(*p, *io, B, mode, g, s) : launch_tiles_mode<8>(*p, *io, B, mode, g, s);
   }
   if (g.group == 8) {

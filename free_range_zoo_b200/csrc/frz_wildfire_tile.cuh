@@ -9,6 +9,8 @@
 // the warp's mbarrier), a thread then reads and writes its environment's rows in shared memory (row stride = row
 // size: odd strides such as 9 cells are conflict-free).  The variable-length outputs (live task-observation rows, the
 // action-mask words that can differ from their padding) are stored directly, in whole 16-byte / 4-byte pieces.
+// (Measured alternative, not kept: staging only the three cell planes and letting every thread read / write its
+// per-agent rows directly -- 6 KB of shared memory per tile instead of 12 -- was 27 % slower on the 3x3 grid.)
 //
 // Randomness: the SAME Philox calls and word assignment as the group kernel uses for this grid (a host-built table
 // says which word of which call feeds which cell / agent event), so a trajectory does not depend on which of the two
@@ -521,8 +523,11 @@ wildfire_tile_kernel(const __grid_constant__ FrzWildfireParams p, const __grid_c
                 skip ? kPublishNothing : (MODE == kStep ? kPublishStep : kPublishRefresh));
 }
 
-// environments from which the tiled kernel steps a small grid (below, a tile per warp leaves most of the GPU idle and
-// the group kernel's eight lanes per environment finish sooner)
+// When the dispatcher picks the tiled kernel by itself: tiny grids (measured on B200: 3x3 / 3 agents at 524 288 envs
+// 105 us against 188 us with groups of eight lanes; 5x6 / 6 agents at 262 144 envs 278 us against 159 us -- the serial
+// walk over cells and agents grows with the grid while the group kernel's lanes fill up) from 49 152 environments up
+// (below, a tile per warp leaves most of the GPU idle).  FRZ_WF_KERNEL_TILES forces it for any grid it can step.
 constexpr int kSmallTileMinimumBatch = 49152;
 
 inline bool small_grid(const FrzWildfireParams& p) { return p.height * p.width <= kSmallMaxCells && p.num_agents <= 8; }
+inline bool tiny_grid(const FrzWildfireParams& p) { return p.height * p.width <= 16 && p.num_agents <= 4; }

@@ -94,8 +94,9 @@ typedef struct {
 #define FRZ_WF_LOCALIZE_PUTOUTS 0x0800u
 #define FRZ_WF_SHOW_BAD_ACTIONS 0x1000u
 /* Grids of at most 32 cells with at most 8 agents have two step kernels -- a group of eight lanes per environment, and
- * (from 49 152 environments up) one thread per environment -- with identical results and identical random streams.
- * These two bits force one of them whatever the batch size (tests, kernel timing). */
+ * one thread per environment -- with identical results and identical random streams.  The second one is chosen for
+ * tiny grids (at most 16 cells, at most 4 agents) from 49 152 environments up; these two bits force one of them
+ * whatever the grid and batch size (tests, kernel timing). */
 #define FRZ_WF_KERNEL_TILES 0x2000u
 #define FRZ_WF_KERNEL_GROUPS 0x4000u
 
