@@ -206,6 +206,13 @@ __device__ __forceinline__ void mbarrier_init(uint32_t barrier, uint32_t arrival
 __device__ __forceinline__ void mbarrier_expect_bytes(uint32_t barrier, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" : : "r"(barrier), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbarrier_arrive(uint32_t barrier) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" : : "r"(barrier) : "memory");
+}
+// barrier among a subset of the CTA's warps (named barrier `id`, `threads` = participating threads, a multiple of 32)
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" : : "r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void mbarrier_wait(uint32_t barrier, uint32_t parity) {
   asm volatile(
       "{\n"

@@ -340,16 +340,21 @@ __device__ __forceinline__ void tile_copy(uint8_t* dst, const uint8_t* src, int 
   for (int i = threadIdx.x; i < bytes; i += kCyThreads) dst[i] = src[i];
 }
 
-// Persistent: a CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...  With two tile buffers (`buffers` = 2,
-// whenever two tiles fit) the loads of the CTA's next tile are issued before the current one is stepped, and the stores
-// of the previous one drain meanwhile -- load, step and store of consecutive tiles overlap inside the CTA instead of
-// only across CTAs, and the launch epilogue (a handful of same-address atomics per CTA) runs once per ~30 tiles.
+// Persistent and warp-specialised: a CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...; its first kCyThreads
+// threads step one environment each, the extra warp's first thread does nothing but move tiles.  With two tile buffers
+// (whenever two tiles fit and the batch is large) the copy thread requests tile i, then stores tile i-1 as soon as the
+// stepping threads are done with it, then waits until those stores have left shared memory and requests tile i+1 into
+// that buffer -- so the loads of one tile, the stepping of the next and the write-back of the previous one overlap
+// inside the CTA, and no stepping thread ever waits for a store to drain.  Hand-offs: full[b] (mbarrier armed with the
+// tile's byte count, completed by the bulk loads) and done[b] (mbarrier the kCyThreads stepping threads arrive on).
+constexpr int kCyBlock = kCyThreads + 32;
+
 template <bool INJECTED, int MAXN, int MAXATT, int MAXDEF>
-__global__ void __launch_bounds__(kCyThreads)
+__global__ void __launch_bounds__(kCyBlock, 4)
 cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_constant__ FrzCyberBuffers io, const int B,
                         const int buffers) {
   extern __shared__ __align__(128) uint8_t tiles_storage[];
-  __shared__ __align__(8) uint64_t barrier_storage[2];
+  __shared__ __align__(8) uint64_t barrier_storage[4];  // full[0], full[1], done[0], done[1]
   const int N = p.num_nodes, n_att = p.num_attackers, n_def = p.num_defenders, n = n_att + n_def;
   FrzControl* control = io.control;
   const uint64_t step = control->step;
@@ -364,100 +369,42 @@ cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_c
     const bool inject_agent = INJECTED && io.agent_uniforms != nullptr;
     const int tile_count = (B + kCyThreads - 1) / kCyThreads;
     const uint32_t storage_s = shared_address(tiles_storage);
+    const auto full_barrier = [&](int b) { return shared_address(&barrier_storage[b]); };
+    const auto done_barrier = [&](int b) { return shared_address(&barrier_storage[2 + b]); };
     if (threadIdx.x == 0) {
-      mbarrier_init(shared_address(&barrier_storage[0]), 1);
-      mbarrier_init(shared_address(&barrier_storage[1]), 1);
+      mbarrier_init(full_barrier(0), 1);
+      mbarrier_init(full_barrier(1), 1);
+      mbarrier_init(done_barrier(0), kCyThreads);
+      mbarrier_init(done_barrier(1), kCyThreads);
     }
     __syncthreads();
-
-    // the bulk loads of one full tile into buffer `b` (thread 0 only)
-    const auto request = [&](int tile_index, int b) {
-      const size_t e = size_t(tile_index) * kCyThreads;
-      const uint32_t T = kCyThreads, tile_s = storage_s + uint32_t(b) * uint32_t(L.total);
-      const uint32_t barrier = shared_address(&barrier_storage[b]);
-      uint32_t bytes = T * (N * 4 + n_def * 4 + n + n * 4 + 4 + n * 8);
-      if (inject_network) bytes += T * N * 4;
-      if (inject_agent) bytes += T * n * 4;
-      mbarrier_expect_bytes(barrier, bytes);
-      bulk_load(tile_s + L.state, io.network_state + e * N, T * N * 4, barrier);
-      bulk_load(tile_s + L.location, io.location + e * n_def, T * n_def * 4, barrier);
-      bulk_load(tile_s + L.presence, io.presence + e * n, T * n, barrier);
-      bulk_load(tile_s + L.cumulative, io.cumulative_rewards + e * n, T * n * 4, barrier);
-      bulk_load(tile_s + L.num_moves, io.num_moves + e, T * 4, barrier);
-      bulk_load(tile_s + L.actions, io.actions + e * n * 2, T * n * 8, barrier);
-      if (inject_network) bulk_load(tile_s + L.network_uniforms, io.network_uniforms + e * N, T * N * 4, barrier);
-      if (inject_agent) bulk_load(tile_s + L.agent_uniforms, io.agent_uniforms + e * n, T * n * 4, barrier);
-    };
     const auto is_full = [&](int tile_index) { return (tile_index + 1) * kCyThreads <= B; };
 
-    uint32_t parity = 0u;  // bit b = phase parity of buffer b's barrier
-    int b = 0;
-    if (threadIdx.x == 0 && int(blockIdx.x) < tile_count && is_full(blockIdx.x)) request(blockIdx.x, 0);
-    for (int tile_index = blockIdx.x; tile_index < tile_count; tile_index += gridDim.x) {
-      const int first = tile_index * kCyThreads;
-      const int count = min(kCyThreads, B - first);
-      const size_t e = size_t(first);
-      const bool full = count == kCyThreads;
-      uint8_t* const tile = tiles_storage + size_t(b) * size_t(L.total);
-      const uint32_t tile_s = storage_s + uint32_t(b) * uint32_t(L.total);
-      const int next = tile_index + gridDim.x;
-
-      // ------------------------------------------------------------------ stage in
-      if (buffers == 2) {
-        // the other buffer is free once the stores of the tile before this one have read it: fetch the next tile into it
-        if (threadIdx.x == 0 && next < tile_count && is_full(next)) {
-          bulk_wait_read();
-          request(next, b ^ 1);
-        }
-      }
-      if (full) {
-        mbarrier_wait(shared_address(&barrier_storage[b]), (parity >> b) & 1u);
-        parity ^= 1u << b;
-      } else {
-        if (threadIdx.x == 0) bulk_wait_read();  // (a partial tile is the last one: nothing else is in flight)
-        __syncthreads();
-        tile_copy(tile + L.state, reinterpret_cast<const uint8_t*>(io.network_state + e * N), count * N * 4);
-        tile_copy(tile + L.location, reinterpret_cast<const uint8_t*>(io.location + e * n_def), count * n_def * 4);
-        tile_copy(tile + L.presence, io.presence + e * n, count * n);
-        tile_copy(tile + L.cumulative, reinterpret_cast<const uint8_t*>(io.cumulative_rewards + e * n), count * n * 4);
-        tile_copy(tile + L.num_moves, reinterpret_cast<const uint8_t*>(io.num_moves + e), count * 4);
-        tile_copy(tile + L.actions, reinterpret_cast<const uint8_t*>(io.actions + e * n * 2), count * n * 8);
-        if (inject_network)
-          tile_copy(tile + L.network_uniforms, reinterpret_cast<const uint8_t*>(io.network_uniforms + e * N), count * N * 4);
-        if (inject_agent)
-          tile_copy(tile + L.agent_uniforms, reinterpret_cast<const uint8_t*>(io.agent_uniforms + e * n), count * n * 4);
-        __syncthreads();
-      }
-
-      // ------------------------------------------------------------------ step, entirely in shared memory
-      const int t = threadIdx.x;
-      if (t < count) {
-        CyberRows r;
-        r.state = reinterpret_cast<int32_t*>(tile + L.state) + t * N;
-        r.location = reinterpret_cast<int32_t*>(tile + L.location) + t * n_def;
-        r.presence = tile + L.presence + t * n;
-        r.actions = reinterpret_cast<const int2*>(tile + L.actions) + t * n;
-        r.rewards = reinterpret_cast<float*>(tile + L.rewards) + t * n;
-        r.cumulative = reinterpret_cast<float*>(tile + L.cumulative) + t * n;
-        r.num_moves = reinterpret_cast<int32_t*>(tile + L.num_moves) + t;
-        r.truncated = tile + L.truncated + t;
-        r.env_task_count = reinterpret_cast<int32_t*>(tile + L.env_task_count) + t;
-        r.agent_task_count = reinterpret_cast<int32_t*>(tile + L.agent_task_count) + t * n;
-        r.attacker_self = reinterpret_cast<float2*>(tile + L.attacker_self) + t * n_att;
-        r.defender_self = reinterpret_cast<float*>(tile + L.defender_self) + t * n_def * 3;
-        r.task_obs = reinterpret_cast<int2*>(tile + L.task_obs) + t * N;
-        r.monitored = tile + L.monitored + t * n_def;
-        r.network_uniforms = inject_network ? reinterpret_cast<const float*>(tile + L.network_uniforms) + t * N : nullptr;
-        r.agent_uniforms = inject_agent ? reinterpret_cast<const float*>(tile + L.agent_uniforms) + t * n : nullptr;
-        cyber_env_step<kCyStep, MAXN, MAXATT, MAXDEF>(p, r, io.score_lut, philox, step, p.env_offset + first + t, alive_bits, faults);
-      }
-
-      // ------------------------------------------------------------------ stage out
-      if (full) {
-        fence_async_shared();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          const uint32_t T = kCyThreads;
+    if (threadIdx.x >= kCyThreads) {
+      // ================================================================== the copy thread
+      if (threadIdx.x == kCyThreads) {
+        const uint32_t T = kCyThreads;
+        // the bulk loads of one full tile into buffer b
+        const auto request = [&](int tile_index, int b) {
+          const size_t e = size_t(tile_index) * kCyThreads;
+          const uint32_t tile_s = storage_s + uint32_t(b) * uint32_t(L.total), barrier = full_barrier(b);
+          uint32_t bytes = T * (N * 4 + n_def * 4 + n + n * 4 + 4 + n * 8);
+          if (inject_network) bytes += T * N * 4;
+          if (inject_agent) bytes += T * n * 4;
+          mbarrier_expect_bytes(barrier, bytes);
+          bulk_load(tile_s + L.state, io.network_state + e * N, T * N * 4, barrier);
+          bulk_load(tile_s + L.location, io.location + e * n_def, T * n_def * 4, barrier);
+          bulk_load(tile_s + L.presence, io.presence + e * n, T * n, barrier);
+          bulk_load(tile_s + L.cumulative, io.cumulative_rewards + e * n, T * n * 4, barrier);
+          bulk_load(tile_s + L.num_moves, io.num_moves + e, T * 4, barrier);
+          bulk_load(tile_s + L.actions, io.actions + e * n * 2, T * n * 8, barrier);
+          if (inject_network) bulk_load(tile_s + L.network_uniforms, io.network_uniforms + e * N, T * N * 4, barrier);
+          if (inject_agent) bulk_load(tile_s + L.agent_uniforms, io.agent_uniforms + e * n, T * n * 4, barrier);
+        };
+        // the bulk stores of one stepped full tile out of buffer b (one bulk group)
+        const auto write_back = [&](int tile_index, int b) {
+          const size_t e = size_t(tile_index) * kCyThreads;
+          const uint32_t tile_s = storage_s + uint32_t(b) * uint32_t(L.total);
           bulk_store(io.network_state + e * N, tile_s + L.state, T * N * 4);
           bulk_store(io.location + e * n_def, tile_s + L.location, T * n_def * 4);
           bulk_store(io.presence + e * n, tile_s + L.presence, T * n);
@@ -472,30 +419,102 @@ cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_c
           bulk_store(io.task_obs + e * N * 2, tile_s + L.task_obs, T * N * 8);
           bulk_store(io.monitored + e * n_def, tile_s + L.monitored, T * n_def);
           bulk_commit();
-          if (buffers == 1) {  // one buffer: it is reloaded right away
-            bulk_wait_read();
-            if (next < tile_count && is_full(next)) request(next, 0);
-          }
+        };
+        uint32_t done_parity = 0u;  // bit b = phase parity of done[b]
+        const auto finish_tile = [&](int tile_index, int b) {  // once its environments are stepped, write the tile back
+          if (!is_full(tile_index)) return;  // (the stepping threads store a partial tile themselves)
+          mbarrier_wait(done_barrier(b), (done_parity >> b) & 1u);
+          done_parity ^= 1u << b;
+          write_back(tile_index, b);
+        };
+        int previous = -1, previous_buffer = 0, iteration = 0;
+        for (int tile_index = blockIdx.x; tile_index < tile_count; tile_index += gridDim.x, ++iteration) {
+          const int b = buffers == 2 ? (iteration & 1) : 0;
+          if (buffers == 1 && previous >= 0) finish_tile(previous, previous_buffer);
+          bulk_wait_read();  // buffer b is free: the stores that read it last have left shared memory
+          if (is_full(tile_index)) request(tile_index, b);
+          else mbarrier_arrive(full_barrier(b));  // partial tile: the stepping threads copy it themselves
+          if (buffers == 2 && previous >= 0) finish_tile(previous, previous_buffer);
+          previous = tile_index;
+          previous_buffer = b;
         }
-      } else {
-        __syncthreads();
-        tile_copy(reinterpret_cast<uint8_t*>(io.network_state + e * N), tile + L.state, count * N * 4);
-        tile_copy(reinterpret_cast<uint8_t*>(io.location + e * n_def), tile + L.location, count * n_def * 4);
-        tile_copy(io.presence + e * n, tile + L.presence, count * n);
-        tile_copy(reinterpret_cast<uint8_t*>(io.cumulative_rewards + e * n), tile + L.cumulative, count * n * 4);
-        tile_copy(reinterpret_cast<uint8_t*>(io.num_moves + e), tile + L.num_moves, count * 4);
-        tile_copy(reinterpret_cast<uint8_t*>(io.rewards + e * n), tile + L.rewards, count * n * 4);
-        tile_copy(io.truncated + e, tile + L.truncated, count);
-        tile_copy(reinterpret_cast<uint8_t*>(io.env_task_count + e), tile + L.env_task_count, count * 4);
-        tile_copy(reinterpret_cast<uint8_t*>(io.agent_task_count + e * n), tile + L.agent_task_count, count * n * 4);
-        tile_copy(reinterpret_cast<uint8_t*>(io.attacker_self + e * n_att * 2), tile + L.attacker_self, count * n_att * 8);
-        tile_copy(reinterpret_cast<uint8_t*>(io.defender_self + e * n_def * 3), tile + L.defender_self, count * n_def * 12);
-        tile_copy(reinterpret_cast<uint8_t*>(io.task_obs + e * N * 2), tile + L.task_obs, count * N * 8);
-        tile_copy(io.monitored + e * n_def, tile + L.monitored, count * n_def);
+        if (previous >= 0) finish_tile(previous, previous_buffer);
+        bulk_wait_read();  // the last stores have left shared memory before the CTA exits
       }
-      if (buffers == 2) b ^= 1;
+    } else {
+      // ================================================================== the stepping threads
+      uint32_t full_parity = 0u;  // bit b = phase parity of full[b]
+      int iteration = 0;
+      for (int tile_index = blockIdx.x; tile_index < tile_count; tile_index += gridDim.x, ++iteration) {
+        const int b = buffers == 2 ? (iteration & 1) : 0;
+        const int first = tile_index * kCyThreads;
+        const int count = min(kCyThreads, B - first);
+        const size_t e = size_t(first);
+        const bool full = count == kCyThreads;
+        uint8_t* const tile = tiles_storage + size_t(b) * size_t(L.total);
+
+        // ------------------------------------------------------------------ the tile has arrived (or the buffer is free)
+        mbarrier_wait(full_barrier(b), (full_parity >> b) & 1u);
+        full_parity ^= 1u << b;
+        if (!full) {
+          tile_copy(tile + L.state, reinterpret_cast<const uint8_t*>(io.network_state + e * N), count * N * 4);
+          tile_copy(tile + L.location, reinterpret_cast<const uint8_t*>(io.location + e * n_def), count * n_def * 4);
+          tile_copy(tile + L.presence, io.presence + e * n, count * n);
+          tile_copy(tile + L.cumulative, reinterpret_cast<const uint8_t*>(io.cumulative_rewards + e * n), count * n * 4);
+          tile_copy(tile + L.num_moves, reinterpret_cast<const uint8_t*>(io.num_moves + e), count * 4);
+          tile_copy(tile + L.actions, reinterpret_cast<const uint8_t*>(io.actions + e * n * 2), count * n * 8);
+          if (inject_network)
+            tile_copy(tile + L.network_uniforms, reinterpret_cast<const uint8_t*>(io.network_uniforms + e * N), count * N * 4);
+          if (inject_agent)
+            tile_copy(tile + L.agent_uniforms, reinterpret_cast<const uint8_t*>(io.agent_uniforms + e * n), count * n * 4);
+          named_barrier_sync(1, kCyThreads);
+        }
+
+        // ------------------------------------------------------------------ step, entirely in shared memory
+        const int t = threadIdx.x;
+        if (t < count) {
+          CyberRows r;
+          r.state = reinterpret_cast<int32_t*>(tile + L.state) + t * N;
+          r.location = reinterpret_cast<int32_t*>(tile + L.location) + t * n_def;
+          r.presence = tile + L.presence + t * n;
+          r.actions = reinterpret_cast<const int2*>(tile + L.actions) + t * n;
+          r.rewards = reinterpret_cast<float*>(tile + L.rewards) + t * n;
+          r.cumulative = reinterpret_cast<float*>(tile + L.cumulative) + t * n;
+          r.num_moves = reinterpret_cast<int32_t*>(tile + L.num_moves) + t;
+          r.truncated = tile + L.truncated + t;
+          r.env_task_count = reinterpret_cast<int32_t*>(tile + L.env_task_count) + t;
+          r.agent_task_count = reinterpret_cast<int32_t*>(tile + L.agent_task_count) + t * n;
+          r.attacker_self = reinterpret_cast<float2*>(tile + L.attacker_self) + t * n_att;
+          r.defender_self = reinterpret_cast<float*>(tile + L.defender_self) + t * n_def * 3;
+          r.task_obs = reinterpret_cast<int2*>(tile + L.task_obs) + t * N;
+          r.monitored = tile + L.monitored + t * n_def;
+          r.network_uniforms = inject_network ? reinterpret_cast<const float*>(tile + L.network_uniforms) + t * N : nullptr;
+          r.agent_uniforms = inject_agent ? reinterpret_cast<const float*>(tile + L.agent_uniforms) + t * n : nullptr;
+          cyber_env_step<kCyStep, MAXN, MAXATT, MAXDEF>(p, r, io.score_lut, philox, step, p.env_offset + first + t, alive_bits, faults);
+        }
+
+        // ------------------------------------------------------------------ hand the tile to the copy thread
+        if (full) {
+          fence_async_shared();  // this thread's writes become visible to the bulk stores
+          mbarrier_arrive(done_barrier(b));
+        } else {
+          named_barrier_sync(1, kCyThreads);
+          tile_copy(reinterpret_cast<uint8_t*>(io.network_state + e * N), tile + L.state, count * N * 4);
+          tile_copy(reinterpret_cast<uint8_t*>(io.location + e * n_def), tile + L.location, count * n_def * 4);
+          tile_copy(io.presence + e * n, tile + L.presence, count * n);
+          tile_copy(reinterpret_cast<uint8_t*>(io.cumulative_rewards + e * n), tile + L.cumulative, count * n * 4);
+          tile_copy(reinterpret_cast<uint8_t*>(io.num_moves + e), tile + L.num_moves, count * 4);
+          tile_copy(reinterpret_cast<uint8_t*>(io.rewards + e * n), tile + L.rewards, count * n * 4);
+          tile_copy(io.truncated + e, tile + L.truncated, count);
+          tile_copy(reinterpret_cast<uint8_t*>(io.env_task_count + e), tile + L.env_task_count, count * 4);
+          tile_copy(reinterpret_cast<uint8_t*>(io.agent_task_count + e * n), tile + L.agent_task_count, count * n * 4);
+          tile_copy(reinterpret_cast<uint8_t*>(io.attacker_self + e * n_att * 2), tile + L.attacker_self, count * n_att * 8);
+          tile_copy(reinterpret_cast<uint8_t*>(io.defender_self + e * n_def * 3), tile + L.defender_self, count * n_def * 12);
+          tile_copy(reinterpret_cast<uint8_t*>(io.task_obs + e * N * 2), tile + L.task_obs, count * N * 8);
+          tile_copy(io.monitored + e * n_def, tile + L.monitored, count * n_def);
+        }
+      }
     }
-    if (threadIdx.x == 0) bulk_wait_read();  // the last stores have left shared memory before the CTA exits
   }
   finish_launch(control, alive_bits, faults, 0u, skip ? kPublishNothing : kPublishStep);
 }
@@ -598,9 +617,9 @@ int cyber_launch(const FrzCyberParams* p, const FrzCyberBuffers* io, int B, int 
         return check_launch("cyber tile shared memory");
       cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       int ctas_per_sm = 0;  // (not cached: the same instantiation runs with one or two buffers)
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kCyThreads, size_t(smem));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kCyBlock, size_t(smem));
       const int grid = persistent_grid(tile_count, ctas_per_sm < 1 ? 1 : ctas_per_sm);
-      kernel<<<grid, kCyThreads, smem, s>>>(*p, *io, B, buffers);
+      kernel<<<grid, kCyBlock, smem, s>>>(*p, *io, B, buffers);
       return check_launch("cyber_step_tiled_kernel");
     }
   }
