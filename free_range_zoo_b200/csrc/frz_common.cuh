@@ -234,6 +234,11 @@ __device__ __forceinline__ void bulk_store(void* global_dst, uint32_t shared_src
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" : : : "memory"); }
 // wait until the committed bulk stores have finished READING shared memory (it may then be reused / the CTA may exit)
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" : : : "memory"); }
+// ... until at most `pending` of the most recently committed bulk-store groups are still reading shared memory
+template <int pending>
+__device__ __forceinline__ void bulk_wait_read_all_but() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" : : "n"(pending) : "memory");
+}
 // make generic-proxy writes to shared memory visible to the async proxy before a bulk store reads them
 __device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" : : : "memory"); }
 

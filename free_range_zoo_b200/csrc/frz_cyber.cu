@@ -13,6 +13,8 @@
 // with a uniform draw.  Because few agents act on a node, the score takes at most 2^(Att+D) distinct values: they are
 // tabulated on the host with the reference's own torch.tanh and indexed here by the set of agents acting on the node,
 // so the threshold compare is bit-exact.
+#include <cstdlib>
+
 #include "frz_common.cuh"
 #include "frz_host.cuh"
 
@@ -341,20 +343,21 @@ __device__ __forceinline__ void tile_copy(uint8_t* dst, const uint8_t* src, int 
 }
 
 // Persistent and warp-specialised: a CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...; its first kCyThreads
-// threads step one environment each, the extra warp's first thread does nothing but move tiles.  With two tile buffers
-// (whenever two tiles fit and the batch is large) the copy thread requests tile i, then stores tile i-1 as soon as the
-// stepping threads are done with it, then waits until those stores have left shared memory and requests tile i+1 into
-// that buffer -- so the loads of one tile, the stepping of the next and the write-back of the previous one overlap
-// inside the CTA, and no stepping thread ever waits for a store to drain.  Hand-offs: full[b] (mbarrier armed with the
+// threads step one environment each, the extra warp's first thread does nothing but move tiles.  With two or three tile
+// buffers (as many as fit, when the batch is large) the copy thread requests tile i, then stores tile i-1 as soon as the
+// stepping threads are done with it, then waits until the stores that last read the next buffer have left shared memory
+// and requests tile i+1 into it -- so the loads of one tile, the stepping of the next and the write-back of the
+// previous ones overlap inside the CTA, and no stepping thread ever waits for a store to drain.  Hand-offs: full[b] (mbarrier armed with the
 // tile's byte count, completed by the bulk loads) and done[b] (mbarrier the kCyThreads stepping threads arrive on).
 constexpr int kCyBlock = kCyThreads + 32;
+constexpr int kCyMaxBuffers = 3;
 
 template <bool INJECTED, int MAXN, int MAXATT, int MAXDEF>
 __global__ void __launch_bounds__(kCyBlock, 4)
 cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_constant__ FrzCyberBuffers io, const int B,
                         const int buffers) {
   extern __shared__ __align__(128) uint8_t tiles_storage[];
-  __shared__ __align__(8) uint64_t barrier_storage[4];  // full[0], full[1], done[0], done[1]
+  __shared__ __align__(8) uint64_t barrier_storage[2 * kCyMaxBuffers];  // full[b], then done[b]
   const int N = p.num_nodes, n_att = p.num_attackers, n_def = p.num_defenders, n = n_att + n_def;
   FrzControl* control = io.control;
   const uint64_t step = control->step;
@@ -370,12 +373,12 @@ cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_c
     const int tile_count = (B + kCyThreads - 1) / kCyThreads;
     const uint32_t storage_s = shared_address(tiles_storage);
     const auto full_barrier = [&](int b) { return shared_address(&barrier_storage[b]); };
-    const auto done_barrier = [&](int b) { return shared_address(&barrier_storage[2 + b]); };
+    const auto done_barrier = [&](int b) { return shared_address(&barrier_storage[kCyMaxBuffers + b]); };
     if (threadIdx.x == 0) {
-      mbarrier_init(full_barrier(0), 1);
-      mbarrier_init(full_barrier(1), 1);
-      mbarrier_init(done_barrier(0), kCyThreads);
-      mbarrier_init(done_barrier(1), kCyThreads);
+      for (int b = 0; b < kCyMaxBuffers; ++b) {
+        mbarrier_init(full_barrier(b), 1);
+        mbarrier_init(done_barrier(b), kCyThreads);
+      }
     }
     __syncthreads();
     const auto is_full = [&](int tile_index) { return (tile_index + 1) * kCyThreads <= B; };
@@ -429,12 +432,15 @@ cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_c
         };
         int previous = -1, previous_buffer = 0, iteration = 0;
         for (int tile_index = blockIdx.x; tile_index < tile_count; tile_index += gridDim.x, ++iteration) {
-          const int b = buffers == 2 ? (iteration & 1) : 0;
+          const int b = iteration % buffers;
           if (buffers == 1 && previous >= 0) finish_tile(previous, previous_buffer);
-          bulk_wait_read();  // buffer b is free: the stores that read it last have left shared memory
+          // buffer b is free once the stores that read it last (tile `iteration - buffers`) have left shared memory:
+          // all but the `buffers - 2` groups committed after them
+          if (buffers == 3) bulk_wait_read_all_but<1>();
+          else bulk_wait_read();
           if (is_full(tile_index)) request(tile_index, b);
           else mbarrier_arrive(full_barrier(b));  // partial tile: the stepping threads copy it themselves
-          if (buffers == 2 && previous >= 0) finish_tile(previous, previous_buffer);
+          if (buffers >= 2 && previous >= 0) finish_tile(previous, previous_buffer);
           previous = tile_index;
           previous_buffer = b;
         }
@@ -446,7 +452,7 @@ cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_c
       uint32_t full_parity = 0u;  // bit b = phase parity of full[b]
       int iteration = 0;
       for (int tile_index = blockIdx.x; tile_index < tile_count; tile_index += gridDim.x, ++iteration) {
-        const int b = buffers == 2 ? (iteration & 1) : 0;
+        const int b = iteration % buffers;
         const int first = tile_index * kCyThreads;
         const int count = min(kCyThreads, B - first);
         const size_t e = size_t(first);
@@ -591,6 +597,16 @@ int cyber_validate(const FrzCyberParams* p, const FrzCyberBuffers* io, int B, co
 
 constexpr int kCyMaxTileBytes = 72 * 1024;  // keeps >= 3 tiles resident per SM
 
+// tuning experiment knob (profiles/README.md): FRZ_CYBER_BUFFERS=1|2|3 fixes the tile buffers per CTA for large batches
+inline int cyber_buffer_override() {
+  static const int value = [] {
+    const char* text = std::getenv("FRZ_CYBER_BUFFERS");
+    const int n = text != nullptr ? std::atoi(text) : 0;
+    return n >= 1 && n <= kCyMaxBuffers ? n : 0;
+  }();
+  return value;
+}
+
 int cyber_launch(const FrzCyberParams* p, const FrzCyberBuffers* io, int B, int mode, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (mode == kCyStep) {
@@ -611,7 +627,11 @@ int cyber_launch(const FrzCyberParams* p, const FrzCyberBuffers* io, int B, int 
       // two tile buffers per CTA (the next tile is fetched while this one is stepped) when that still leaves several
       // CTAs per SM, and when the batch has more tiles than one wave of CTAs anyway
       const int tile_count = (B + kCyThreads - 1) / kCyThreads;
-      const int buffers = (2 * layout.total <= kCyMaxTileBytes && tile_count > sm_count() * 4) ? 2 : 1;
+      int buffers = 1;
+      if (tile_count > sm_count() * 4) {
+        if (cyber_buffer_override() > 0) buffers = cyber_buffer_override();
+        else buffers = 2 * layout.total <= kCyMaxTileBytes ? 2 : 1;  // (three buffers = one CTA fewer per SM: 205 us against 181 at 4 M envs)
+      }
       const int smem = buffers * layout.total;
       if (smem > 48 * 1024 && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return check_launch("cyber tile shared memory");
