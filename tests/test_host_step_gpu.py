@@ -19,6 +19,7 @@ CASES = [
     ('wildfire', 'wildfire_large', {}, 5000, 3),
     ('wildfire', 'wildfire_large', {}, 3000, 1),
     ('wildfire', 'wildfire_3x3', {}, 4096, 4),
+    ('wildfire', 'wildfire_large', {}, 30000, 3),
     ('rideshare', 'rideshare_c2', {}, 4100, 3),
     ('rideshare', 'rideshare_c2', {}, 2500, 2),
     ('cybersecurity', 'cyber_c3', dict(show_bad_actions=False, partially_observable=True), 6000, 5),
