@@ -255,3 +255,29 @@ def test_step_host_returns_the_next_observations():
         assert np.array_equal(observations['offsets'].numpy(), offsets)
         for name, tensor in want.items():
             assert torch.equal(observations[name].reshape(tensor.shape), tensor), (name, t)
+
+
+def test_a_fault_in_one_slice_reaches_check_errors():
+    """An invalid task index submitted through step_host in ONE slice of the batch: the slice's control block records
+    the fault, the merge folds it into the environment's block, check_errors raises (and clears it) -- and the other
+    environments stepped normally."""
+    B = 30000
+    device_env, host_env = make('wildfire', 'wildfire_large', {}, B, 20), make('wildfire', 'wildfire_large', {}, B, 20)
+    device_env.reset(seed=6)
+    host_env.reset(seed=6)
+    reference, raw = device_env.unwrapped, host_env.unwrapped
+    reference.sample_actions(1)
+    host_actions = torch.empty((B, len(raw.agents), 2), dtype=torch.int32).pin_memory()
+    host_actions.copy_(reference._actions)
+    torch.cuda.synchronize()
+    bad_env = 25000  # inside the last of three slices
+    host_actions[bad_env, 0] = torch.tensor([99, 0], dtype=torch.int32)  # fight task 99 of a 10x10 grid with ~15 fires
+    reference._actions.copy_(host_actions)
+    reference.step_all()
+    rewards, _, _ = host_env.step_host(host_actions, 3)
+    assert torch.equal(rewards, reference._rewards.cpu())  # identical to the device step, faulty environment included
+    with pytest.raises(ValueError, match='not a valid index'):
+        raw.check_errors()
+    raw.check_errors()  # cleared
+    with pytest.raises(ValueError, match='not a valid index'):
+        reference.check_errors()
