@@ -19,7 +19,7 @@ One JSON line is printed by rank 0:
   e2e              the same metric through the public Parallel API with HOST buffers (``parallel_env.step_host``):
                    page-locked int32 actions H2D + step + rewards / dones D2H + stream sync, every step; upload, kernel
                    and download are pipelined over slices of the batch inside frz_<domain>_step_host
-  e2e_i16_actions  the same call with the opt-in int16 action format (half the upload)
+  e2e_i16_actions  the same call with the opt-in int16 action format (half the upload); e2e_i8_actions: int8 (a quarter)
   e2e_full_obs     the same call returning the observations as well (self observations, task counts, the live task rows
                    and action-mask rows, compacted on the device): what a CPU policy needs per step
   cpu_baseline     the UNMODIFIED reference (oracle/_ref, stepped through oracle/ref_driver.py) on all host cores on a
@@ -603,6 +603,10 @@ def run_engine(args):
     e2e_ms, h2d, d2h, slices = h.host_leg(recorded, args.host_chunks or None)
     packed = recorded.to(torch.int16).pin_memory()
     i16_ms, i16_h2d, i16_d2h, _ = h.host_leg(packed, args.host_chunks or None)
+    bytes_ok = int(recorded.max()) <= 127 and int(recorded.min()) >= -128
+    tiny = recorded.to(torch.int8).pin_memory() if bytes_ok else None
+    if tiny is not None:
+        i8_ms, i8_h2d, i8_d2h, _ = h.host_leg(tiny, args.host_chunks or None)
     full = None
     if hasattr(raw, 'gather_observations'):
         full_ms, full_h2d, full_d2h, _ = h.host_leg(recorded, args.host_chunks or None, observations=True)
@@ -654,9 +658,13 @@ def run_engine(args):
             'stats': {'env_steps_executed': float(stats[0]), 'terminated_envs': float(stats[1]),
                       'truncated_envs': float(stats[2]), 'cumulative_reward_sum': float(stats[3:].sum())},
         }
+        if tiny is not None:
+            line['e2e_i8_actions'] = {'value': world * B / (i8_ms * 1e-3), 'unit': 'env-steps/s', 'ms_per_step': i8_ms,
+                                      'h2d_bytes_per_step': i8_h2d, 'd2h_bytes_per_step': i8_d2h,
+                                      'api': 'parallel_env.step_host with int8 actions (FRZ_HOST_ACTIONS_I8)'}
         if full is not None:
             line['e2e_full_obs'] = full
-        del h, raw, recorded, packed
+        del h, raw, recorded, packed, tiny
         torch.cuda.empty_cache()
         if world == 1:
             line['cpu_baseline'] = cpu_baseline

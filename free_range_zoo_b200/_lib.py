@@ -145,7 +145,7 @@ class GatherArray(C.Structure):
                 ('groups', C.c_int32), ('reserved', C.c_int32)]
 
 
-HOST_ACTIONS_I32, HOST_ACTIONS_I16 = 0, 1
+HOST_ACTIONS_I32, HOST_ACTIONS_I16, HOST_ACTIONS_I8 = 0, 1, 2
 ABI_VERSION = 4
 
 

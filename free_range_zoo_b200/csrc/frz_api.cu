@@ -101,10 +101,12 @@ bool create_events(FrzHostPipeline* pipeline) {
   return true;
 }
 
-__global__ void widen_actions_kernel(const short4* __restrict__ packed, int4* __restrict__ actions, size_t quads,
-                                     const int16_t* __restrict__ tail_in, int32_t* __restrict__ tail_out, int tail) {
+// four packed action words (short4 / char4) -> four int32
+template <class Packed4, class Scalar>
+__global__ void widen_actions_kernel(const Packed4* __restrict__ packed, int4* __restrict__ actions, size_t quads,
+                                     const Scalar* __restrict__ tail_in, int32_t* __restrict__ tail_out, int tail) {
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < quads; i += size_t(gridDim.x) * blockDim.x) {
-    const short4 v = packed[i];
+    const Packed4 v = packed[i];
     actions[i] = make_int4(v.x, v.y, v.z, v.w);
   }
   if (blockIdx.x == 0 && int(threadIdx.x) < tail) tail_out[threadIdx.x] = tail_in[threadIdx.x];
@@ -138,13 +140,21 @@ cudaEvent_t* pipeline_events(FrzHostPipeline* pipeline) {
   return per_device[device]->events;
 }
 
-int widen_actions(const int16_t* packed, int32_t* actions, size_t count, cudaStream_t stream) {
+int widen_actions(const void* packed, int element_bytes, int32_t* actions, size_t count, cudaStream_t stream) {
   const size_t quads = count / 4;  // (both arrays start 16-byte aligned: slices begin on multiples of 1024 environments)
   const int tail = int(count % 4);
   const size_t blocks = (quads + 255) / 256;
   const int grid = persistent_grid(int(blocks < 1 ? 1 : (blocks > (1u << 20) ? (1u << 20) : blocks)), 8);
-  widen_actions_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const short4*>(packed), reinterpret_cast<int4*>(actions),
-                                                 quads, packed + 4 * quads, actions + 4 * quads, tail);
+  int4* const out = reinterpret_cast<int4*>(actions);
+  if (element_bytes == 2) {
+    const int16_t* in = static_cast<const int16_t*>(packed);
+    widen_actions_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const short4*>(in), out, quads, in + 4 * quads,
+                                                   actions + 4 * quads, tail);
+  } else {
+    const int8_t* in = static_cast<const int8_t*>(packed);
+    widen_actions_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const char4*>(in), out, quads, in + 4 * quads,
+                                                   actions + 4 * quads, tail);
+  }
   return check_launch("widen_actions_kernel");
 }
 

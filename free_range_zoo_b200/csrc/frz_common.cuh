@@ -87,8 +87,8 @@ int control_broadcast(FrzControl* main_block, FrzControl* chunk_blocks, int coun
 int control_merge(FrzControl* main_block, FrzControl* chunk_blocks, int count, cudaStream_t stream);
 // the events of `pipeline`, or (NULL) of the calling thread on the current device; nullptr + error string on failure
 cudaEvent_t* pipeline_events(FrzHostPipeline* pipeline);
-// int16 [count] -> int32 [count] on the device (FRZ_HOST_ACTIONS_I16)
-int widen_actions(const int16_t* packed, int32_t* actions, size_t count, cudaStream_t stream);
+// int16 / int8 [count] (element_bytes = 2 / 1) -> int32 [count] on the device (FRZ_HOST_ACTIONS_I16 / _I8)
+int widen_actions(const void* packed, int element_bytes, int32_t* actions, size_t count, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------- Philox4x32-10
 

@@ -69,13 +69,14 @@ int run_host_pipeline(const char* what, const FrzHostStep* host, const HostArray
     set_error("%s: chunks=%d outside [1, %d]", what, host->chunks, FRZ_MAX_CHUNKS);
     return FRZ_ERR_SHAPE;
   }
-  const bool packed = host->action_format == FRZ_HOST_ACTIONS_I16;
+  const bool packed = host->action_format == FRZ_HOST_ACTIONS_I16 || host->action_format == FRZ_HOST_ACTIONS_I8;
+  const size_t packed_bytes = host->action_format == FRZ_HOST_ACTIONS_I8 ? 1 : 2;  // per action word
   if (host->action_format != FRZ_HOST_ACTIONS_I32 && !packed) {
     set_error("%s: unknown action_format %d", what, host->action_format);
     return FRZ_ERR_UNSUPPORTED;
   }
   if (packed && host->packed_actions == nullptr) {
-    set_error("%s: FRZ_HOST_ACTIONS_I16 needs the packed_actions device scratch", what);
+    set_error("%s: FRZ_HOST_ACTIONS_I16 / _I8 need the packed_actions device scratch", what);
     return FRZ_ERR_NULL;
   }
   cudaEvent_t* const events = pipeline_events(host->pipeline);
@@ -87,7 +88,7 @@ int run_host_pipeline(const char* what, const FrzHostStep* host, const HostArray
   int bounds[FRZ_MAX_CHUNKS + 1];
   const int slices = slice_bounds(B, host->chunks, bounds);
   const size_t A = size_t(device.agents);
-  // upload the actions of environments [first, first + count) on `stream`; int16 pairs are widened on the device
+  // upload the actions of environments [first, first + count) on `stream`; int16 / int8 pairs are widened on the device
   const auto upload = [&](int first, int count, cudaStream_t stream, bool widen_here) -> int {
     const size_t at = size_t(first) * A * 2, words = size_t(count) * A * 2;
     int32_t* const actions = const_cast<int32_t*>(device.actions) + at;
@@ -95,10 +96,11 @@ int run_host_pipeline(const char* what, const FrzHostStep* host, const HostArray
       cudaMemcpyAsync(actions, static_cast<const int32_t*>(host->actions) + at, words * sizeof(int32_t), cudaMemcpyHostToDevice, stream);
       return FRZ_OK;
     }
-    cudaMemcpyAsync(host->packed_actions + at, static_cast<const int16_t*>(host->actions) + at, words * sizeof(int16_t),
+    char* const staged = reinterpret_cast<char*>(host->packed_actions) + at * packed_bytes;
+    cudaMemcpyAsync(staged, static_cast<const char*>(host->actions) + at * packed_bytes, words * packed_bytes,
                     cudaMemcpyHostToDevice, stream);
     // (the pipelined path widens on the slice's own stream instead, once the slice has arrived)
-    return widen_here ? widen_actions(host->packed_actions + at, actions, words, stream) : FRZ_OK;
+    return widen_here ? widen_actions(staged, int(packed_bytes), actions, words, stream) : FRZ_OK;
   };
 
   if (slices == 1) {  // nothing to overlap: upload, step and download on the caller's stream, on the main control block
@@ -130,8 +132,9 @@ int run_host_pipeline(const char* what, const FrzHostStep* host, const HostArray
       cudaStream_t stream = (i == 0) ? main_stream : static_cast<cudaStream_t>(host->streams[i]);
       cudaStreamWaitEvent(stream, uploaded[i], 0);
       launched = i + 1;
-      if (packed) status = widen_actions(host->packed_actions + size_t(first) * A * 2,
-                                         const_cast<int32_t*>(device.actions) + size_t(first) * A * 2, size_t(count) * A * 2, stream);
+      if (packed) status = widen_actions(reinterpret_cast<const char*>(host->packed_actions) + size_t(first) * A * 2 * packed_bytes,
+                                         int(packed_bytes), const_cast<int32_t*>(device.actions) + size_t(first) * A * 2,
+                                         size_t(count) * A * 2, stream);
       if (status == FRZ_OK) status = launch_slice(first, count, host->chunk_controls + i, stream);
       if (status == FRZ_OK)
         cudaMemcpyAsync(host->rewards + size_t(first) * A, device.rewards + size_t(first) * A, size_t(count) * A * sizeof(float),
@@ -206,7 +209,7 @@ int run_host_pipeline(const char* what, const FrzHostStep* host, const HostArray
     cudaGraphGetNodes(graph, nullptr, &node_count);
     std::vector<cudaGraphNode_t> nodes(node_count);
     cudaGraphGetNodes(graph, nodes.data(), &node_count);
-    const size_t element = packed ? sizeof(int16_t) : sizeof(int32_t);
+    const size_t element = packed ? packed_bytes : sizeof(int32_t);
     const char* const base = static_cast<const char*>(host->actions);
     const size_t span = size_t(B) * A * 2 * element;
     for (cudaGraphNode_t node : nodes) {

@@ -453,8 +453,9 @@ class BatchedAECEnv(ABC):
     @torch.no_grad()
     def step_host(self, host_actions: torch.Tensor, chunks: Optional[int] = None, observations: bool = False
                   ) -> Tuple[torch.Tensor, ...]:
-        """One environment step for callers that live on the host: ``host_actions`` is a page-locked int32 -- or int16,
-        which halves the upload and is widened on the device -- ``[B, A, 2]`` CPU tensor (agent order = ``env.agents``);
+        """One environment step for callers that live on the host: ``host_actions`` is a page-locked int32 -- or int16 /
+        int8 (at most 127 tasks per environment), which halve / quarter the upload and are widened on the device --
+        ``[B, A, 2]`` CPU tensor (agent order = ``env.agents``);
         returns page-locked CPU tensors ``(rewards f32 [B, A],
         terminated bool [B], truncated bool [B])`` that are valid when the call returns and are overwritten by the next
         ``step_host``.  Equivalent to copying the actions to the device, ``step_all`` and copying the results back,
@@ -464,15 +465,15 @@ class BatchedAECEnv(ABC):
         ``gather_observations()`` returns (the next observations in host memory, packed), which is what a policy that
         runs on the CPU needs for its next decision."""
         B, A = self.parallel_envs, len(self.possible_agents)
-        if (host_actions.device.type != 'cpu' or host_actions.dtype not in (torch.int32, torch.int16)
+        if (host_actions.device.type != 'cpu' or host_actions.dtype not in (torch.int32, torch.int16, torch.int8)
                 or not host_actions.is_contiguous() or tuple(host_actions.shape) != (B, A, 2)
                 or not host_actions.is_pinned()):
-            raise ValueError(f'step_host expects a page-locked contiguous int32 / int16 CPU tensor of shape {(B, A, 2)} '
+            raise ValueError(f'step_host expects a page-locked contiguous int32 / int16 / int8 CPU tensor of shape {(B, A, 2)} '
                              '(torch.empty(..., dtype=torch.int32).pin_memory())')
         state = self._host_pipeline(chunks)
         state['block'].actions = host_actions.data_ptr()
-        state['block'].action_format = (_lib.HOST_ACTIONS_I16 if host_actions.dtype == torch.int16
-                                        else _lib.HOST_ACTIONS_I32)
+        state['block'].action_format = {torch.int32: _lib.HOST_ACTIONS_I32, torch.int16: _lib.HOST_ACTIONS_I16,
+                                        torch.int8: _lib.HOST_ACTIONS_I8}[host_actions.dtype]
         current, main = torch.cuda.current_stream(self.device), state['main']
         main.wait_stream(current)
         _lib.check(self._host_entry()(ctypes.byref(self._params), ctypes.byref(self._io), B,

@@ -349,6 +349,10 @@ int frz_host_pipeline_destroy(FrzHostPipeline* pipeline);
 #define FRZ_HOST_ACTIONS_I32 0  /* actions: int32 [B, A, 2], the device layout */
 #define FRZ_HOST_ACTIONS_I16 1  /* actions: int16 [B, A, 2] -- half the upload; widened on the device (every task index
                                    and action id of the three domains fits: <= 256 tasks, ids in [-3, 2]) */
+#define FRZ_HOST_ACTIONS_I8 2   /* actions: int8 [B, A, 2] -- a quarter of the upload, for configurations with at most
+                                   127 tasks per environment (grids of <= 127 cells, every rideshare / cybersecurity
+                                   shape); where several GPUs share a PCIe uplink the upload is what a host-driven
+                                   step waits for */
 
 typedef struct {
   const void* actions;         /* HOST, page-locked: [B, A, 2] in `action_format` */
@@ -359,7 +363,7 @@ typedef struct {
   void* const* streams;        /* `chunks` cudaStream_t of the caller, one per slice */
   int32_t chunks;              /* 1 .. FRZ_MAX_CHUNKS */
   int32_t action_format;       /* FRZ_HOST_ACTIONS_* */
-  int16_t* packed_actions;     /* DEVICE scratch [B, A, 2] int16, required for FRZ_HOST_ACTIONS_I16 */
+  int16_t* packed_actions;     /* DEVICE scratch [B, A, 2] int16, required for FRZ_HOST_ACTIONS_I16 / _I8 */
   FrzHostPipeline* pipeline;   /* NULL = per-thread, per-device events kept by the library */
 } FrzHostStep;
 

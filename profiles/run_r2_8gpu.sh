@@ -1,0 +1,6 @@
+# round 2: four-GPU bench line (weak scaling, no step-path collective)
+cd "$(dirname "$0")/.."
+O=gpurun_out/r2g
+mkdir -p $O
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 8 --steps 20 --warmup 5 > $O/bench_8gpu.json 2> $O/bench_8gpu.err; tail -c 300 $O/bench_8gpu.err
+cat $O/bench_8gpu.json | cut -c1-300

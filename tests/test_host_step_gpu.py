@@ -39,7 +39,7 @@ def device_arrays(raw):
             if tensor is not None and not name.startswith('init_') and name != 'control'}
 
 
-@pytest.mark.parametrize('dtype', [torch.int32, torch.int16], ids=['i32', 'i16'])
+@pytest.mark.parametrize('dtype', [torch.int32, torch.int16, torch.int8], ids=['i32', 'i16', 'i8'])
 @pytest.mark.parametrize('domain,preset,kwargs,B,chunks', CASES)
 def test_host_step_equals_device_step(domain, preset, kwargs, B, chunks, dtype):
     steps = 12
