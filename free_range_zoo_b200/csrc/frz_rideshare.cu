@@ -9,6 +9,11 @@
 // re-sorts / compacts it with `unique`, boolean-mask indexing and a stable `argsort` every step.  Here environment b
 // owns rows passengers[b, 0:count[b]] (same relative order).
 //
+// Two kernels with identical results; the batch size picks one (FRZ_RS_KERNEL_* force it):
+//   * rideshare_tile_kernel (batches of 24 576 environments and more, tables with a multiple of four rows, at most
+//     eight drivers): one THREAD per environment -- see the comment above that kernel;
+//   * rideshare_step_kernel (everything else), described here.
+//
 // Mapping: a group of G lanes (8, 16 or 32, chosen from the table capacity and the number of drivers) owns one
 // environment, so a warp steps 4, 2 or 1 environments at once.  The environment's rows are staged in shared memory
 // (cp.async) for the whole step and edited in place; lane s of the group looks after rows s, s+G, ... (PPL of them)
@@ -491,15 +496,27 @@ rideshare_step_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
 // and a warp instruction serves 32 environments instead of 4.
 //
 // What makes that possible is the staging: the live rows of an environment are one contiguous byte range of the table
-// (rows 0 .. count-1 of its slot), so they move global -> shared -> global as ONE 1-D bulk async copy per environment
+// (rows 0 .. count-1 of its slot), so they move global -> shared as ONE 1-D bulk async copy per environment
 // (cp.async.bulk, the TMA unit; completion on the warp's mbarrier), never through registers or the LSU.  The warp's
 // buffer is carved up by a prefix sum over what its environments need this step (live rows + rows that may enter), so
 // shared memory is sized for the typical table fill, not for the capacity; a tile whose environments do not fit in one
-// go is stepped in several passes (each pass takes the longest prefix of the waiting environments that fits).
+// go is stepped in several passes of similar size.
+//
+// The way back is selective: a step touches few rows (riding passengers that moved, an accept, a pick, the rows behind an
+// exit, an entry), and task_obs / task_mask are functions of the table alone, so only the changed rows, their
+// observation rows and the 16-row mask pieces whose membership changed are stored (directly, as 8- / 16-byte pieces).
+// Measured: rewriting everything with coalescing sweeps cost 60 us of DRAM write traffic at 524 288 environments.
+// Row sets (unaccepted / accepted / riding / per driver) live in registers as bit masks, built once from the table and
+// kept up to date through every edit (an exit removes a bit position: bit-compress).
 // One warp per CTA: the tile index is then a function of blockIdx alone, which the compiler can prove warp-uniform -- the
 // addresses of the bulk copies stay in uniform registers -- and up to 20 such CTAs share an SM.
 constexpr int kTileThreads = 32;
 constexpr int kTileWarps = kTileThreads / 32;
+// profiling experiments only (profiles/README.md; never defined in the shipped build): 1 = copies but no stepping,
+// 2 = stepping but no copies, 3 = no observation / mask stores -- results are wrong on purpose, time only
+#ifndef FRZ_RS_ABLATE
+#define FRZ_RS_ABLATE 0
+#endif
 constexpr int kTileRowBudget = 8;   // rows per environment the warp buffers are sized for (32 * 8 rows per warp)
 
 constexpr int kTileIndexWords = 2048;      // longest schedule_index copied to shared memory
@@ -669,9 +686,6 @@ rideshare_tile_kernel(const __grid_constant__ FrzRideshareParams p, const __grid
         // ---------------------------------------------------------------- stage the live rows (one bulk copy each)
         const uint32_t load_bytes = now ? bytes_in : 0u;
         const uint32_t total_in = __reduce_add_sync(kFullMask, load_bytes);
-#ifndef FRZ_RS_ABLATE
-#define FRZ_RS_ABLATE 0  // profiling experiments (profiles/README.md): 1 = copies only, 2 = no copies, 3 = no observation stores
-#endif
         if (FRZ_RS_ABLATE != 2) {
           if (elect_one()) mbarrier_expect_bytes(barrier, total_in);
           // the pass's environments are consecutive lanes; everything but the two shuffled words is warp-uniform
