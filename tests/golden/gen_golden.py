@@ -3,6 +3,7 @@
 Run in the build container only (needs /root/reference):
 
     python tests/golden/gen_golden.py            # regenerates every fixture
+    python tests/golden/gen_golden.py NAME ...   # only the named fixtures
 
 For each fixture the reference environment (imported through ``ref_shim``) is rolled out on CPU with random legal
 actions, with ``env.generator.generate`` replaced by a recorder that serves seeded uniforms of the shape the
@@ -38,6 +39,7 @@ from free_range_zoo.envs.cybersecurity.env.structures import configuration as re
 from free_range_zoo_b200 import presets  # noqa: E402
 
 PAD = -100
+ONLY = set(sys.argv[1:])  # fixture names given on the command line (empty = all)
 
 
 def padded(nested, width, dtype=np.int32):
@@ -134,6 +136,8 @@ def wildfire_actions(raw, gen):
 
 
 def gen_wildfire(name, preset, B, steps, seed, preset_kwargs=None, **env_kwargs):
+    if ONLY and name not in ONLY:
+        return
     torch.manual_seed(seed)
     preset_kwargs = preset_kwargs or {}
     config = preset(ref_wf_conf, **preset_kwargs)
@@ -238,6 +242,8 @@ def rideshare_actions(raw, gen, wild):
 
 
 def gen_rideshare(name, preset, B, steps, seed, wild=0.0, preset_kwargs=None, **env_kwargs):
+    if ONLY and name not in ONLY:
+        return
     config = preset(ref_rs_conf, **(preset_kwargs or {}))
     K = int(config.passenger_config.schedule.shape[0])
     env = rideshare_v0.parallel_env(parallel_envs=B, max_steps=steps, configuration=config, device=torch.device('cpu'),
@@ -317,6 +323,8 @@ def cyber_actions(raw, gen):
 
 
 def gen_cyber(name, preset, B, steps, seed, preset_kwargs=None, **env_kwargs):
+    if ONLY and name not in ONLY:
+        return
     preset_kwargs = preset_kwargs or {}
     config = preset(ref_cy_conf, **preset_kwargs)
     env = cybersecurity_v0.parallel_env(parallel_envs=B, max_steps=steps, configuration=config,
@@ -359,6 +367,9 @@ def main():
                  preset_kwargs=dict(height=7, width=8, num_agents=5, seed=5))
     gen_wildfire('wildfire_12x12', presets.wildfire_large, B=6, steps=20, seed=17,
                  preset_kwargs=dict(height=12, width=12, num_agents=20, seed=3))
+    # a 32-cell grid with 8 agents: the largest shape of the small-grid kernels (8 lanes x 4 cells / one thread per env)
+    gen_wildfire('wildfire_4x8', presets.wildfire_large, B=10, steps=25, seed=18,
+                 preset_kwargs=dict(height=4, width=8, num_agents=8, seed=33))
 
     gen_rideshare('rideshare_profile', presets.rideshare_profile, B=8, steps=20, seed=21)
     gen_rideshare('rideshare_c2', presets.rideshare_c2, B=24, steps=100, seed=22)
@@ -374,6 +385,12 @@ def main():
                   preset_kwargs=dict(drivers=12, rows=40))
     gen_rideshare('rideshare_20drivers', presets.rideshare_synthetic, B=4, steps=25, seed=27,
                   preset_kwargs=dict(drivers=20, rows=64))
+
+    # the eight-driver variants of the tiled kernel (one thread per environment): 32- and 64-bit row sets
+    gen_rideshare('rideshare_7drivers', presets.rideshare_synthetic, B=8, steps=25, seed=28,
+                  preset_kwargs=dict(drivers=7, rows=24))
+    gen_rideshare('rideshare_8drivers', presets.rideshare_synthetic, B=6, steps=25, seed=29,
+                  preset_kwargs=dict(drivers=8, rows=40))
 
     gen_cyber('cyber_profile', presets.cyber_profile, B=8, steps=20, seed=31)
     gen_cyber('cyber_c3', presets.cyber_c3, B=32, steps=60, seed=32, show_bad_actions=False, partially_observable=True)
