@@ -308,8 +308,8 @@ struct CyberTileLayout {  // byte offsets of the staged arrays inside the tile (
   int total;
 };
 
-__host__ __device__ inline CyberTileLayout cyber_tile_layout(int N, int n_att, int n_def, bool injected) {
-  const int n = n_att + n_def, T = kCyThreads;
+__host__ __device__ inline CyberTileLayout cyber_tile_layout(int N, int n_att, int n_def, bool injected, int T = kCyThreads) {
+  const int n = n_att + n_def;
   CyberTileLayout L;
   int at = 0;
   auto take = [&at](int bytes) {
@@ -338,8 +338,8 @@ __host__ __device__ inline CyberTileLayout cyber_tile_layout(int N, int n_att, i
 }
 
 // cooperative copy for the (at most one) partial tile at the end of the batch: sizes need not be multiples of 16
-__device__ __forceinline__ void tile_copy(uint8_t* dst, const uint8_t* src, int bytes) {
-  for (int i = threadIdx.x; i < bytes; i += kCyThreads) dst[i] = src[i];
+__device__ __forceinline__ void tile_copy(uint8_t* dst, const uint8_t* src, int bytes, int threads) {
+  for (int i = threadIdx.x; i < bytes; i += threads) dst[i] = src[i];
 }
 
 // Persistent and warp-specialised: a CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...; its first kCyThreads
@@ -355,7 +355,8 @@ constexpr int kCyMaxBuffers = 3;
 template <bool INJECTED, int MAXN, int MAXATT, int MAXDEF>
 __global__ void __launch_bounds__(kCyBlock, 4)
 cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_constant__ FrzCyberBuffers io, const int B,
-                        const int buffers) {
+                        const int buffers, const int tile_envs) {
+  const int T = tile_envs;  // environments per tile = stepping threads (64 or 128; the CTA has one more warp)
   extern __shared__ __align__(128) uint8_t tiles_storage[];
   __shared__ __align__(8) uint64_t barrier_storage[2 * kCyMaxBuffers];  // full[b], then done[b]
   const int N = p.num_nodes, n_att = p.num_attackers, n_def = p.num_defenders, n = n_att + n_def;
@@ -367,29 +368,29 @@ cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_c
   unsigned alive_bits = 0, faults = 0;
 
   if (!skip) {
-    const CyberTileLayout L = cyber_tile_layout(N, n_att, n_def, INJECTED);
+    const CyberTileLayout L = cyber_tile_layout(N, n_att, n_def, INJECTED, T);
     const bool inject_network = INJECTED && io.network_uniforms != nullptr;
     const bool inject_agent = INJECTED && io.agent_uniforms != nullptr;
-    const int tile_count = (B + kCyThreads - 1) / kCyThreads;
+    const int tile_count = (B + T - 1) / T;
     const uint32_t storage_s = shared_address(tiles_storage);
     const auto full_barrier = [&](int b) { return shared_address(&barrier_storage[b]); };
     const auto done_barrier = [&](int b) { return shared_address(&barrier_storage[kCyMaxBuffers + b]); };
     if (threadIdx.x == 0) {
       for (int b = 0; b < kCyMaxBuffers; ++b) {
         mbarrier_init(full_barrier(b), 1);
-        mbarrier_init(done_barrier(b), kCyThreads);
+        mbarrier_init(done_barrier(b), T);
       }
     }
     __syncthreads();
-    const auto is_full = [&](int tile_index) { return (tile_index + 1) * kCyThreads <= B; };
+    const auto is_full = [&](int tile_index) { return (tile_index + 1) * T <= B; };
 
-    if (threadIdx.x >= kCyThreads) {
+    if (threadIdx.x >= T) {
       // ================================================================== the copy thread
-      if (threadIdx.x == kCyThreads) {
-        const uint32_t T = kCyThreads;
+      if (threadIdx.x == T) {
+        const uint32_t T = uint32_t(tile_envs);
         // the bulk loads of one full tile into buffer b
         const auto request = [&](int tile_index, int b) {
-          const size_t e = size_t(tile_index) * kCyThreads;
+          const size_t e = size_t(tile_index) * T;
           const uint32_t tile_s = storage_s + uint32_t(b) * uint32_t(L.total), barrier = full_barrier(b);
           uint32_t bytes = T * (N * 4 + n_def * 4 + n + n * 4 + 4 + n * 8);
           if (inject_network) bytes += T * N * 4;
@@ -406,7 +407,7 @@ cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_c
         };
         // the bulk stores of one stepped full tile out of buffer b (one bulk group)
         const auto write_back = [&](int tile_index, int b) {
-          const size_t e = size_t(tile_index) * kCyThreads;
+          const size_t e = size_t(tile_index) * T;
           const uint32_t tile_s = storage_s + uint32_t(b) * uint32_t(L.total);
           bulk_store(io.network_state + e * N, tile_s + L.state, T * N * 4);
           bulk_store(io.location + e * n_def, tile_s + L.location, T * n_def * 4);
@@ -453,27 +454,27 @@ cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_c
       int iteration = 0;
       for (int tile_index = blockIdx.x; tile_index < tile_count; tile_index += gridDim.x, ++iteration) {
         const int b = iteration % buffers;
-        const int first = tile_index * kCyThreads;
-        const int count = min(kCyThreads, B - first);
+        const int first = tile_index * T;
+        const int count = min(T, B - first);
         const size_t e = size_t(first);
-        const bool full = count == kCyThreads;
+        const bool full = count == T;
         uint8_t* const tile = tiles_storage + size_t(b) * size_t(L.total);
 
         // ------------------------------------------------------------------ the tile has arrived (or the buffer is free)
         mbarrier_wait(full_barrier(b), (full_parity >> b) & 1u);
         full_parity ^= 1u << b;
         if (!full) {
-          tile_copy(tile + L.state, reinterpret_cast<const uint8_t*>(io.network_state + e * N), count * N * 4);
-          tile_copy(tile + L.location, reinterpret_cast<const uint8_t*>(io.location + e * n_def), count * n_def * 4);
-          tile_copy(tile + L.presence, io.presence + e * n, count * n);
-          tile_copy(tile + L.cumulative, reinterpret_cast<const uint8_t*>(io.cumulative_rewards + e * n), count * n * 4);
-          tile_copy(tile + L.num_moves, reinterpret_cast<const uint8_t*>(io.num_moves + e), count * 4);
-          tile_copy(tile + L.actions, reinterpret_cast<const uint8_t*>(io.actions + e * n * 2), count * n * 8);
+          tile_copy(tile + L.state, reinterpret_cast<const uint8_t*>(io.network_state + e * N), count * N * 4, T);
+          tile_copy(tile + L.location, reinterpret_cast<const uint8_t*>(io.location + e * n_def), count * n_def * 4, T);
+          tile_copy(tile + L.presence, io.presence + e * n, count * n, T);
+          tile_copy(tile + L.cumulative, reinterpret_cast<const uint8_t*>(io.cumulative_rewards + e * n), count * n * 4, T);
+          tile_copy(tile + L.num_moves, reinterpret_cast<const uint8_t*>(io.num_moves + e), count * 4, T);
+          tile_copy(tile + L.actions, reinterpret_cast<const uint8_t*>(io.actions + e * n * 2), count * n * 8, T);
           if (inject_network)
-            tile_copy(tile + L.network_uniforms, reinterpret_cast<const uint8_t*>(io.network_uniforms + e * N), count * N * 4);
+            tile_copy(tile + L.network_uniforms, reinterpret_cast<const uint8_t*>(io.network_uniforms + e * N), count * N * 4, T);
           if (inject_agent)
-            tile_copy(tile + L.agent_uniforms, reinterpret_cast<const uint8_t*>(io.agent_uniforms + e * n), count * n * 4);
-          named_barrier_sync(1, kCyThreads);
+            tile_copy(tile + L.agent_uniforms, reinterpret_cast<const uint8_t*>(io.agent_uniforms + e * n), count * n * 4, T);
+          named_barrier_sync(1, T);
         }
 
         // ------------------------------------------------------------------ step, entirely in shared memory
@@ -504,20 +505,20 @@ cyber_step_tiled_kernel(const __grid_constant__ FrzCyberParams p, const __grid_c
           fence_async_shared();  // this thread's writes become visible to the bulk stores
           mbarrier_arrive(done_barrier(b));
         } else {
-          named_barrier_sync(1, kCyThreads);
-          tile_copy(reinterpret_cast<uint8_t*>(io.network_state + e * N), tile + L.state, count * N * 4);
-          tile_copy(reinterpret_cast<uint8_t*>(io.location + e * n_def), tile + L.location, count * n_def * 4);
-          tile_copy(io.presence + e * n, tile + L.presence, count * n);
-          tile_copy(reinterpret_cast<uint8_t*>(io.cumulative_rewards + e * n), tile + L.cumulative, count * n * 4);
-          tile_copy(reinterpret_cast<uint8_t*>(io.num_moves + e), tile + L.num_moves, count * 4);
-          tile_copy(reinterpret_cast<uint8_t*>(io.rewards + e * n), tile + L.rewards, count * n * 4);
-          tile_copy(io.truncated + e, tile + L.truncated, count);
-          tile_copy(reinterpret_cast<uint8_t*>(io.env_task_count + e), tile + L.env_task_count, count * 4);
-          tile_copy(reinterpret_cast<uint8_t*>(io.agent_task_count + e * n), tile + L.agent_task_count, count * n * 4);
-          tile_copy(reinterpret_cast<uint8_t*>(io.attacker_self + e * n_att * 2), tile + L.attacker_self, count * n_att * 8);
-          tile_copy(reinterpret_cast<uint8_t*>(io.defender_self + e * n_def * 3), tile + L.defender_self, count * n_def * 12);
-          tile_copy(reinterpret_cast<uint8_t*>(io.task_obs + e * N * 2), tile + L.task_obs, count * N * 8);
-          tile_copy(io.monitored + e * n_def, tile + L.monitored, count * n_def);
+          named_barrier_sync(1, T);
+          tile_copy(reinterpret_cast<uint8_t*>(io.network_state + e * N), tile + L.state, count * N * 4, T);
+          tile_copy(reinterpret_cast<uint8_t*>(io.location + e * n_def), tile + L.location, count * n_def * 4, T);
+          tile_copy(io.presence + e * n, tile + L.presence, count * n, T);
+          tile_copy(reinterpret_cast<uint8_t*>(io.cumulative_rewards + e * n), tile + L.cumulative, count * n * 4, T);
+          tile_copy(reinterpret_cast<uint8_t*>(io.num_moves + e), tile + L.num_moves, count * 4, T);
+          tile_copy(reinterpret_cast<uint8_t*>(io.rewards + e * n), tile + L.rewards, count * n * 4, T);
+          tile_copy(io.truncated + e, tile + L.truncated, count, T);
+          tile_copy(reinterpret_cast<uint8_t*>(io.env_task_count + e), tile + L.env_task_count, count * 4, T);
+          tile_copy(reinterpret_cast<uint8_t*>(io.agent_task_count + e * n), tile + L.agent_task_count, count * n * 4, T);
+          tile_copy(reinterpret_cast<uint8_t*>(io.attacker_self + e * n_att * 2), tile + L.attacker_self, count * n_att * 8, T);
+          tile_copy(reinterpret_cast<uint8_t*>(io.defender_self + e * n_def * 3), tile + L.defender_self, count * n_def * 12, T);
+          tile_copy(reinterpret_cast<uint8_t*>(io.task_obs + e * N * 2), tile + L.task_obs, count * N * 8, T);
+          tile_copy(io.monitored + e * n_def, tile + L.monitored, count * n_def, T);
         }
       }
     }
@@ -611,10 +612,14 @@ int cyber_launch(const FrzCyberParams* p, const FrzCyberBuffers* io, int B, int 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (mode == kCyStep) {
     const bool injected = io->network_uniforms != nullptr || io->agent_uniforms != nullptr;
-    const CyberTileLayout layout = cyber_tile_layout(p->num_nodes, p->num_attackers, p->num_defenders, injected);
+    // tiles of 128 environments; 64 when that is what it takes to put a tile on every SM (the named 16 384 environments
+    // are 128 tiles of 128 on a 148-SM B200)
+    const int tile_envs = (B + kCyThreads - 1) / kCyThreads < sm_count() ? kCyThreads / 2 : kCyThreads;
+    const int tile_count = (B + tile_envs - 1) / tile_envs;
+    const CyberTileLayout layout = cyber_tile_layout(p->num_nodes, p->num_attackers, p->num_defenders, injected, tile_envs);
     if (layout.total <= kCyMaxTileBytes) {
       // size classes: loops over nodes / attackers / defenders are unrolled to the class bound (0 = runtime loops)
-      void (*kernel)(FrzCyberParams, FrzCyberBuffers, int, int);
+      void (*kernel)(FrzCyberParams, FrzCyberBuffers, int, int, int);
       const int N = p->num_nodes, att = p->num_attackers, def = p->num_defenders;
       if (N <= 4 && att <= 2 && def <= 2)
         kernel = injected ? cyber_step_tiled_kernel<true, 4, 2, 2> : cyber_step_tiled_kernel<false, 4, 2, 2>;
@@ -626,7 +631,6 @@ int cyber_launch(const FrzCyberParams* p, const FrzCyberBuffers* io, int B, int 
         kernel = injected ? cyber_step_tiled_kernel<true, 0, 0, 0> : cyber_step_tiled_kernel<false, 0, 0, 0>;
       // two tile buffers per CTA (the next tile is fetched while this one is stepped) when that still leaves several
       // CTAs per SM, and when the batch has more tiles than one wave of CTAs anyway
-      const int tile_count = (B + kCyThreads - 1) / kCyThreads;
       int buffers = 1;
       if (tile_count > sm_count() * 4) {
         if (cyber_buffer_override() > 0) buffers = cyber_buffer_override();
@@ -637,9 +641,9 @@ int cyber_launch(const FrzCyberParams* p, const FrzCyberBuffers* io, int B, int 
         return check_launch("cyber tile shared memory");
       cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       int ctas_per_sm = 0;  // (not cached: the same instantiation runs with one or two buffers)
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, kCyBlock, size_t(smem));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, tile_envs + 32, size_t(smem));
       const int grid = persistent_grid(tile_count, ctas_per_sm < 1 ? 1 : ctas_per_sm);
-      kernel<<<grid, kCyBlock, smem, s>>>(*p, *io, B, buffers);
+      kernel<<<grid, tile_envs + 32, smem, s>>>(*p, *io, B, buffers, tile_envs);
       return check_launch("cyber_step_tiled_kernel");
     }
   }
