@@ -186,6 +186,7 @@ def library() -> C.CDLL:
                                   ('frz_rideshare_step_host', RideshareParams, RideshareBuffers)):
         getattr(lib, name).argtypes = [C.POINTER(params), C.POINTER(buffers), C.c_int32, C.POINTER(HostStep), C.c_void_p]
     lib.frz_host_slices.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    lib.frz_wildfire_tile_random_layout.argtypes = [C.POINTER(WildfireParams), C.POINTER(C.c_uint32), C.POINTER(C.c_int8)]
     lib.frz_gather_live_rows.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(GatherArray), C.c_int32,
                                          C.c_void_p]
     if lib.frz_version() != ABI_VERSION:

@@ -1312,6 +1312,29 @@ int frz_wildfire_step_host(const FrzWildfireParams* params, const FrzWildfireBuf
       });
 }
 
+int frz_wildfire_tile_random_layout(const FrzWildfireParams* params, uint32_t* streams, int8_t* destinations) {
+  frz::Geometry g;
+  if (params == nullptr || streams == nullptr || destinations == nullptr) {
+    frz::set_error("frz_wildfire_tile_random_layout: NULL argument");
+    return -FRZ_ERR_NULL;
+  }
+  if (!frz::pick_geometry(*params, &g) || !frz::small_grid(*params) || g.group != 8) {
+    frz::set_error("frz_wildfire_tile_random_layout: H=%d W=%d A=%d is not a small grid", params->height, params->width,
+                   params->num_agents);
+    return -FRZ_ERR_SHAPE;
+  }
+  FrzWildfireParams folded;
+  frz::Derived derived;
+  frz::fold_configuration(*params, g.group, g.cells_per_lane, &folded, &derived);
+  const frz::SmallRandomLayout layout = frz::small_random_layout(
+      params->height * params->width, params->num_agents, g.group, g.cells_per_lane, derived.spare_lanes_feed_agents != 0);
+  for (int i = 0; i < layout.calls; ++i) {
+    streams[i] = layout.stream[i];
+    for (int j = 0; j < 4; ++j) destinations[4 * i + j] = layout.dest[i][j];
+  }
+  return layout.calls;
+}
+
 int frz_wildfire_refresh(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
                          void* stream) {
   return frz::dispatch(params, io, parallel_envs, frz::kRefresh, stream);

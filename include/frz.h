@@ -367,6 +367,12 @@ typedef struct {
   FrzHostPipeline* pipeline;   /* NULL = per-thread, per-device events kept by the library */
 } FrzHostStep;
 
+/* Which Philox call feeds which draw in the one-thread-per-environment kernel of a small grid (pure host logic, for
+ * tests): returns the number of calls n (<= 24) or -FrzStatus; call i uses streams[i] as its third counter word, its
+ * word j feeds slot destinations[4 i + j]: c = increase / decrease of cell c, H*W + c = spread of cell c,
+ * 2 H*W + 4 a + j = word j of agent a, -1 = unused.  The table restates the word assignment of the group kernel for the
+ * same grid, which is why the two kernels draw identical trajectories. */
+int frz_wildfire_tile_random_layout(const FrzWildfireParams* params, uint32_t* streams, int8_t* destinations);
 int frz_wildfire_step_host(const FrzWildfireParams* params, const FrzWildfireBuffers* io, int32_t parallel_envs,
                            const FrzHostStep* host, void* stream);
 /* How frz_<domain>_step_host cuts a batch: writes bounds[0] = 0 < ... < bounds[n] = parallel_envs (room for

@@ -53,3 +53,47 @@ def test_cyber_uniform_layout():
     assert u_network.shape == (1, 5, 10) and u_agent.shape == (1, 5, 9)
     raw = P._calls(11, np.arange(5), 2, np.array([1], dtype=np.uint32))
     assert np.array_equal(u_network[0, :, 4:8], P.u01(raw[:, 0, :]))
+
+
+def test_tiled_wildfire_kernel_uses_the_group_kernels_word_layout():
+    """frz_wildfire_tile_random_layout (the table the one-thread-per-environment kernel draws from) == the word layout of
+    the group kernel as restated in tests/philox_ref.py, for EVERY small grid (<= 32 cells, <= 8 agents): the two
+    kernels consume the same Philox words for the same events, so the batch size -- which selects the kernel -- never
+    changes a trajectory."""
+    import ctypes
+
+    from free_range_zoo_b200 import _lib
+    from tests import philox_ref as P
+    lib = _lib.library()
+    streams, destinations = (ctypes.c_uint32 * 24)(), (ctypes.c_int8 * 96)()
+    checked = 0
+    for H in range(1, 9):
+        for W in range(1, 33):
+            if H * W > 32:
+                continue
+            for A in range(1, 9):
+                params = _lib.WildfireParams()
+                params.height, params.width, params.num_agents = H, W, A
+                calls = lib.frz_wildfire_tile_random_layout(ctypes.byref(params), streams, destinations)
+                assert calls > 0, (H, W, A, lib.frz_last_error())
+                layout = P.wildfire_layout(H, W, A)
+                assert layout['G'] == 8 and not layout['split']
+                HW = H * W
+                slot = {}  # destination slot -> (stream, word)
+                for i in range(calls):
+                    for j in range(4):
+                        if destinations[4 * i + j] >= 0:
+                            assert destinations[4 * i + j] not in slot
+                            slot[destinations[4 * i + j]] = (streams[i], j)
+                for c in range(HW):
+                    assert slot[c] == tuple(layout['grow'][c]), (H, W, A, c)
+                    assert slot[HW + c] == tuple(layout['spread'][c]), (H, W, A, c)
+                for a in range(A):
+                    for j in range(4):
+                        assert slot[2 * HW + 4 * a + j] == tuple(layout['agent'][a][j]), (H, W, A, a, j)
+                assert len(slot) == 2 * HW + 4 * A
+                checked += 1
+    assert checked > 500
+    params = _lib.WildfireParams()
+    params.height, params.width, params.num_agents = 10, 10, 10
+    assert lib.frz_wildfire_tile_random_layout(ctypes.byref(params), streams, destinations) < 0  # not a small grid
