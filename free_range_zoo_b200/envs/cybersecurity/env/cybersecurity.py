@@ -241,7 +241,6 @@ class raw_env(BatchedAECEnv):
         _lib.check(self._lib.frz_cyber_refresh(ctypes.byref(self._params), ctypes.byref(self._io), self.parallel_envs,
                                                self._stream()), 'frz_cyber_refresh')
 
-
     def _observation_download(self):
         """Host-side observation download (``gather_observations``): every environment always has all N subnetworks as
         tasks, so everything is dense."""

@@ -193,7 +193,6 @@ class raw_env(BatchedAECEnv):
         _lib.check(self._lib.frz_rideshare_refresh(ctypes.byref(self._params), ctypes.byref(self._io),
                                                    self.parallel_envs, self._stream()), 'frz_rideshare_refresh')
 
-
     def _observation_download(self):
         """Host-side observation download (``gather_observations``): self observations and per-driver task counts whole,
         the live rows of the task observations and of every driver's task-mask row packed."""

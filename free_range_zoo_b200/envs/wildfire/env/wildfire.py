@@ -289,7 +289,6 @@ class raw_env(BatchedAECEnv):
         _lib.check(self._lib.frz_wildfire_refresh(ctypes.byref(self._params), ctypes.byref(self._io),
                                                   self.parallel_envs, self._stream()), 'frz_wildfire_refresh')
 
-
     def _observation_download(self):
         """Host-side observation download (``gather_observations``): self observations and per-agent task counts whole,
         the live rows of the task observations and of every agent's action-mask row packed."""
