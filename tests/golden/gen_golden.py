@@ -371,6 +371,17 @@ def main():
     gen_wildfire('wildfire_4x8', presets.wildfire_large, B=10, steps=25, seed=18,
                  preset_kwargs=dict(height=4, width=8, num_agents=8, seed=33))
 
+    # the other cells-per-lane classes of the small-grid kernels (1, 3 and 4 cells per lane of the 8-lane layout, with
+    # and without spare lanes feeding the agents' random words), bad actions shown, one row of 32 cells
+    gen_wildfire('wildfire_2x4', presets.wildfire_large, B=12, steps=20, seed=19,
+                 preset_kwargs=dict(height=2, width=4, num_agents=3, seed=41))
+    gen_wildfire('wildfire_4x5_bad', presets.wildfire_large, B=10, steps=25, seed=51, show_bad_actions=True,
+                 preset_kwargs=dict(height=4, width=5, num_agents=4, seed=32))
+    gen_wildfire('wildfire_5x6', presets.wildfire_large, B=10, steps=25, seed=52,
+                 preset_kwargs=dict(height=5, width=6, num_agents=6, seed=21))
+    gen_wildfire('wildfire_1x32', presets.wildfire_large, B=8, steps=20, seed=53,
+                 preset_kwargs=dict(height=1, width=32, num_agents=5, seed=42))
+
     gen_rideshare('rideshare_profile', presets.rideshare_profile, B=8, steps=20, seed=21)
     gen_rideshare('rideshare_c2', presets.rideshare_c2, B=24, steps=100, seed=22)
     gen_rideshare('rideshare_quirks', presets.rideshare_quirks, B=16, steps=40, seed=23,
@@ -391,6 +402,10 @@ def main():
                   preset_kwargs=dict(drivers=7, rows=24))
     gen_rideshare('rideshare_8drivers', presets.rideshare_synthetic, B=6, steps=25, seed=29,
                   preset_kwargs=dict(drivers=8, rows=40))
+    gen_rideshare('rideshare_6drivers', presets.rideshare_synthetic, B=8, steps=25, seed=30,
+                  preset_kwargs=dict(drivers=6, rows=16))
+    gen_rideshare('rideshare_2drivers', presets.rideshare_synthetic, B=6, steps=25, seed=38, wild=0.2,
+                  preset_kwargs=dict(drivers=2, rows=64))
 
     gen_cyber('cyber_profile', presets.cyber_profile, B=8, steps=20, seed=31)
     gen_cyber('cyber_c3', presets.cyber_c3, B=32, steps=60, seed=32, show_bad_actions=False, partially_observable=True)
