@@ -604,6 +604,10 @@ def run_engine(args):
     packed = recorded.to(torch.int16).pin_memory()
     i16_ms, i16_h2d, i16_d2h, _ = h.host_leg(packed, args.host_chunks or None)
     bytes_ok = int(recorded.max()) <= 127 and int(recorded.min()) >= -128
+    if world > 1:  # every rank must take the same legs (their timings are reduced over the ranks)
+        flag = torch.tensor([int(bytes_ok)], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        bytes_ok = bool(flag.item())
     tiny = recorded.to(torch.int8).pin_memory() if bytes_ok else None
     if tiny is not None:
         i8_ms, i8_h2d, i8_d2h, _ = h.host_leg(tiny, args.host_chunks or None)
